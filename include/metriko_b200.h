@@ -1,0 +1,129 @@
+/* metriko_b200.h -- C ABI of libmetriko_b200.so: the B200 (sm_100a) implementation of the sparse-linear-algebra
+ * hot path of komietty/metriko (N-RoSy field eigen-solve, IGM Poisson solve, iterative-rounding re-solves).
+ *
+ * Conventions: plain pointers and sizes, no C++ / torch types; every entry point returns an int
+ * status (0 = ok, negative = mk_status error; no exceptions cross the ABI -- the C++ shim in
+ * include/metriko_b200/metriko_cuda_shims.hpp rethrows std::runtime_error / returns false as each reference seam
+ * does); the caller owns host buffers, the library owns device buffers inside handles; indices are int32, values
+ * fp64, complex numbers interleaved (re, im) exactly like std::complex<double> / Eigen::SparseMatrix<complex>;
+ * one host thread per context, contexts on different devices are independent. There is NO CPU fallback: every
+ * compute entry point fails with MK_ERR_CUDA when no sm_100a device is usable.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to include/metriko/core/).
+ */
+#ifndef METRIKO_B200_H
+#define METRIKO_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mk_ctx mk_ctx;       /* one per device + stream */
+typedef struct mk_field mk_field;   /* field problem: stencil operator + mass + work vectors */
+typedef struct mk_spd mk_spd;       /* real SPD solver handle (LM inner solver) */
+typedef struct mk_igm mk_igm;       /* IGM problem: A0 = X2F^T X2F, UFull, rounding state */
+
+enum mk_status {
+    MK_OK = 0,
+    MK_ERR_CUDA = -1,        /* CUDA runtime error or no device */
+    MK_ERR_ARG = -2,         /* bad argument */
+    MK_ERR_NOT_CONVERGED = -3, /* inner solve missed the requested residual (result still written) */
+    MK_ERR_NOT_SPD = -4,     /* p^T A p <= 0 met (CHOLMOD "matrix is not positive definite", ss/suitesparse_pdefinite.h:38) */
+    MK_ERR_ROUNDING = -5,    /* post_checking failed ("Rounding has failed!", igm/parameterization_integ.ipp:85) */
+    MK_ERR_INTERNAL = -9
+};
+
+typedef struct mk_solve_opts {
+    double tol;        /* relative residual ||b - A x|| / ||b|| of every inner solve; default 1e-10 */
+    int max_iter;      /* per inner solve; default 100000 */
+    int precond;       /* 0 = none, 1 = smoothed-aggregation multigrid (default) */
+    int use_graph;     /* replay the PCG iteration as a CUDA graph (default 1) */
+} mk_solve_opts;
+
+typedef struct mk_stats {
+    int outer_iterations;     /* inverse-iteration steps or rounding re-solves */
+    int64_t inner_iterations; /* total PCG iterations */
+    int inner_max;            /* max PCG iterations of one solve */
+    double relres_max;        /* worst true relative residual over all inner solves */
+    double lambda;            /* field: Rayleigh quotient at exit */
+    int64_t kernel_launches;  /* kernels launched by the call */
+    double setup_ms, solve_ms;/* host wall clock split (setup = upload + assembly + hierarchy) */
+    int status;               /* mk_status of the worst inner solve */
+} mk_stats;
+
+void mk_default_opts(mk_solve_opts* o);
+
+/* ---- context ---- */
+/* `stream` is a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) or NULL to create a private stream. */
+int mk_ctx_create(int device, void* stream, mk_ctx** out);
+int mk_ctx_destroy(mk_ctx* ctx);
+const char* mk_last_error(mk_ctx* ctx);
+int mk_ctx_sync(mk_ctx* ctx);
+int mk_device_count(void);
+
+/* ---- N-RoSy field: FaceRosyField ctor, vectorfield/face_rosy_field.h:17-44 ---- */
+/* Upload the half-edge arrays connectionLaplacian()/galerkinMassMatrix() read (frf.h:46-84; hmesh/hmesh.h:98-146).
+ * nH = number of halfs, nF = number of faces; closed meshes (README.md:27). */
+int mk_field_create(mk_ctx* ctx, int nF, int nH, int N, const int* face2half, const int* next, const int* twin, const int* face,
+                    const double* heArgOnFace, const double* faceArea, mk_field** out);
+int mk_field_destroy(mk_field* f);
+/* connectionLaplacian() + galerkinMassMatrix() (frf.h:46-84) as one atomic-free per-face kernel. */
+int mk_field_assemble(mk_field* f);
+/* Copy the assembled operator back as CSR (row f: diagonal then the three neighbours) for inspection/tests:
+ * rowptr[nF+1], col[4 nF], val[4 nF] complex interleaved, mass[nF]. */
+int mk_field_get_operator(mk_field* f, int* rowptr, int* col, double* val, double* mass);
+/* solveSmallestEig(L, M, nIter) (solver/sparse_linear_solver.h:29-54): n_iter steps of x = L^{-1}(M u);
+ * x /= sqrt|x^H M x|; u = x, starting from the explicit u0 (the reference's VecXc::Random is unseeded).
+ * u0, x: host, complex interleaved, length nF. */
+int mk_field_solve(mk_field* f, const double* u0, int n_iter, const mk_solve_opts* opts, double* x, mk_stats* stats);
+/* Same, with u0 / x already resident on the device (HBM-resident timing path; pointers are device pointers). */
+int mk_field_solve_dev(mk_field* f, const double* u0_dev, int n_iter, const mk_solve_opts* opts, double* x_dev, mk_stats* stats);
+/* Field decode (frf.h:37-43): field[nF x N] complex interleaved from the last solution. Host output. */
+int mk_field_decode(mk_field* f, double* field);
+/* y = L x on host vectors (tests) and a timed device loop for the roofline (reps launches, returns ms per launch). */
+int mk_field_spmv(mk_field* f, const double* x, double* y);
+int mk_field_spmv_bench(mk_field* f, int reps, int fused_dot, double* ms_per_launch);
+
+/* One-shot drop-in for solveSmallestEig(SprsC& L, SprsC& M, int nIter) on Eigen CSC arrays (sls.h:29): L Hermitian
+ * n x n compressed CSC (outerIndexPtr/innerIndexPtr/valuePtr), M diagonal given as CSC too (only its diagonal is
+ * read, frf.h:78-84). H2D, hierarchy set-up, solve and D2H all inside the call. */
+int mk_solve_smallest_eig_csc(mk_ctx* ctx, int n, const int* L_outer, const int* L_inner, const double* L_values,
+                              const int* M_outer, const int* M_inner, const double* M_values, const double* u0, int n_iter,
+                              const mk_solve_opts* opts, double* x, mk_stats* stats);
+
+/* ---- real SPD solves: the LinearSolver duck type of LMSolver (solver/levenberg_marquardt.h:90,184-189), implemented
+ * in the reference by CholeskyWrapper{factorize, solve} = Eigen::SimplicialLLT (igm/iterative_rounding/iter_rounding.h:14-20) ---- */
+/* factorize(A): A symmetric n x n CSC (= CSR); uploaded and a multigrid hierarchy is built instead of a factor. */
+int mk_spd_factorize(mk_ctx* ctx, int n, const int* outer, const int* inner, const double* values, const mk_solve_opts* opts, mk_spd** out);
+/* solve(rhs, x): x_guess may be NULL (zero start). */
+int mk_spd_solve(mk_spd* s, const double* rhs, const double* x_guess, double* x, mk_stats* stats);
+int mk_spd_destroy(mk_spd* s);
+int mk_spd_spmv_bench(mk_spd* s, int reps, int fused_dot, double* ms_per_launch);
+
+/* ---- IGM: iterative_rounding(...) (igm/iterative_rounding/iter_rounding.h:33-113) for localInjectivity = false ---- */
+/* X2F = (G2 * UFull).pruned() WITHOUT the length factor (iter_rounding_init.h:173), CSR rows = 2 N nF; UFull CSR
+ * (n nR x cols, iter_rounding_init.h:154); F2 = rawF2Vec (parameterization_integ.ipp:30-43). */
+int mk_igm_create(mk_ctx* ctx, int rows, int cols, const int64_t* x2f_ptr, const int* x2f_col, const double* x2f_val,
+                  int ufull_rows, const int64_t* uf_ptr, const int* uf_col, const double* uf_val, const double* F2,
+                  double length, const mk_solve_opts* opts, mk_igm** out);
+int mk_igm_destroy(mk_igm* g);
+/* NaiveIntegration Poisson solve (iter_rounding_init.h:173-212): min ||length X2F x - F2|| s.t. UFull[fixedIdcs] x = fixedVals.
+ * x_small: cols, x0_full: ufull_rows (either may be NULL). */
+int mk_igm_poisson(mk_igm* g, int n_fixed, const int* fixedIdcs, const double* fixedVals, double* x_small, double* x0_full, mk_stats* stats);
+/* The NI closed form + SeamlessIntegration rounding loop (iter_rounding.h:78-112, iter_rounding_loop.h:29-124).
+ * Outputs: fullx[ufull_rows]; fixed_idcs/fixed_vals[n_sing + n_int] in the order dofs were fixed, n_fixed_out their
+ * count; resolve_flags[i] = 1 if fixing entry i triggered a re-solve; tie_flags[i] bit0 = rounding near-tie
+ * (|frac - 0.5| < 1e-6), bit1 = selection near-tie (runner-up distance within 1e-8 and above the 10e-7 skip threshold).
+ * Returns MK_ERR_ROUNDING when post_checking (iter_rounding_loop.h:89-100) fails. */
+int mk_igm_round(mk_igm* g, int n_fixed, const int* fixedIdcs, const double* fixedVals, int n_sing, const int* singularIdcs,
+                 int n_int, const int* integerIdcs, int seamless, int roundSeams, double* fullx, int* fixed_idcs, int* fixed_vals,
+                 int* n_fixed_out, int* resolve_flags, int* tie_flags, mk_stats* stats);
+/* Copy A0 = length^2 X2F^T X2F (assembled on the device) back as CSR for tests: pass NULLs to query nnz. */
+int mk_igm_get_matrix(mk_igm* g, int64_t* nnz, int* rowptr, int* col, double* val);
+int mk_igm_spmv_bench(mk_igm* g, int reps, int fused_dot, double* ms_per_launch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* METRIKO_B200_H */

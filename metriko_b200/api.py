@@ -1,0 +1,244 @@
+"""Host-side mirror of metriko's solver seams above the C-ABI (names and argument meaning follow the reference so the
+parity tests read like calls into metriko itself):
+
+  solveSmallestEig(L, M, nIter, u0)       solver/sparse_linear_solver.h:29      (B1)
+  CholeskyWrapper.factorize / .solve      igm/iterative_rounding/iter_rounding.h:14-20 (B2, LMSolver's LinearSolver)
+  iterative_rounding(...)                 igm/iterative_rounding/iter_rounding.h:33-113 (B4)
+  FaceRosyField                           vectorfield/face_rosy_field.h:17-84   (assembly + solve + decode on device)
+
+Everything computes on the GPU through libmetriko_b200.so; nothing here falls back to the CPU."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import capi
+from .capi import Context, MkError, Stats, as_c128, as_f64, as_i32, default_opts, ptr
+
+
+class FaceRosyField:
+    """FaceRosyField(mesh, N, FieldType::Smoothest) (frf.h:17-44): connectionLaplacian + galerkinMassMatrix are
+    assembled on the device from the half-edge arrays, then solveSmallestEig runs there."""
+
+    def __init__(self, ctx: Context, face2half, next_, twin, face, heArgOnFace, faceArea, N: int = 4):
+        self.ctx = ctx
+        self.N = N
+        self.nF = len(faceArea)
+        self.nH = len(twin)
+        self.h = C.c_void_p()
+        a = [as_i32(face2half), as_i32(next_), as_i32(twin), as_i32(face), as_f64(heArgOnFace), as_f64(faceArea)]
+        ctx.check(ctx.L.mk_field_create(ctx.h, self.nF, self.nH, N, *[ptr(v) for v in a], C.byref(self.h)))
+        ctx.check(ctx.L.mk_field_assemble(self.h))
+        self.stats = None
+
+    def operator(self):
+        """(L, M) as scipy CSR / diagonal, copied back from the device (tests)."""
+        rowptr = np.empty(self.nF + 1, np.int32)
+        col = np.empty(4 * self.nF, np.int32)
+        val = np.empty(4 * self.nF, np.complex128)
+        mass = np.empty(self.nF, np.float64)
+        self.ctx.check(self.ctx.L.mk_field_get_operator(self.h, ptr(rowptr), ptr(col), ptr(val), ptr(mass)))
+        return sp.csr_matrix((val, col, rowptr), shape=(self.nF, self.nF)), mass
+
+    def solveSmallestEig(self, u0, nIter: int = 50, **opts):
+        u0 = as_c128(u0)
+        x = np.empty(self.nF, np.complex128)
+        st = Stats()
+        o = default_opts(**opts)
+        rc = self.ctx.L.mk_field_solve(self.h, ptr(u0), nIter, C.byref(o), ptr(x), C.byref(st))
+        self.stats = st.as_dict()
+        self.ctx.check(rc)
+        return x
+
+    def solve_dev(self, u0_dev_ptr: int, nIter: int = 50, x_dev_ptr: int | None = None, **opts):
+        st = Stats()
+        o = default_opts(**opts)
+        rc = self.ctx.L.mk_field_solve_dev(self.h, C.c_void_p(u0_dev_ptr), nIter, C.byref(o),
+                                           C.c_void_p(x_dev_ptr) if x_dev_ptr else None, C.byref(st))
+        self.stats = st.as_dict()
+        self.ctx.check(rc)
+        return self.stats
+
+    def decode(self):
+        out = np.empty((self.nF, self.N), np.complex128)
+        self.ctx.check(self.ctx.L.mk_field_decode(self.h, ptr(out)))
+        return out
+
+    def spmv(self, x):
+        x = as_c128(x)
+        y = np.empty_like(x)
+        self.ctx.check(self.ctx.L.mk_field_spmv(self.h, ptr(x), ptr(y)))
+        return y
+
+    def spmv_bench(self, reps: int = 50, fused_dot: bool = False) -> float:
+        ms = C.c_double()
+        self.ctx.check(self.ctx.L.mk_field_spmv_bench(self.h, reps, int(fused_dot), C.byref(ms)))
+        return ms.value
+
+    def close(self):
+        if self.h:
+            self.ctx.L.mk_field_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def solveSmallestEig(ctx: Context, L, M, nIter: int = 50, u0=None, return_stats: bool = False, **opts):
+    """Drop-in for `VecXc solveSmallestEig(SprsC& L, SprsC& M, int nIter = 50)` (sls.h:29): L, M scipy sparse
+    (converted to compressed CSC exactly as Eigen holds them). `u0` replaces VecXc::Random (must be given)."""
+    if u0 is None:
+        raise ValueError("u0 must be given explicitly (the reference draws it from an unseeded std::rand)")
+    Lc = sp.csc_matrix(L, dtype=np.complex128)
+    Mc = sp.csc_matrix(M, dtype=np.complex128)
+    Lc.sort_indices()
+    Mc.sort_indices()
+    n = Lc.shape[0]
+    u0 = as_c128(u0)
+    x = np.empty(n, np.complex128)
+    st = Stats()
+    o = default_opts(**opts)
+    a = [as_i32(Lc.indptr), as_i32(Lc.indices), as_c128(Lc.data), as_i32(Mc.indptr), as_i32(Mc.indices), as_c128(Mc.data)]
+    rc = ctx.L.mk_solve_smallest_eig_csc(ctx.h, n, *[ptr(v) for v in a], ptr(u0), nIter, C.byref(o), ptr(x), C.byref(st))
+    ctx.check(rc)
+    return (x, st.as_dict()) if return_stats else x
+
+
+class CholeskyWrapper:
+    """The LinearSolver duck type of LMSolver (lm.h:90): `factorize(A) -> bool`, `solve(rhs, x) -> bool`
+    (ir.h:14-20). The 'factor' is a device-resident operator + multigrid hierarchy; solve is PCG to opts.tol."""
+
+    def __init__(self, ctx: Context, **opts):
+        self.ctx = ctx
+        self.opts = opts
+        self.h = C.c_void_p()
+        self.n = 0
+        self.stats = None
+
+    def factorize(self, A) -> bool:
+        self.close()
+        Ac = sp.csc_matrix(A, dtype=np.float64)
+        Ac.sort_indices()
+        self.n = Ac.shape[0]
+        o = default_opts(**self.opts)
+        rc = self.ctx.L.mk_spd_factorize(self.ctx.h, self.n, ptr(as_i32(Ac.indptr)), ptr(as_i32(Ac.indices)), ptr(as_f64(Ac.data)),
+                                         C.byref(o), C.byref(self.h))
+        return rc == capi.MK_OK
+
+    def solve(self, rhs, x_guess=None):
+        rhs = as_f64(rhs)
+        x = np.empty(self.n, np.float64)
+        g = as_f64(x_guess) if x_guess is not None else None
+        st = Stats()
+        rc = self.ctx.L.mk_spd_solve(self.h, ptr(rhs), ptr(g), ptr(x), C.byref(st))
+        self.stats = st.as_dict()
+        self.ctx.check(rc)
+        return x
+
+    def spmv_bench(self, reps: int = 50, fused_dot: bool = False) -> float:
+        ms = C.c_double()
+        self.ctx.check(self.ctx.L.mk_spd_spmv_bench(self.h, reps, int(fused_dot), C.byref(ms)))
+        return ms.value
+
+    def close(self):
+        if self.h:
+            self.ctx.L.mk_spd_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class IgmProblem:
+    """Device-resident IGM problem (mk_igm): A0 = length^2 X2F^T X2F assembled on the device, UFull, F2."""
+
+    def __init__(self, ctx: Context, X2F, UFull, F2, length: float, **opts):
+        self.ctx = ctx
+        X = sp.csr_matrix(X2F, dtype=np.float64)
+        U = sp.csr_matrix(UFull, dtype=np.float64)
+        X.sort_indices()
+        U.sort_indices()
+        self.rows, self.cols = X.shape
+        self.ufull_rows = U.shape[0]
+        assert U.shape[1] == self.cols
+        self.h = C.c_void_p()
+        o = default_opts(**opts)
+        a = [np.ascontiguousarray(X.indptr, np.int64), as_i32(X.indices), as_f64(X.data),
+             np.ascontiguousarray(U.indptr, np.int64), as_i32(U.indices), as_f64(U.data), as_f64(F2)]
+        ctx.check(ctx.L.mk_igm_create(ctx.h, self.rows, self.cols, ptr(a[0]), ptr(a[1]), ptr(a[2]), self.ufull_rows, ptr(a[3]), ptr(a[4]),
+                                      ptr(a[5]), ptr(a[6]), float(length), C.byref(o), C.byref(self.h)))
+        self.stats = None
+
+    def matrix(self):
+        nnz = C.c_int64()
+        self.ctx.check(self.ctx.L.mk_igm_get_matrix(self.h, C.byref(nnz), None, None, None))
+        rowptr = np.empty(self.cols + 1, np.int32)
+        col = np.empty(nnz.value, np.int32)
+        val = np.empty(nnz.value, np.float64)
+        self.ctx.check(self.ctx.L.mk_igm_get_matrix(self.h, C.byref(nnz), ptr(rowptr), ptr(col), ptr(val)))
+        return sp.csr_matrix((val, col, rowptr), shape=(self.cols, self.cols))
+
+    def poisson(self, fixedIdcs, fixedVals):
+        fi, fv = as_i32(fixedIdcs), as_f64(fixedVals)
+        xs = np.empty(self.cols, np.float64)
+        xf = np.empty(self.ufull_rows, np.float64)
+        st = Stats()
+        rc = self.ctx.L.mk_igm_poisson(self.h, len(fi), ptr(fi), ptr(fv), ptr(xs), ptr(xf), C.byref(st))
+        self.stats = st.as_dict()
+        self.ctx.check(rc)
+        return xs, xf
+
+    def round(self, fixedIdcs, fixedVals, singularIdcs, integerIdcs, seamless=True, roundSeams=False):
+        fi, fv = as_i32(fixedIdcs), as_f64(fixedVals)
+        si, ii = as_i32(singularIdcs), as_i32(integerIdcs)
+        m = len(si) + len(ii)
+        fullx = np.empty(self.ufull_rows, np.float64)
+        out_i = np.zeros(max(m, 1), np.int32)
+        out_v = np.zeros(max(m, 1), np.int32)
+        resolve = np.zeros(max(m, 1), np.int32)
+        ties = np.zeros(max(m, 1), np.int32)
+        nfix = C.c_int()
+        st = Stats()
+        rc = self.ctx.L.mk_igm_round(self.h, len(fi), ptr(fi), ptr(fv), len(si), ptr(si), len(ii), ptr(ii), int(seamless), int(roundSeams),
+                                     ptr(fullx), ptr(out_i), ptr(out_v), C.byref(nfix), ptr(resolve), ptr(ties), C.byref(st))
+        self.stats = st.as_dict()
+        self.ctx.check(rc, allow=(-5,))
+        k = nfix.value
+        return dict(success=(rc == capi.MK_OK), fullx=fullx, fixedIdcs=out_i[:k].tolist(), fixedVals=out_v[:k].tolist(),
+                    resolve_flags=resolve[:k].tolist(), tie_flags=ties[:k].tolist(), n_solves=int(resolve[:k].sum()), stats=self.stats)
+
+    def spmv_bench(self, reps: int = 50, fused_dot: bool = False) -> float:
+        ms = C.c_double()
+        self.ctx.check(self.ctx.L.mk_igm_spmv_bench(self.h, reps, int(fused_dot), C.byref(ms)))
+        return ms.value
+
+    def close(self):
+        if self.h:
+            self.ctx.L.mk_igm_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def iterative_rounding(ctx: Context, fixedIdcs, fixedVals, singularIdcs, integerIdcs, length, UFull, X2F, N, n, nF, seamless,
+                       roundSeams, intrinsicField, **opts):
+    """Drop-in for `iterative_rounding(...)` (ir.h:33-51) with localInjectivity = false. Differences from the reference
+    signature: UFull and X2F = (G2 UFull).pruned() are passed in (the host builds them, ir_init.h:98-173) instead of
+    Cfull and G2; the result dict carries fullx plus the rounding trace instead of an out-parameter."""
+    prob = IgmProblem(ctx, X2F, UFull, intrinsicField, length, **opts)
+    try:
+        return prob.round(fixedIdcs, fixedVals, singularIdcs, integerIdcs, seamless, roundSeams)
+    finally:
+        prob.close()

@@ -1,0 +1,75 @@
+"""In-tree builds of the native libraries (no JIT cache: the .so files travel with the repo snapshot).
+
+  libmetriko_b200.so     CUDA kernels + solver drivers + the C-ABI (include/metriko_b200.h), sm_100a only
+  libmetriko_hostglue.so host-side restatement of the reference's unchanged bookkeeping stages (CPU only)
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+HOSTGLUE = os.path.join(PKG, "hostglue")
+LIB_CUDA = os.path.join(PKG, "libmetriko_b200.so")
+LIB_HOST = os.path.join(HOSTGLUE, "libmetriko_hostglue.so")
+
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+CUDA_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp", "-Xcompiler", "-O3",
+]
+
+
+def _newer(target: str, sources: list[str]) -> bool:
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(s) <= t for s in sources)
+
+
+def _sources(d: str, exts: tuple[str, ...]) -> list[str]:
+    out = []
+    for base, _, files in os.walk(d):
+        for f in sorted(files):
+            if f.endswith(exts):
+                out.append(os.path.join(base, f))
+    return out
+
+
+def build_hostglue(force: bool = False, verbose: bool = False) -> str:
+    deps = _sources(HOSTGLUE, (".cpp", ".hpp"))
+    if not force and _newer(LIB_HOST, deps):
+        return LIB_HOST
+    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", LIB_HOST,
+           os.path.join(HOSTGLUE, "hostglue_capi.cpp")]
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.run(cmd, check=True)
+    return LIB_HOST
+
+
+def build_cuda(force: bool = False, verbose: bool = False) -> str:
+    deps = _sources(CSRC, (".cu", ".cuh", ".h", ".hpp", ".cpp")) + _sources(os.path.join(ROOT, "include"), (".h",))
+    if not force and _newer(LIB_CUDA, deps):
+        return LIB_CUDA
+    srcs = _sources(CSRC, (".cu",))
+    cmd = [NVCC, *CUDA_FLAGS, "-shared", "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", LIB_CUDA, *srcs,
+           "-lcudart", "-lgomp"]
+    if verbose:
+        cmd.insert(1, "-Xptxas")
+        cmd.insert(2, "-v")
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.run(cmd, check=True)
+    return LIB_CUDA
+
+
+def build_all(force: bool = False, verbose: bool = False) -> None:
+    build_hostglue(force, verbose)
+    build_cuda(force, verbose)
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv, verbose="-v" in sys.argv)

@@ -1,0 +1,146 @@
+"""ctypes binding of libmetriko_b200.so (include/metriko_b200.h). Thin: every function maps 1:1 to a C-ABI entry
+point; numpy arrays are passed as plain pointers. There is no CPU fallback -- loading fails loudly when the CUDA
+library has not been built, and every compute call fails when no sm_100a device is present."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmetriko_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "metriko_b200.h")
+
+MK_OK = 0
+STATUS = {0: "MK_OK", -1: "MK_ERR_CUDA", -2: "MK_ERR_ARG", -3: "MK_ERR_NOT_CONVERGED", -4: "MK_ERR_NOT_SPD",
+          -5: "MK_ERR_ROUNDING", -9: "MK_ERR_INTERNAL"}
+
+
+class MkError(RuntimeError):
+    def __init__(self, status: int, msg: str = ""):
+        self.status = status
+        super().__init__(f"{STATUS.get(status, status)}: {msg}")
+
+
+class SolveOpts(C.Structure):
+    _fields_ = [("tol", C.c_double), ("max_iter", C.c_int), ("precond", C.c_int), ("use_graph", C.c_int)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("outer_iterations", C.c_int), ("inner_iterations", C.c_int64), ("inner_max", C.c_int),
+                ("relres_max", C.c_double), ("lambda_", C.c_double), ("kernel_launches", C.c_int64),
+                ("setup_ms", C.c_double), ("solve_ms", C.c_double), ("status", C.c_int)]
+
+    def as_dict(self):
+        return dict(outer_iterations=self.outer_iterations, inner_iterations=self.inner_iterations, inner_max=self.inner_max,
+                    relres_max=self.relres_max, lambda_=self.lambda_, kernel_launches=self.kernel_launches,
+                    setup_ms=self.setup_ms, solve_ms=self.solve_ms, status=self.status)
+
+
+def declared_symbols() -> list[str]:
+    """Every entry point include/metriko_b200.h declares (used by the CPU test that the library exports them all)."""
+    src = open(HEADER_PATH).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mk_[a-z0-9_]+)\s*\(", src)))
+
+
+_LIB = None
+
+
+def lib() -> C.CDLL:
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no CPU fallback for the CUDA path)")
+        L = C.CDLL(LIB_PATH)
+        vp, ip, dp, i64p = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_int64)
+        L.mk_default_opts.argtypes = [C.POINTER(SolveOpts)]
+        L.mk_default_opts.restype = None
+        L.mk_device_count.restype = C.c_int
+        L.mk_ctx_create.argtypes = [C.c_int, vp, C.POINTER(vp)]
+        L.mk_ctx_destroy.argtypes = [vp]
+        L.mk_last_error.argtypes = [vp]
+        L.mk_last_error.restype = C.c_char_p
+        L.mk_ctx_sync.argtypes = [vp]
+        L.mk_field_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]
+        L.mk_field_destroy.argtypes = [vp]
+        L.mk_field_assemble.argtypes = [vp]
+        L.mk_field_get_operator.argtypes = [vp, vp, vp, vp, vp]
+        L.mk_field_solve.argtypes = [vp, vp, C.c_int, C.POINTER(SolveOpts), vp, C.POINTER(Stats)]
+        L.mk_field_solve_dev.argtypes = [vp, vp, C.c_int, C.POINTER(SolveOpts), vp, C.POINTER(Stats)]
+        L.mk_field_decode.argtypes = [vp, vp]
+        L.mk_field_spmv.argtypes = [vp, vp, vp]
+        L.mk_field_spmv_bench.argtypes = [vp, C.c_int, C.c_int, dp]
+        L.mk_solve_smallest_eig_csc.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.POINTER(SolveOpts), vp, C.POINTER(Stats)]
+        L.mk_spd_factorize.argtypes = [vp, C.c_int, vp, vp, vp, C.POINTER(SolveOpts), C.POINTER(vp)]
+        L.mk_spd_solve.argtypes = [vp, vp, vp, vp, C.POINTER(Stats)]
+        L.mk_spd_destroy.argtypes = [vp]
+        L.mk_spd_spmv_bench.argtypes = [vp, C.c_int, C.c_int, dp]
+        L.mk_igm_create.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp, C.c_double, C.POINTER(SolveOpts), C.POINTER(vp)]
+        L.mk_igm_destroy.argtypes = [vp]
+        L.mk_igm_poisson.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.POINTER(Stats)]
+        L.mk_igm_round.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp, ip, vp, vp, C.POINTER(Stats)]
+        L.mk_igm_get_matrix.argtypes = [vp, i64p, vp, vp, vp]
+        L.mk_igm_spmv_bench.argtypes = [vp, C.c_int, C.c_int, dp]
+        _LIB = L
+    return _LIB
+
+
+def ptr(a: np.ndarray | None):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def default_opts(**kw) -> SolveOpts:
+    o = SolveOpts()
+    lib().mk_default_opts(C.byref(o))
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+def as_i32(a):
+    return np.ascontiguousarray(a, np.int32)
+
+
+def as_f64(a):
+    return np.ascontiguousarray(a, np.float64)
+
+
+def as_c128(a):
+    return np.ascontiguousarray(a, np.complex128)
+
+
+class Context:
+    """mk_ctx: one device + stream. Pass `stream` (a raw cudaStream_t int) to run on e.g. torch's current stream."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self.L = lib()
+        self.h = C.c_void_p()
+        rc = self.L.mk_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(self.h))
+        if rc != MK_OK:
+            raise MkError(rc, f"mk_ctx_create(device={device}) -- a B200 (sm_100a) device is required; there is no CPU fallback")
+        self.device = device
+
+    def check(self, rc: int, allow=()):
+        if rc != MK_OK and rc not in allow:
+            raise MkError(rc, self.L.mk_last_error(self.h).decode())
+        return rc
+
+    def sync(self):
+        self.check(self.L.mk_ctx_sync(self.h))
+
+    def close(self):
+        if self.h:
+            self.L.mk_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,464 @@
+// Smoothed-aggregation algebraic multigrid used as the PCG preconditioner. It stands where the reference has a sparse
+// direct factorisation (Eigen::SparseLU sls.h:42-43 / CHOLMOD LDL^T ss/suitesparse_pdefinite.h:26-41 /
+// Eigen::SimplicialLLT ir.h:14-20): plain CG needs O(sqrt(kappa)) ~ thousands of iterations on these operators
+// (kappa grows with the face count), the V-cycle keeps the count nearly mesh-independent while every
+// piece of it stays an HBM-bound SpMV / fused vector kernel.
+//
+// Hierarchy set-up (aggregation, prolongator smoothing, Galerkin products) runs once per operator on the host with
+// OpenMP; the V-cycle runs on the device (Chebyshev smoothing, explicit R = P^H, dense inverse on the coarsest level).
+//
+// Tentative prolongator:
+//   * complex connection Laplacian: there is no global near-kernel vector, but locally parallel fields are low energy,
+//     so each aggregate transports a unit value from its root along the matrix' own connection phases
+//     (value_j = -a_ji/|a_ji| value_i), recursively on every level;
+//   * real IGM operator: a caller-supplied near-kernel candidate (smoothed constants), standard SA.
+#pragma once
+#include <complex>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "csr.cuh"
+#include "hostcsr.hpp"
+#include "solver.cuh"
+
+namespace mk {
+
+template <class T> struct HostScalar;
+template <> struct HostScalar<double> { using type = double; };
+template <> struct HostScalar<cdouble> { using type = std::complex<double>; };
+
+struct AmgParams {
+    double theta = 0.0;        // strength threshold (0: every off-diagonal is strong)
+    int coarse_max = 300;      // stop coarsening below this many rows (dense inverse there)
+    int max_levels = 14;
+    int cheb_degree = 2;       // SpMVs per pre- and per post-smoothing
+    double cheb_ratio = 8.0;   // smoother targets [lmax / ratio, lmax] of D^{-1} A
+    double omega_scale = 4.0 / 3.0;  // prolongator smoothing omega = omega_scale / rho(D^{-1}A)
+};
+
+inline AmgParams amg_params_from_env() {
+    AmgParams p;
+    if (const char* e = getenv("MK_AMG_DEG")) p.cheb_degree = atoi(e);
+    if (const char* e = getenv("MK_AMG_RATIO")) p.cheb_ratio = atof(e);
+    if (const char* e = getenv("MK_AMG_THETA")) p.theta = atof(e);
+    if (const char* e = getenv("MK_AMG_COARSE")) p.coarse_max = atoi(e);
+    if (const char* e = getenv("MK_AMG_OMEGA")) p.omega_scale = atof(e);
+    return p;
+}
+
+template <class S>
+struct AmgHostLevel {
+    HostCsr<S> A, P, R;
+    std::vector<S> dinv;
+    double lmax = 2.0;
+};
+
+// ---- host set-up ---------------------------------------------------------------------------------
+
+template <class S>
+inline double estimate_rho_dinvA(const HostCsr<S>& A, const std::vector<S>& dinv, int iters = 12) {
+    const int n = A.rows;
+    std::vector<S> v(n), w;
+    for (int i = 0; i < n; i++) v[i] = S(std::sin(1.0 + 0.7 * i) + 0.3);
+    double rho = 1.0;
+    for (int it = 0; it < iters; it++) {
+        matvec(A, v, w);
+        double nw = 0, nv = 0;
+#pragma omp parallel for reduction(+ : nw, nv)
+        for (int i = 0; i < n; i++) {
+            w[i] = dinv[i] * w[i];
+            nw += std::norm(w[i]);
+            nv += std::norm(v[i]);
+        }
+        rho = std::sqrt(nw / nv);
+        const double s = 1.0 / std::sqrt(nw);
+#pragma omp parallel for
+        for (int i = 0; i < n; i++) v[i] = w[i] * s;
+    }
+    return rho;
+}
+
+template <class S>
+inline S unit_phase(S v) {
+    double a = std::abs(v);
+    return a > 0 ? v / a : S(1);
+}
+
+// Greedy root-plus-neighbours aggregation (Vanek). Returns the aggregate id per node and the tentative value per node.
+template <class S>
+inline int aggregate(const HostCsr<S>& A, double theta, const std::vector<S>* cand, std::vector<int>& agg, std::vector<S>& tval) {
+    const int n = A.rows;
+    std::vector<double> dabs(n, 0.0);
+    for (int i = 0; i < n; i++)
+        for (int k = A.ptr[i]; k < A.ptr[i + 1]; k++)
+            if (A.col[k] == i) dabs[i] = std::abs(A.val[k]);
+    auto strong = [&](int i, int k) {
+        const int j = A.col[k];
+        if (j == i) return false;
+        const double a = std::abs(A.val[k]);
+        return a > 0 && a * a >= theta * theta * dabs[i] * dabs[j];
+    };
+    agg.assign(n, -1);
+    tval.assign(n, S(0));
+    int nagg = 0;
+    // pass 1: roots whose whole strong neighbourhood is free
+    for (int i = 0; i < n; i++) {
+        if (agg[i] != -1) continue;
+        bool ok = true, any = false;
+        for (int k = A.ptr[i]; k < A.ptr[i + 1] && ok; k++)
+            if (strong(i, k)) { any = true; if (agg[A.col[k]] != -1) ok = false; }
+        if (!ok || !any) continue;
+        agg[i] = nagg;
+        tval[i] = S(1);
+        for (int k = A.ptr[i]; k < A.ptr[i + 1]; k++)
+            if (strong(i, k)) {
+                const int j = A.col[k];
+                agg[j] = nagg;
+                tval[j] = unit_phase(S(-1) * hconj(A.val[k]));  // -a_ji = -conj(a_ij) (Hermitian): transport root -> j
+            }
+        nagg++;
+    }
+    // pass 2: attach the rest to the strongest neighbouring pass-1 aggregate
+    std::vector<int> agg1 = agg;
+    for (int i = 0; i < n; i++) {
+        if (agg[i] != -1) continue;
+        double best = -1;
+        int bk = -1;
+        for (int k = A.ptr[i]; k < A.ptr[i + 1]; k++)
+            if (strong(i, k) && agg1[A.col[k]] != -1 && std::abs(A.val[k]) > best) { best = std::abs(A.val[k]); bk = k; }
+        if (bk >= 0) {
+            const int j = A.col[bk];
+            agg[i] = agg1[j];
+            tval[i] = unit_phase(S(-1) * A.val[bk]) * tval[j];  // value_i = -a_ij/|a_ij| value_j
+        }
+    }
+    // pass 3: leftovers (isolated or surrounded by pass-2 nodes) form their own aggregates
+    for (int i = 0; i < n; i++) {
+        if (agg[i] != -1) continue;
+        agg[i] = nagg;
+        tval[i] = S(1);
+        for (int k = A.ptr[i]; k < A.ptr[i + 1]; k++)
+            if (strong(i, k) && agg[A.col[k]] == -1) {
+                const int j = A.col[k];
+                agg[j] = nagg;
+                tval[j] = unit_phase(S(-1) * hconj(A.val[k]));
+            }
+        nagg++;
+    }
+    if (cand) tval = *cand;  // global-candidate mode: tentative values are the candidate itself
+    return nagg;
+}
+
+template <class S>
+inline std::vector<AmgHostLevel<S>> build_hierarchy(HostCsr<S> A, std::vector<S> cand, bool use_cand, const AmgParams& prm) {
+    std::vector<AmgHostLevel<S>> lv;
+    while (true) {
+        AmgHostLevel<S> L;
+        L.A = std::move(A);
+        const int n = L.A.rows;
+        std::vector<S> d = diagonal(L.A);
+        L.dinv.resize(n);
+        for (int i = 0; i < n; i++) L.dinv[i] = std::abs(d[i]) > 0 ? S(1) / d[i] : S(1);
+        L.lmax = 1.1 * estimate_rho_dinvA(L.A, L.dinv);
+        if (n <= prm.coarse_max || (int)lv.size() + 1 >= prm.max_levels) { lv.push_back(std::move(L)); break; }
+        std::vector<int> agg;
+        std::vector<S> tv;
+        const int nc = aggregate(L.A, prm.theta, use_cand ? &cand : nullptr, agg, tv);
+        if (nc >= n * 0.8 || nc == 0) { lv.push_back(std::move(L)); break; }  // stagnation: stop here
+        // normalise the tentative columns; the column norms are the coarse candidate
+        std::vector<double> nrm(nc, 0.0);
+        for (int i = 0; i < n; i++) nrm[agg[i]] += std::norm(tv[i]);
+        std::vector<S> ccand(nc);
+        for (int a = 0; a < nc; a++) { nrm[a] = std::sqrt(nrm[a]); ccand[a] = S(nrm[a]); }
+        HostCsr<S> T;
+        T.rows = n;
+        T.cols = nc;
+        T.ptr.resize(n + 1);
+        T.col.resize(n);
+        T.val.resize(n);
+        for (int i = 0; i < n; i++) {
+            T.ptr[i] = i;
+            T.col[i] = agg[i];
+            T.val[i] = nrm[agg[i]] > 0 ? tv[i] / nrm[agg[i]] : S(0);
+        }
+        T.ptr[n] = n;
+        // P = (I - omega D^{-1} A) T
+        HostCsr<S> AT = matmul(L.A, T);
+        const double omega = prm.omega_scale / (L.lmax / 1.1);
+        {
+            // merge T (one entry per row) into -omega dinv AT
+            HostCsr<S>& P = L.P;
+            P.rows = n;
+            P.cols = nc;
+            P.ptr.assign(n + 1, 0);
+            P.col.reserve(AT.col.size() + n);
+            P.val.reserve(AT.col.size() + n);
+            for (int i = 0; i < n; i++) {
+                bool placed = false;
+                for (int k = AT.ptr[i]; k < AT.ptr[i + 1]; k++) {
+                    int c = AT.col[k];
+                    S v = S(-omega) * L.dinv[i] * AT.val[k];
+                    if (!placed && T.col[i] < c) { P.col.push_back(T.col[i]); P.val.push_back(T.val[i]); placed = true; }
+                    if (c == T.col[i]) { v += T.val[i]; placed = true; }
+                    P.col.push_back(c);
+                    P.val.push_back(v);
+                }
+                if (!placed) { P.col.push_back(T.col[i]); P.val.push_back(T.val[i]); }
+                P.ptr[i + 1] = (int)P.col.size();
+            }
+        }
+        L.R = transpose(L.P, true);
+        HostCsr<S> AP = matmul(L.A, L.P);
+        A = matmul(L.R, AP);
+        cand = std::move(ccand);
+        lv.push_back(std::move(L));
+    }
+    return lv;
+}
+
+// dense inverse of the coarsest operator (Gauss-Jordan with partial pivoting), row-major n x n
+template <class S>
+inline std::vector<S> dense_inverse(const HostCsr<S>& A) {
+    const int n = A.rows;
+    std::vector<S> M((size_t)n * n, S(0)), I((size_t)n * n, S(0));
+    for (int i = 0; i < n; i++) {
+        for (int k = A.ptr[i]; k < A.ptr[i + 1]; k++) M[(size_t)i * n + A.col[k]] += A.val[k];
+        I[(size_t)i * n + i] = S(1);
+    }
+    for (int c = 0; c < n; c++) {
+        int p = c;
+        for (int r = c + 1; r < n; r++)
+            if (std::abs(M[(size_t)r * n + c]) > std::abs(M[(size_t)p * n + c])) p = r;
+        if (std::abs(M[(size_t)p * n + c]) == 0) throw std::runtime_error("amg: singular coarsest operator");
+        if (p != c)
+            for (int j = 0; j < n; j++) { std::swap(M[(size_t)p * n + j], M[(size_t)c * n + j]); std::swap(I[(size_t)p * n + j], I[(size_t)c * n + j]); }
+        const S inv = S(1) / M[(size_t)c * n + c];
+        for (int j = 0; j < n; j++) { M[(size_t)c * n + j] *= inv; I[(size_t)c * n + j] *= inv; }
+#pragma omp parallel for schedule(static)
+        for (int r = 0; r < n; r++) {
+            if (r == c) continue;
+            const S f = M[(size_t)r * n + c];
+            if (f == S(0)) continue;
+            for (int j = 0; j < n; j++) { M[(size_t)r * n + j] -= f * M[(size_t)c * n + j]; I[(size_t)r * n + j] -= f * I[(size_t)c * n + j]; }
+        }
+    }
+    return I;
+}
+
+// ---- device V-cycle ------------------------------------------------------------------------------
+
+// r = b (or b - q) ; d = inv_theta * dinv .* r ; x untouched (first Chebyshev step overwrites it)
+template <class T>
+__global__ void __launch_bounds__(kThreads) k_cheb_init(int n, const T* __restrict__ b, const T* __restrict__ q, const T* __restrict__ dinv,
+                                                        T* __restrict__ r, T* __restrict__ d, double inv_theta, const PcgState* st) {
+    if (st && st->done) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        T ri = ld_ro(b + i);
+        if (q) ri = ri - ld_ro(q + i);
+        st_rw(r + i, ri);
+        st_rw(d + i, ST<T>::scale(inv_theta, ld_ro(dinv + i) * ri));
+    }
+}
+
+// x (+)= d ; r -= q ; d = c1 d + c2 dinv .* r      (one Chebyshev step after q = A d)
+template <class T>
+__global__ void __launch_bounds__(kThreads) k_cheb_step(int n, const T* __restrict__ q, const T* __restrict__ dinv, T* __restrict__ r,
+                                                        T* __restrict__ x, T* __restrict__ d, double c1, double c2, int first,
+                                                        const PcgState* st) {
+    if (st && st->done) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        T di = ld_rw(d + i);
+        T xi = first ? di : ld_rw(x + i) + di;
+        T ri = ld_rw(r + i) - ld_ro(q + i);
+        st_rw(x + i, xi);
+        st_rw(r + i, ri);
+        st_rw(d + i, ST<T>::scale(c1, di) + ST<T>::scale(c2, ld_ro(dinv + i) * ri));
+    }
+}
+
+// x = Ainv b for the dense coarsest level: one warp per row
+template <class T>
+__global__ void __launch_bounds__(kThreads) k_dense_matvec(int n, const T* __restrict__ Ainv, const T* __restrict__ b, T* __restrict__ x,
+                                                           const PcgState* st) {
+    if (st && st->done) return;
+    const int lane = threadIdx.x & 31;
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= n) return;
+    T acc = ST<T>::zero();
+    for (int j = lane; j < n; j += 32) acc = ST<T>::fma_(ld_ro(Ainv + (size_t)row * n + j), ld_ro(b + j), acc);
+    acc = group_sum<T>(acc, 32);
+    if (lane == 0) st_rw(x + row, acc);
+}
+
+// y (+)= A x, G lanes per row, no reduction; honours the done flag (graph replay)
+template <class T, int G>
+__global__ void __launch_bounds__(kThreads) k_spmv_plain(int n, const int* __restrict__ ptr, const int* __restrict__ col, const T* __restrict__ val,
+                                                         const T* __restrict__ x, T* __restrict__ y, int accumulate, const PcgState* st) {
+    if (st && st->done) return;
+    const int gl = threadIdx.x & (G - 1);
+    const int rows_per_pass = (gridDim.x * blockDim.x) / G;
+    for (int base = (blockIdx.x * blockDim.x + (threadIdx.x & ~31)) / G; base < n; base += rows_per_pass) {
+        const int row = base + ((threadIdx.x & 31) / G);
+        T acc = ST<T>::zero();
+        if (row < n) {
+            const int b = ptr[row], e = ptr[row + 1];
+            for (int k = b + gl; k < e; k += G) acc = ST<T>::fma_(ld_ro(val + k), ld_ro(x + col[k]), acc);
+        }
+        acc = group_sum<T>(acc, G);
+        if (gl == 0 && row < n) {
+            if (accumulate) acc = acc + ld_rw(y + row);
+            st_rw(y + row, acc);
+        }
+    }
+}
+
+template <class T>
+inline void spmv_plain(const DeviceCsr<T>& A, const T* x, T* y, bool accumulate, const PcgState* st, cudaStream_t s) {
+    const int grid = stream_grid((int64_t)A.rows * A.group, kThreads, 16);
+    switch (A.group) {
+        case 2: k_spmv_plain<T, 2><<<grid, kThreads, 0, s>>>(A.rows, A.ptr.p, A.col.p, A.val.p, x, y, accumulate, st); break;
+        case 4: k_spmv_plain<T, 4><<<grid, kThreads, 0, s>>>(A.rows, A.ptr.p, A.col.p, A.val.p, x, y, accumulate, st); break;
+        case 8: k_spmv_plain<T, 8><<<grid, kThreads, 0, s>>>(A.rows, A.ptr.p, A.col.p, A.val.p, x, y, accumulate, st); break;
+        case 16: k_spmv_plain<T, 16><<<grid, kThreads, 0, s>>>(A.rows, A.ptr.p, A.col.p, A.val.p, x, y, accumulate, st); break;
+        default: k_spmv_plain<T, 32><<<grid, kThreads, 0, s>>>(A.rows, A.ptr.p, A.col.p, A.val.p, x, y, accumulate, st); break;
+    }
+    MK_CHECK_LAUNCH();
+}
+
+template <class T>
+struct AmgLevelDev {
+    int n = 0;
+    DeviceCsr<T> A;  // unused on level 0 when an external fine operator is given
+    DeviceCsr<T> P, R;
+    DevBuf<T> dinv, x, b, r, d, q;
+    double lmax = 2.0;
+};
+
+template <class T>
+struct AmgPrecond : Precond<T> {
+    using S = typename HostScalar<T>::type;
+    AmgParams prm;
+    std::vector<AmgLevelDev<T>> lv;
+    LinOp<T>* fine_op = nullptr;  // level-0 operator (e.g. the face stencil); falls back to lv[0].A
+    DevBuf<T> coarse_inv;
+    int coarse_n = 0;
+    bool coarse_dense = false;
+    double op_complexity = 0, grid_complexity = 0;
+    ReduceWs dummy_ws{nullptr, nullptr};
+
+    void apply_A(int l, const T* x, T* y, const PcgState* st, cudaStream_t s) {
+        if (l == 0 && fine_op) fine_op->apply(x, y, const_cast<PcgState*>(st), dummy_ws, s, false);
+        else spmv_plain(lv[l].A, x, y, false, st, s);
+    }
+
+    void smooth(int l, const T* b, T* x, bool zero_guess, const PcgState* st, cudaStream_t s) {
+        AmgLevelDev<T>& L = lv[l];
+        const int grid = stream_grid(L.n);
+        const double lmax = L.lmax, lmin = L.lmax / prm.cheb_ratio;
+        const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
+        double rho = 1.0 / sigma;
+        if (zero_guess) {
+            k_cheb_init<T><<<grid, kThreads, 0, s>>>(L.n, b, (const T*)nullptr, L.dinv.p, L.r.p, L.d.p, 1.0 / theta, st);
+        } else {
+            apply_A(l, x, L.q.p, st, s);
+            k_cheb_init<T><<<grid, kThreads, 0, s>>>(L.n, b, L.q.p, L.dinv.p, L.r.p, L.d.p, 1.0 / theta, st);
+        }
+        for (int k = 0; k < prm.cheb_degree; k++) {
+            apply_A(l, L.d.p, L.q.p, st, s);
+            const double rho1 = 1.0 / (2.0 * sigma - rho);
+            k_cheb_step<T><<<grid, kThreads, 0, s>>>(L.n, L.q.p, L.dinv.p, L.r.p, x, L.d.p, rho1 * rho, 2.0 * rho1 / delta,
+                                                    (zero_guess && k == 0) ? 1 : 0, st);
+            rho = rho1;
+        }
+        MK_CHECK_LAUNCH();
+    }
+
+    // x_l = V(b_l); on return lv[l].r holds nothing the caller may rely on
+    void vcycle(int l, const T* b, T* x, const PcgState* st, cudaStream_t s) {
+        AmgLevelDev<T>& L = lv[l];
+        if (l == (int)lv.size() - 1) {
+            if (coarse_dense) {
+                k_dense_matvec<T><<<(L.n * 32 + kThreads - 1) / kThreads, kThreads, 0, s>>>(L.n, coarse_inv.p, b, x, st);
+                MK_CHECK_LAUNCH();
+            } else {
+                const int save = prm.cheb_degree;
+                prm.cheb_degree = 8;
+                smooth(l, b, x, true, st, s);
+                prm.cheb_degree = save;
+            }
+            return;
+        }
+        smooth(l, b, x, true, st, s);  // leaves r = b - A x in L.r
+        AmgLevelDev<T>& C = lv[l + 1];
+        spmv_plain(L.R, L.r.p, C.b.p, false, st, s);
+        vcycle(l + 1, C.b.p, C.x.p, st, s);
+        spmv_plain(L.P, C.x.p, x, true, st, s);
+        smooth(l, b, x, false, st, s);
+    }
+
+    void apply(const T* r, T* z, const PcgState* st, cudaStream_t s) override { vcycle(0, r, z, st, s); }
+
+    int launches_per_apply() const override {
+        const int nl = (int)lv.size();
+        const int per = 5 + 4 * prm.cheb_degree;
+        return (nl - 1) * per + (coarse_dense ? 1 : 17);
+    }
+};
+
+template <class T>
+inline void upload_host_csr(DeviceCsr<T>& D, const HostCsr<typename HostScalar<T>::type>& H, cudaStream_t s) {
+    using S = typename HostScalar<T>::type;
+    static_assert(sizeof(S) == sizeof(T), "layout");
+    std::vector<T> v(H.val.size());
+    std::memcpy(v.data(), H.val.data(), H.val.size() * sizeof(T));
+    upload_csr<T>(D, H.rows, H.cols, H.ptr, H.col, v, s);
+}
+
+// Builds the hierarchy for A (host CSR) and uploads it. `fine_op` non-null: level 0 applies that operator instead of a
+// CSR copy of A (A is still needed on the host for the Galerkin products).
+template <class T>
+inline std::unique_ptr<AmgPrecond<T>> build_amg(cudaStream_t s, HostCsr<typename HostScalar<T>::type> A,
+                                                std::vector<typename HostScalar<T>::type> cand, bool use_cand, LinOp<T>* fine_op,
+                                                const AmgParams& prm) {
+    using S = typename HostScalar<T>::type;
+    auto amg = std::make_unique<AmgPrecond<T>>();
+    amg->prm = prm;
+    amg->fine_op = fine_op;
+    const double nnz0 = (double)A.nnz(), n0 = (double)A.rows;
+    std::vector<AmgHostLevel<S>> H = build_hierarchy<S>(std::move(A), std::move(cand), use_cand, prm);
+    amg->lv.resize(H.size());
+    double nnz_sum = 0, n_sum = 0;
+    for (size_t l = 0; l < H.size(); l++) {
+        AmgLevelDev<T>& D = amg->lv[l];
+        D.n = H[l].A.rows;
+        D.lmax = H[l].lmax;
+        nnz_sum += (double)H[l].A.nnz();
+        n_sum += D.n;
+        if (!(l == 0 && fine_op)) upload_host_csr<T>(D.A, H[l].A, s);
+        if (l + 1 < H.size()) {
+            upload_host_csr<T>(D.P, H[l].P, s);
+            upload_host_csr<T>(D.R, H[l].R, s);
+        }
+        D.dinv.alloc(D.n);
+        D.dinv.upload((const T*)H[l].dinv.data(), D.n, s);
+        D.r.alloc(D.n); D.d.alloc(D.n); D.q.alloc(D.n);
+        if (l > 0) { D.x.alloc(D.n); D.b.alloc(D.n); }
+        MK_CUDA(cudaStreamSynchronize(s));
+    }
+    amg->op_complexity = nnz_sum / nnz0;
+    amg->grid_complexity = n_sum / n0;
+    const AmgHostLevel<S>& last = H.back();
+    amg->coarse_n = last.A.rows;
+    if (last.A.rows <= 1500) {
+        std::vector<S> inv = dense_inverse(last.A);
+        amg->coarse_inv.alloc(inv.size());
+        amg->coarse_inv.upload((const T*)inv.data(), inv.size(), s);
+        MK_CUDA(cudaStreamSynchronize(s));
+        amg->coarse_dense = true;
+    }
+    return amg;
+}
+
+}  // namespace mk

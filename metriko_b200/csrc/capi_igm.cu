@@ -1,0 +1,547 @@
+// C-ABI entry points: generic Hermitian eigen-solve on CSC input, real SPD solves (LM inner solver) and the IGM
+// Poisson + iterative-rounding driver (see include/metriko_b200.h for the reference seams they replace).
+#include <chrono>
+#include <complex>
+#include <cstring>
+#include <set>
+
+#include "amg.cuh"
+#include "capi_util.cuh"
+#include "csr.cuh"
+#include "field.cuh"
+#include "igm.cuh"
+#include "metriko_b200.h"
+
+using namespace mk;
+using hclock = std::chrono::steady_clock;
+static double ms_since(hclock::time_point t0) { return std::chrono::duration<double, std::milli>(hclock::now() - t0).count(); }
+
+static mk_solve_opts opts_or_default(const mk_solve_opts* o) {
+    mk_solve_opts r;
+    if (o) r = *o; else mk_default_opts(&r);
+    return r;
+}
+static int status_of(int s) { return s == 0 ? MK_OK : (s == 2 ? MK_ERR_NOT_SPD : MK_ERR_NOT_CONVERGED); }
+
+// ------------------------------------------------------------------------------------------------
+// solveSmallestEig on Eigen CSC arrays (sls.h:29)
+// ------------------------------------------------------------------------------------------------
+extern "C" int mk_solve_smallest_eig_csc(mk_ctx* ctx, int n, const int* L_outer, const int* L_inner, const double* L_values,
+                                         const int* M_outer, const int* M_inner, const double* M_values, const double* u0, int n_iter,
+                                         const mk_solve_opts* opts, double* x, mk_stats* stats) {
+    if (!ctx || n <= 0 || !L_outer || !L_inner || !L_values || !M_outer || !M_inner || !M_values || !u0 || !x) return MK_ERR_ARG;
+    int rc = MK_OK;
+    MK_API_BEGIN(ctx)
+    MK_CUDA(cudaSetDevice(ctx->c.device));
+    cudaStream_t s = ctx->c.stream;
+    const mk_solve_opts o = opts_or_default(opts);
+    auto t0 = hclock::now();
+    // CSC arrays of a Hermitian matrix read as CSR give conj(L): conjugate the values to get CSR(L).
+    const int64_t nnz = L_outer[n];
+    HostCsr<std::complex<double>> A;
+    A.rows = A.cols = n;
+    A.ptr.assign(L_outer, L_outer + n + 1);
+    A.col.assign(L_inner, L_inner + nnz);
+    A.val.resize(nnz);
+    for (int64_t k = 0; k < nnz; k++) A.val[k] = std::complex<double>(L_values[2 * k], -L_values[2 * k + 1]);
+    std::vector<double> mass(n, 0.0);
+    for (int c = 0; c < n; c++)
+        for (int k = M_outer[c]; k < M_outer[c + 1]; k++)
+            if (M_inner[k] == c) mass[c] += M_values[2 * k];
+    DeviceCsr<cdouble> dA;
+    upload_host_csr<cdouble>(dA, A, s);
+    CsrOp<cdouble> op(&dA);
+    DevBuf<double> dmass(n);
+    dmass.upload(mass.data(), n, s);
+    DevBuf<cdouble> u(n), xx(n), b(n);
+    u.upload((const cdouble*)u0, n, s);
+    MK_CUDA(cudaMemcpyAsync(xx.p, u.p, sizeof(cdouble) * n, cudaMemcpyDeviceToDevice, s));
+    Pcg<cdouble> pcg(n, s);
+    std::unique_ptr<AmgPrecond<cdouble>> amg;
+    if (o.precond == 1) amg = build_amg<cdouble>(s, std::move(A), {}, false, &op, amg_params_from_env());
+    MK_CUDA(cudaStreamSynchronize(s));
+    const double setup_ms = ms_since(t0);
+    auto t1 = hclock::now();
+    EigStats es = inverse_iteration(ctx->c, op, amg.get(), dmass.p, n, u.p, xx.p, b.p, pcg, n_iter, o.tol, o.max_iter, o.use_graph != 0);
+    xx.download((cdouble*)x, n, s);
+    MK_CUDA(cudaStreamSynchronize(s));
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        stats->outer_iterations = es.outer;
+        stats->inner_iterations = es.inner_total;
+        stats->inner_max = es.inner_max;
+        stats->relres_max = es.relres_max;
+        stats->lambda = es.lambda;
+        stats->kernel_launches = es.launches;
+        stats->setup_ms = setup_ms;
+        stats->solve_ms = ms_since(t1);
+        stats->status = status_of(es.status);
+    }
+    rc = status_of(es.status);
+    MK_API_END_RC(ctx, rc)
+}
+
+// ------------------------------------------------------------------------------------------------
+// real SPD solver handle (CholeskyWrapper, ir.h:14-20)
+// ------------------------------------------------------------------------------------------------
+struct mk_spd {
+    mk_ctx* ctx = nullptr;
+    int n = 0;
+    mk_solve_opts o;
+    DeviceCsr<double> A;
+    std::unique_ptr<CsrOp<double>> op;
+    std::unique_ptr<AmgPrecond<double>> amg;
+    std::unique_ptr<Pcg<double>> pcg;
+    DevBuf<double> b, x;
+    double setup_ms = 0;
+};
+
+// near-kernel candidate for the real operators: constants relaxed by a few Jacobi sweeps on A b = 0
+static std::vector<double> smoothed_constant_candidate(const HostCsr<double>& A, int sweeps) {
+    const int n = A.rows;
+    std::vector<double> b(n, 1.0), Ab, d = diagonal(A);
+    for (int it = 0; it < sweeps; it++) {
+        matvec(A, b, Ab);
+#pragma omp parallel for
+        for (int i = 0; i < n; i++)
+            if (d[i] != 0) b[i] -= (2.0 / 3.0) * Ab[i] / d[i];
+    }
+    return b;
+}
+
+extern "C" int mk_spd_factorize(mk_ctx* ctx, int n, const int* outer, const int* inner, const double* values, const mk_solve_opts* opts,
+                                mk_spd** out) {
+    if (!ctx || !out || n <= 0 || !outer || !inner || !values) return MK_ERR_ARG;
+    MK_API_BEGIN(ctx)
+    MK_CUDA(cudaSetDevice(ctx->c.device));
+    cudaStream_t s = ctx->c.stream;
+    auto t0 = hclock::now();
+    auto h = std::make_unique<mk_spd>();
+    h->ctx = ctx;
+    h->n = n;
+    h->o = opts_or_default(opts);
+    HostCsr<double> A;  // symmetric: CSC arrays are CSR arrays
+    A.rows = A.cols = n;
+    A.ptr.assign(outer, outer + n + 1);
+    A.col.assign(inner, inner + outer[n]);
+    A.val.assign(values, values + outer[n]);
+    upload_host_csr<double>(h->A, A, s);
+    h->op = std::make_unique<CsrOp<double>>(&h->A);
+    h->pcg = std::make_unique<Pcg<double>>(n, s);
+    h->b.alloc(n);
+    h->x.alloc(n);
+    if (h->o.precond == 1) {
+        std::vector<double> cand = smoothed_constant_candidate(A, 6);
+        h->amg = build_amg<double>(s, std::move(A), std::move(cand), true, h->op.get(), amg_params_from_env());
+    }
+    MK_CUDA(cudaStreamSynchronize(s));
+    h->setup_ms = ms_since(t0);
+    *out = h.release();
+    MK_API_END(ctx)
+}
+
+extern "C" int mk_spd_solve(mk_spd* h, const double* rhs, const double* x_guess, double* x, mk_stats* stats) {
+    if (!h || !rhs || !x) return MK_ERR_ARG;
+    int rc = MK_OK;
+    MK_API_BEGIN(h->ctx)
+    MK_CUDA(cudaSetDevice(h->ctx->c.device));
+    cudaStream_t s = h->ctx->c.stream;
+    auto t0 = hclock::now();
+    h->b.upload(rhs, h->n, s);
+    if (x_guess) h->x.upload(x_guess, h->n, s);
+    else h->x.zero(s);
+    h->pcg->bind(h->op.get(), h->amg.get(), nullptr);
+    SolveStats ss = h->pcg->solve(h->b.p, h->x.p, h->o.tol, h->o.max_iter, false, 16, h->o.use_graph != 0);
+    h->x.download(x, h->n, s);
+    MK_CUDA(cudaStreamSynchronize(s));
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        stats->outer_iterations = 1;
+        stats->inner_iterations = ss.iterations;
+        stats->inner_max = ss.iterations;
+        stats->relres_max = ss.relres;
+        stats->kernel_launches = ss.launches;
+        stats->setup_ms = h->setup_ms;
+        stats->solve_ms = ms_since(t0);
+        stats->status = status_of(ss.status);
+    }
+    rc = status_of(ss.status);
+    MK_API_END_RC(h->ctx, rc)
+}
+
+extern "C" int mk_spd_destroy(mk_spd* h) {
+    delete h;
+    return MK_OK;
+}
+
+extern "C" int mk_spd_spmv_bench(mk_spd* h, int reps, int fused_dot, double* ms_per_launch) {
+    if (!h || reps <= 0 || !ms_per_launch) return MK_ERR_ARG;
+    MK_API_BEGIN(h->ctx)
+    cudaStream_t s = h->ctx->c.stream;
+    std::vector<double> hx(h->n);
+    for (int i = 0; i < h->n; i++) hx[i] = std::sin(0.37 * i);
+    h->x.upload(hx.data(), h->n, s);
+    PcgState init;
+    std::memset(&init, 0, sizeof(init));
+    init.rho = 1.0;
+    MK_CUDA(cudaMemcpyAsync(h->pcg->state(), &init, sizeof(init), cudaMemcpyHostToDevice, s));
+    *ms_per_launch = time_op(*h->op, h->x.p, h->b.p, fused_dot ? h->pcg->state() : nullptr, h->pcg->ws(), reps, s);
+    MK_API_END(h->ctx)
+}
+
+// ------------------------------------------------------------------------------------------------
+// IGM
+// ------------------------------------------------------------------------------------------------
+struct mk_igm {
+    mk_ctx* ctx = nullptr;
+    int rows = 0, cols = 0, ufull_rows = 0;
+    double length = 1.0;
+    mk_solve_opts o;
+    HostCsr<double> UFull;           // host copy: candidate rows are extracted from it
+    DeviceCsr<double> A0, dUFull;    // A0 = length^2 X2F^T X2F
+    DevBuf<double> rhs0;             // length X2F^T F2
+    std::unique_ptr<CsrOp<double>> opA0, opA;  // A0 and A0 + 1e-4 I
+    std::unique_ptr<AmgPrecond<double>> amg;   // hierarchy of A0 + 1e-4 I, used for both stages
+    std::unique_ptr<Pcg<double>> pcg;
+    DevBuf<double> x, xprev, b, tmp;
+    double setup_ms = 0;
+};
+
+static HostCsr<double> csr_from_abi(int rows, int cols, const int64_t* ptr, const int* col, const double* val) {
+    HostCsr<double> A;
+    A.rows = rows;
+    A.cols = cols;
+    A.ptr.resize(rows + 1);
+    for (int i = 0; i <= rows; i++) A.ptr[i] = (int)ptr[i];
+    A.col.assign(col, col + ptr[rows]);
+    A.val.assign(val, val + ptr[rows]);
+    return A;
+}
+
+extern "C" int mk_igm_create(mk_ctx* ctx, int rows, int cols, const int64_t* x2f_ptr, const int* x2f_col, const double* x2f_val,
+                             int ufull_rows, const int64_t* uf_ptr, const int* uf_col, const double* uf_val, const double* F2,
+                             double length, const mk_solve_opts* opts, mk_igm** out) {
+    if (!ctx || !out || rows <= 0 || cols <= 0 || !x2f_ptr || !x2f_col || !x2f_val || !uf_ptr || !uf_col || !uf_val || !F2) return MK_ERR_ARG;
+    if (x2f_ptr[rows] > 2000000000LL) return MK_ERR_ARG;
+    MK_API_BEGIN(ctx)
+    MK_CUDA(cudaSetDevice(ctx->c.device));
+    cudaStream_t s = ctx->c.stream;
+    auto t0 = hclock::now();
+    auto g = std::make_unique<mk_igm>();
+    g->ctx = ctx;
+    g->rows = rows; g->cols = cols; g->ufull_rows = ufull_rows;
+    g->length = length;
+    g->o = opts_or_default(opts);
+    HostCsr<double> X = csr_from_abi(rows, cols, x2f_ptr, x2f_col, x2f_val);
+    g->UFull = csr_from_abi(ufull_rows, cols, uf_ptr, uf_col, uf_val);
+    // A0 = length^2 X^T X (host SpGEMM at set-up, as the reference's E = X2F^T X2F, ir_init.h:174); rhs0 = length X^T F2
+    HostCsr<double> Xt = transpose(X, false);
+    HostCsr<double> A0 = matmul(Xt, X);
+    const double l2 = length * length;
+#pragma omp parallel for
+    for (int64_t k = 0; k < (int64_t)A0.val.size(); k++) A0.val[k] *= l2;
+    std::vector<double> f2(F2, F2 + rows), rhs0;
+    matvec(Xt, f2, rhs0);
+    for (double& v : rhs0) v *= length;
+    upload_host_csr<double>(g->A0, A0, s);
+    upload_host_csr<double>(g->dUFull, g->UFull, s);
+    g->rhs0.alloc(cols);
+    g->rhs0.upload(rhs0.data(), cols, s);
+    g->opA0 = std::make_unique<CsrOp<double>>(&g->A0, 0.0);
+    g->opA = std::make_unique<CsrOp<double>>(&g->A0, 1e-4);  // wClose^2 = 0.01^2 (ir_loop.h:109)
+    g->pcg = std::make_unique<Pcg<double>>(cols, s);
+    g->x.alloc(cols); g->xprev.alloc(cols); g->b.alloc(cols); g->tmp.alloc(std::max(cols, ufull_rows));
+    MK_CUDA(cudaStreamSynchronize(s));
+    if (g->o.precond == 1) {
+        HostCsr<double> As = A0;
+        for (int i = 0; i < As.rows; i++)
+            for (int k = As.ptr[i]; k < As.ptr[i + 1]; k++)
+                if (As.col[k] == i) As.val[k] += 1e-4;
+        std::vector<double> cand = smoothed_constant_candidate(As, 6);
+        g->amg = build_amg<double>(s, std::move(As), std::move(cand), true, g->opA.get(), amg_params_from_env());
+    }
+    MK_CUDA(cudaStreamSynchronize(s));
+    g->setup_ms = ms_since(t0);
+    *out = g.release();
+    MK_API_END(ctx)
+}
+
+extern "C" int mk_igm_destroy(mk_igm* g) {
+    delete g;
+    return MK_OK;
+}
+
+extern "C" int mk_igm_get_matrix(mk_igm* g, int64_t* nnz, int* rowptr, int* col, double* val) {
+    if (!g || !nnz) return MK_ERR_ARG;
+    MK_API_BEGIN(g->ctx)
+    *nnz = g->A0.nnz;
+    if (rowptr && col && val) {
+        cudaStream_t s = g->ctx->c.stream;
+        g->A0.ptr.download(rowptr, g->cols + 1, s);
+        g->A0.col.download(col, g->A0.nnz, s);
+        g->A0.val.download(val, g->A0.nnz, s);
+        MK_CUDA(cudaStreamSynchronize(s));
+    }
+    MK_API_END(g->ctx)
+}
+
+extern "C" int mk_igm_spmv_bench(mk_igm* g, int reps, int fused_dot, double* ms_per_launch) {
+    if (!g || reps <= 0 || !ms_per_launch) return MK_ERR_ARG;
+    MK_API_BEGIN(g->ctx)
+    cudaStream_t s = g->ctx->c.stream;
+    std::vector<double> hx(g->cols);
+    for (int i = 0; i < g->cols; i++) hx[i] = std::sin(0.37 * i);
+    g->x.upload(hx.data(), g->cols, s);
+    PcgState init;
+    std::memset(&init, 0, sizeof(init));
+    init.rho = 1.0;
+    MK_CUDA(cudaMemcpyAsync(g->pcg->state(), &init, sizeof(init), cudaMemcpyHostToDevice, s));
+    *ms_per_launch = time_op(*g->opA, g->x.p, g->b.p, fused_dot ? g->pcg->state() : nullptr, g->pcg->ws(), reps, s);
+    MK_API_END(g->ctx)
+}
+
+namespace {
+
+// Candidate/constraint rows of UFull restricted to their joint support S
+struct RowBank {
+    std::vector<int> S;
+    std::unordered_map<int, int> pos;
+    std::unordered_map<int, std::vector<double>> rows;  // full-dof index -> dense row over S
+    void build(const HostCsr<double>& U, const std::vector<int>& idcs) {
+        std::set<int> sup;
+        for (int i : idcs)
+            for (int k = U.ptr[i]; k < U.ptr[i + 1]; k++) sup.insert(U.col[k]);
+        S.assign(sup.begin(), sup.end());
+        for (size_t p = 0; p < S.size(); p++) pos[S[p]] = (int)p;
+        for (int i : idcs) {
+            if (rows.count(i)) continue;
+            std::vector<double> r(S.size(), 0.0);
+            for (int k = U.ptr[i]; k < U.ptr[i + 1]; k++) r[pos[U.col[k]]] += U.val[k];
+            rows.emplace(i, std::move(r));
+        }
+    }
+};
+
+struct IgmRun {
+    mk_igm* g;
+    cudaStream_t s;
+    RowBank bank;
+    ConstraintSet cs;
+    ConstraintProjector proj;
+    DevBuf<double> qtmp, xS_dev;
+    std::vector<double> xS;
+    size_t applied = 0;  // constraints already eliminated from x
+    mk_stats st{};
+
+    void init(const std::vector<int>& idcs) {
+        bank.build(g->UFull, idcs);
+        const int m = (int)bank.S.size();
+        if (m > 5000) throw std::invalid_argument("igm: constraint support too large for the single-CTA projector");
+        proj.m = m;
+        proj.k = 0;
+        proj.kmax = (int)idcs.size() + 8;
+        proj.S.alloc(std::max(m, 1));
+        proj.S.upload(bank.S.data(), m, s);
+        proj.Q.alloc((size_t)proj.kmax * std::max(m, 1));
+        qtmp.alloc(std::max(m, 1));
+        xS_dev.alloc(std::max(m, 1));
+        xS.assign(m, 0.0);
+        if ((size_t)(m + proj.kmax) * sizeof(double) > 48 * 1024)
+            MK_CUDA(cudaFuncSetAttribute(k_project, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((m + proj.kmax) * sizeof(double))));
+        MK_CUDA(cudaStreamSynchronize(s));
+    }
+    void reset_constraints() {
+        cs.Q.clear();
+        cs.beta.clear();
+        proj.k = 0;
+        applied = 0;
+        g->pcg->invalidate_graph();
+    }
+    void fetch_xS() {
+        const int m = proj.m;
+        if (m == 0) return;
+        k_gather<<<(m + 127) / 128, 128, 0, s>>>(m, proj.S.p, g->x.p, xS_dev.p);
+        xS_dev.download(xS.data(), m, s);
+        MK_CUDA(cudaStreamSynchronize(s));
+    }
+    double value_of(int idx) const {
+        const std::vector<double>& r = bank.rows.at(idx);
+        double v = 0;
+        for (size_t p = 0; p < r.size(); p++) v += r[p] * xS[p];
+        return v;
+    }
+    // registers the constraint row(idx) . x = val; returns false when it contradicts the earlier ones
+    bool add_constraint(int idx, double val) {
+        double resid = 0;
+        int indep = cs.add(bank.rows.at(idx), val, xS, &resid);
+        if (indep) {
+            const int j = (int)cs.Q.size() - 1;
+            MK_CUDA(cudaMemcpyAsync(proj.Q.p + (size_t)j * proj.m, cs.Q[j].data(), sizeof(double) * proj.m, cudaMemcpyHostToDevice, s));
+            MK_CUDA(cudaStreamSynchronize(s));
+            return true;
+        }
+        return resid <= 10e-7;
+    }
+    // rank-1 eliminations for every constraint added since the last solve: x becomes feasible
+    void eliminate_pending() {
+        for (; applied < cs.Q.size(); applied++) {
+            k_constraint_eliminate<<<1, kThreads, 0, s>>>(proj.m, proj.S.p, proj.Q.p + applied * proj.m, cs.beta[applied], g->x.p);
+            st.kernel_launches++;
+        }
+        MK_CHECK_LAUNCH();
+        if (proj.k != (int)cs.Q.size()) {
+            proj.k = (int)cs.Q.size();
+            g->pcg->invalidate_graph();  // the projector launch parameters changed
+        }
+    }
+    SolveStats solve(CsrOp<double>* op) {
+        g->pcg->bind(op, g->amg.get(), &proj);
+        SolveStats ss = g->pcg->solve(g->b.p, g->x.p, g->o.tol, g->o.max_iter, false, 16, g->o.use_graph != 0);
+        st.outer_iterations++;
+        st.inner_iterations += ss.iterations;
+        st.inner_max = std::max(st.inner_max, ss.iterations);
+        st.relres_max = std::max(st.relres_max, ss.relres);
+        st.kernel_launches += ss.launches;
+        if (ss.status != 0 && st.status == MK_OK) st.status = status_of(ss.status);
+        return ss;
+    }
+    // Poisson stage: min ||length X2F x - F2|| s.t. UFull[fixed] x = vals  (ir_init.h:173-212)
+    void poisson(int n_fixed, const int* fixedIdcs, const double* fixedVals) {
+        reset_constraints();
+        g->x.zero(s);
+        fetch_xS();
+        for (int i = 0; i < n_fixed; i++)
+            if (!add_constraint(fixedIdcs[i], fixedVals[i])) throw std::runtime_error("igm: inconsistent fixed values");
+        eliminate_pending();
+        MK_CUDA(cudaMemcpyAsync(g->b.p, g->rhs0.p, sizeof(double) * g->cols, cudaMemcpyDeviceToDevice, s));
+        solve(g->opA0.get());
+    }
+};
+
+std::vector<int> concat_idcs(int n_fixed, const int* fixedIdcs, int n_sing, const int* sing, int n_int, const int* integ) {
+    std::vector<int> v;
+    if (fixedIdcs) v.insert(v.end(), fixedIdcs, fixedIdcs + n_fixed);
+    if (sing) v.insert(v.end(), sing, sing + n_sing);
+    if (integ) v.insert(v.end(), integ, integ + n_int);
+    return v;
+}
+
+void full_from_small(mk_igm* g, cudaStream_t s, double* host_out) {
+    spmv_plain(g->dUFull, g->x.p, g->tmp.p, false, nullptr, s);
+    g->tmp.download(host_out, g->ufull_rows, s);
+    MK_CUDA(cudaStreamSynchronize(s));
+}
+
+}  // namespace
+
+extern "C" int mk_igm_poisson(mk_igm* g, int n_fixed, const int* fixedIdcs, const double* fixedVals, double* x_small, double* x0_full,
+                              mk_stats* stats) {
+    if (!g || n_fixed < 0 || (n_fixed && (!fixedIdcs || !fixedVals))) return MK_ERR_ARG;
+    int rc = MK_OK;
+    MK_API_BEGIN(g->ctx)
+    MK_CUDA(cudaSetDevice(g->ctx->c.device));
+    auto t0 = hclock::now();
+    IgmRun run{g, g->ctx->c.stream};
+    run.init(concat_idcs(n_fixed, fixedIdcs, 0, nullptr, 0, nullptr));
+    run.poisson(n_fixed, fixedIdcs, fixedVals);
+    if (x_small) g->x.download(x_small, g->cols, run.s);
+    if (x0_full) full_from_small(g, run.s, x0_full);
+    MK_CUDA(cudaStreamSynchronize(run.s));
+    run.st.setup_ms = g->setup_ms;
+    run.st.solve_ms = ms_since(t0);
+    if (stats) *stats = run.st;
+    rc = run.st.status;
+    MK_API_END_RC(g->ctx, rc)
+}
+
+extern "C" int mk_igm_round(mk_igm* g, int n_fixed, const int* fixedIdcs, const double* fixedVals, int n_sing, const int* singularIdcs,
+                            int n_int, const int* integerIdcs, int seamless, int roundSeams, double* fullx, int* fixed_idcs, int* fixed_vals,
+                            int* n_fixed_out, int* resolve_flags, int* tie_flags, mk_stats* stats) {
+    if (!g || !fullx || n_fixed < 0 || n_sing < 0 || n_int < 0) return MK_ERR_ARG;
+    int rc = MK_OK;
+    MK_API_BEGIN(g->ctx)
+    MK_CUDA(cudaSetDevice(g->ctx->c.device));
+    cudaStream_t s = g->ctx->c.stream;
+    auto t0 = hclock::now();
+    IgmRun run{g, s};
+    run.init(concat_idcs(n_fixed, fixedIdcs, n_sing, singularIdcs, n_int, integerIdcs));
+    if (n_fixed_out) *n_fixed_out = 0;
+
+    // ---- NI stage: Poisson solution, then the closed form of the linear LM
+    run.poisson(n_fixed, fixedIdcs, fixedVals);
+    bool ok = true;
+    if (seamless) {
+        // SI right-hand side base: X2F^T F2_ with F2_ = (1e8 length B x + F2) / (1e8 + 1)  ->  (1e8 A0 x + rhs0) / (1e8 + 1)
+        DevBuf<double> base(g->cols);
+        g->opA0->apply(g->x.p, g->tmp.p, nullptr, run.g->pcg->ws(), s);
+        const double w = 1e8 / (1e8 + 1.0), w0 = 1.0 / (1e8 + 1.0);
+        k_axpby<<<stream_grid(g->cols), kThreads, 0, s>>>(g->cols, w, g->tmp.p, w0, g->rhs0.p, base.p);
+        MK_CHECK_LAUNCH();
+        run.st.kernel_launches += 2;
+        // ---- SI loop (ir.h:90-110, ir_loop.h:29-74)
+        run.reset_constraints();
+        std::vector<int> left = roundSeams ? std::vector<int>(integerIdcs, integerIdcs + n_int)
+                                           : std::vector<int>(singularIdcs, singularIdcs + n_sing);
+        bool roundedSingulars = false;
+        std::vector<int> fixed_local;
+        int nfix = 0;
+        bool rounded = false;
+        DevBuf<double> x_ni(g->cols);
+        MK_CUDA(cudaMemcpyAsync(x_ni.p, g->x.p, sizeof(double) * g->cols, cudaMemcpyDeviceToDevice, s));
+        while (!left.empty()) {
+            run.fetch_xS();
+            double minDif = 3276700.0, second = 1e300;
+            int minIdx = -1;
+            for (size_t i = 0; i < left.size(); i++) {
+                const double v = run.value_of(left[i]);
+                const double d = std::fabs(v - std::round(v));
+                if (d < minDif) { second = minDif; minIdx = (int)i; minDif = d; }
+                else if (d < second) second = d;
+            }
+            const int idx = left[minIdx];
+            const double X = run.value_of(idx);
+            const int val = (int)std::round(X);
+            left.erase(left.begin() + minIdx);
+            if (left.empty() && !roundSeams && !roundedSingulars) {
+                left.assign(integerIdcs, integerIdcs + n_int);
+                roundedSingulars = true;
+            }
+            int flags = 0;
+            if (std::fabs(std::fabs(X - std::floor(X)) - 0.5) < 1e-6) flags |= 1;
+            if (minDif > 10e-7 && second - minDif < 1e-8) flags |= 2;
+            const bool consistent = run.add_constraint(idx, (double)val);
+            const bool resolve = minDif > 10e-7;
+            fixed_local.push_back(idx);
+            if (fixed_idcs) fixed_idcs[nfix] = idx;
+            if (fixed_vals) fixed_vals[nfix] = val;
+            if (resolve_flags) resolve_flags[nfix] = resolve ? 1 : 0;
+            if (tie_flags) tie_flags[nfix] = flags;
+            nfix++;
+            if (!consistent) { ok = false; break; }  // the penalty system of the reference would fail post_checking
+            if (!resolve) continue;                  // ir.h:100
+            rounded = true;
+            MK_CUDA(cudaMemcpyAsync(g->xprev.p, g->x.p, sizeof(double) * g->cols, cudaMemcpyDeviceToDevice, s));
+            run.eliminate_pending();
+            k_axpby<<<stream_grid(g->cols), kThreads, 0, s>>>(g->cols, 1.0, base.p, 1e-4, g->xprev.p, g->b.p);
+            MK_CHECK_LAUNCH();
+            run.st.kernel_launches++;
+            run.solve(g->opA.get());
+            // post_checking (ir_loop.h:89-100): constraints are exact here, so this only guards the solver
+            run.fetch_xS();
+            double mx = 0;
+            for (int fi : fixed_local) {
+                const double v = run.value_of(fi);
+                mx = std::max(mx, std::fabs(v - std::round(v)));
+            }
+            if (!(mx <= 10e-7)) { ok = false; break; }
+        }
+        if (n_fixed_out) *n_fixed_out = nfix;
+        if (!rounded) MK_CUDA(cudaMemcpyAsync(g->x.p, x_ni.p, sizeof(double) * g->cols, cudaMemcpyDeviceToDevice, s));  // ir.h:111
+    }
+    full_from_small(g, s, fullx);
+    run.st.setup_ms = g->setup_ms;
+    run.st.solve_ms = ms_since(t0);
+    if (stats) *stats = run.st;
+    rc = !ok ? MK_ERR_ROUNDING : run.st.status;
+    MK_API_END_RC(g->ctx, rc)
+}

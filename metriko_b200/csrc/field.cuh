@@ -1,0 +1,228 @@
+// N-RoSy field hot path on the device: connection-Laplacian / mass assembly (frf.h:46-84), the face-stencil
+// SpMV, the 50-step inverse power iteration of solveSmallestEig (sls.h:29-54) and the decode (frf.h:37-43).
+#pragma once
+#include <cmath>
+#include <vector>
+
+#include "csr.cuh"
+#include "solver.cuh"
+
+namespace mk {
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    std::string err;
+};
+
+// Face stencil storage ("ELL-3", SoA): every face row of L has the constant diagonal 3 + 1e-9 (frf.h:65-75, closed
+// mesh) and exactly three off-diagonals of unit modulus, so the row is nbr[j][f], val[j][f], j = 0..2. 92 B/row moved
+// per SpMV (48 values + 12 indices + 16 x + 16 y) against 116 B/row for CSR with an explicit diagonal.
+struct FaceStencil {
+    int nF = 0;
+    double diag = 3.0 + 1e-9;
+    DevBuf<int> nbr;      // 3 * nF
+    DevBuf<cdouble> val;  // 3 * nF
+    DevBuf<double> mass;  // nF (faceArea, frf.h:78-84)
+};
+
+// One thread per face: the three halves of f come from face2half/next (hmesh.h:305-310, 379); each face owns its own
+// row, so the scatter map is the identity and no atomics are needed.
+// L(f, face(twin h)) = -transport[twin h]^N with transport[t] = -e^{i (farg(twin t) - farg(t))} (frf.h:52-71).
+static __global__ void __launch_bounds__(kThreads) k_field_assemble(int nF, int N, const int* __restrict__ face2half, const int* __restrict__ next,
+                                                             const int* __restrict__ twin, const int* __restrict__ face,
+                                                             const double* __restrict__ farg, int* __restrict__ nbr, cdouble* __restrict__ val) {
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nF; f += gridDim.x * blockDim.x) {
+        int h = face2half[f];
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const int t = twin[h];
+            const int g = face[t];
+            // transport[t]^N = (-1)^N e^{i N (farg(h) - farg(t))}
+            const double ang = (double)N * (farg[h] - farg[t]);
+            double s, c;
+            sincos(ang, &s, &c);
+            const double sign = (N & 1) ? -1.0 : 1.0;
+            nbr[(size_t)j * nF + f] = g;
+            stc(val + (size_t)j * nF + f, make_c(-sign * c, -sign * s));
+            h = next[h];
+        }
+    }
+}
+
+// y = L x for the face stencil; DOT: pq = <x, y>, alpha = rho / pq.
+template <bool DOT>
+static __global__ void __launch_bounds__(kThreads) k_spmv_face(int nF, double diag, const int* __restrict__ nbr, const cdouble* __restrict__ val,
+                                                        const cdouble* __restrict__ x, cdouble* __restrict__ y, PcgState* st, ReduceWs ws) {
+    __shared__ double red[32];
+    if (st && st->done) return;
+    double dot = 0.0;
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nF; f += gridDim.x * blockDim.x) {
+        const int n0 = __ldg(nbr + f), n1 = __ldg(nbr + (size_t)nF + f), n2 = __ldg(nbr + 2 * (size_t)nF + f);
+        const cdouble v0 = ldc_nc(val + f), v1 = ldc_nc(val + (size_t)nF + f), v2 = ldc_nc(val + 2 * (size_t)nF + f);
+        const cdouble xf = ldc_nc(x + f);
+        const cdouble x0 = ldc_nc(x + n0), x1 = ldc_nc(x + n1), x2 = ldc_nc(x + n2);
+        cdouble acc = make_c(diag * xf.x, diag * xf.y);
+        acc = ST<cdouble>::fma_(v0, x0, acc);
+        acc = ST<cdouble>::fma_(v1, x1, acc);
+        acc = ST<cdouble>::fma_(v2, x2, acc);
+        stc(y + f, acc);
+        if (DOT) dot += xf.x * acc.x + xf.y * acc.y;
+    }
+    if (DOT) {
+        double v[1] = {dot};
+        grid_reduce<1>(v, ws.partials, ws.ticket, red, [&](const double* s) {
+            st->pq = s[0];
+            st->alpha = st->rho / s[0];
+            if (!(s[0] > 0.0)) st->done = 2;
+        });
+    }
+}
+
+struct FaceOp : LinOp<cdouble> {
+    const FaceStencil* S;
+    explicit FaceOp(const FaceStencil* S_) : S(S_) { n = S_->nF; }
+    void apply(const cdouble* x, cdouble* y, PcgState* st, ReduceWs ws, cudaStream_t s, bool dot = true) override {
+        int grid = stream_grid(S->nF, kThreads, 8);
+        if (st && dot) k_spmv_face<true><<<grid, kThreads, 0, s>>>(S->nF, S->diag, S->nbr.p, S->val.p, x, y, st, ws);
+        else k_spmv_face<false><<<grid, kThreads, 0, s>>>(S->nF, S->diag, S->nbr.p, S->val.p, x, y, st, ws);
+        MK_CHECK_LAUNCH();
+    }
+};
+
+// ---- inverse iteration helper kernels (sls.h:44-51) ----
+
+// b = m .* u ; aux0 = <u, b> = u^H M u
+static __global__ void __launch_bounds__(kThreads) k_mass_rhs(int n, const double* __restrict__ m, const cdouble* __restrict__ u, cdouble* __restrict__ b,
+                                                       PcgState* st, ReduceWs ws) {
+    __shared__ double red[32];
+    double acc = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double mi = __ldg(m + i);
+        const cdouble ui = ldc_nc(u + i);
+        stc(b + i, make_c(mi * ui.x, mi * ui.y));
+        acc += mi * (ui.x * ui.x + ui.y * ui.y);
+    }
+    double v[1] = {acc};
+    grid_reduce<1>(v, ws.partials, ws.ticket, red, [&](const double* s) { st->aux0 = s[0]; });
+}
+
+// pq = <a, b> (real part of a^H b)
+static __global__ void __launch_bounds__(kThreads) k_dot_uq(int n, const cdouble* __restrict__ a, const cdouble* __restrict__ b, PcgState* st, ReduceWs ws) {
+    __shared__ double red[32];
+    double acc = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const cdouble ai = ldc_nc(a + i), bi = ldc_nc(b + i);
+        acc += ai.x * bi.x + ai.y * bi.y;
+    }
+    double v[1] = {acc};
+    grid_reduce<1>(v, ws.partials, ws.ticket, red, [&](const double* s) { st->pq = s[0]; });
+}
+
+// Warm start: x = theta u, r = b - theta q with q = L u and theta = <u,b> / <u,q> (the energy-optimal multiple of u);
+// also rr, bnorm2 and the PCG state reset (what k_residual does for a generic start).
+static __global__ void __launch_bounds__(kThreads) k_warm_start(int n, const cdouble* __restrict__ u, const cdouble* __restrict__ b,
+                                                         const cdouble* __restrict__ q, cdouble* __restrict__ x, cdouble* __restrict__ r,
+                                                         PcgState* st, ReduceWs ws, double tol2, int maxit) {
+    __shared__ double red[32];
+    const double theta = st->aux0 / st->pq;
+    double a0 = 0.0, a1 = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const cdouble ui = ldc_nc(u + i), bi = ldc_nc(b + i), qi = ldc_nc(q + i);
+        const cdouble ri = make_c(bi.x - theta * qi.x, bi.y - theta * qi.y);
+        stc(x + i, make_c(theta * ui.x, theta * ui.y));
+        stc(r + i, ri);
+        a0 += ri.x * ri.x + ri.y * ri.y;
+        a1 += bi.x * bi.x + bi.y * bi.y;
+    }
+    double v[2] = {a0, a1};
+    grid_reduce<2>(v, ws.partials, ws.ticket, red, [&](const double* s) {
+        st->rr = s[0];
+        st->bnorm2 = s[1];
+        st->thresh = tol2 * s[1];
+        st->iter = 0;
+        st->maxit = maxit;
+        st->aux2 = st->pq;  // u^H L u, kept for the Rayleigh quotient
+        st->done = (s[0] <= st->thresh) ? 1 : 0;
+    });
+}
+
+// aux1 = x^H M x
+static __global__ void __launch_bounds__(kThreads) k_mnorm2(int n, const double* __restrict__ m, const cdouble* __restrict__ x, PcgState* st, ReduceWs ws) {
+    __shared__ double red[32];
+    double acc = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const cdouble xi = ldc_nc(x + i);
+        acc += __ldg(m + i) * (xi.x * xi.x + xi.y * xi.y);
+    }
+    double v[1] = {acc};
+    grid_reduce<1>(v, ws.partials, ws.ticket, red, [&](const double* s) { st->aux1 = s[0]; });
+}
+
+// x /= sqrt(|x^H M x|) ; u = x     (sls.h:48-50)
+static __global__ void __launch_bounds__(kThreads) k_normalize_copy(int n, cdouble* __restrict__ x, cdouble* __restrict__ u, const PcgState* st) {
+    const double s = 1.0 / sqrt(fabs(st->aux1));
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        cdouble xi = ldc(x + i);
+        xi = make_c(xi.x * s, xi.y * s);
+        stc(x + i, xi);
+        stc(u + i, xi);
+    }
+}
+
+// frf.h:37-43: field(f,i) = (e^{i arg z_f})^{1/N} (e^{2 pi i / N})^i, row-major nF x N
+static __global__ void __launch_bounds__(kThreads) k_decode(int nF, int N, const cdouble* __restrict__ z, cdouble* __restrict__ field) {
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nF; f += gridDim.x * blockDim.x) {
+        const cdouble zf = ldc_nc(z + f);
+        const double a = atan2(zf.y, zf.x) / (double)N;
+        for (int i = 0; i < N; i++) {
+            double s, c;
+            sincos(a + 2.0 * M_PI * (double)i / (double)N, &s, &c);
+            stc(field + (size_t)f * N + i, make_c(c, s));
+        }
+    }
+}
+
+struct EigStats {
+    int outer = 0;
+    long inner_total = 0;
+    int inner_max = 0;
+    double relres_max = 0.0;
+    int status = 0;
+    long launches = 0;
+    double lambda = 0.0;  // Rayleigh quotient u^H L u / u^H M u at the last step
+};
+
+// solveSmallestEig (sls.h:29-54) with the factorisation replaced by warm-started PCG solves; u0 is an explicit input
+// (the reference draws VecXc::Random from an unseeded std::rand).
+template <class OpT>
+inline EigStats inverse_iteration(Ctx& ctx, OpT& A, Precond<cdouble>* M, const double* mass, int n, cdouble* u, cdouble* x, cdouble* b,
+                                  Pcg<cdouble>& pcg, int n_iter, double tol, int maxit, bool use_graph) {
+    EigStats es;
+    cudaStream_t s = ctx.stream;
+    pcg.bind(&A, M, nullptr);
+    const int grid = pcg.grid();
+    for (int it = 0; it < n_iter; it++) {
+        k_mass_rhs<<<grid, kThreads, 0, s>>>(n, mass, u, b, pcg.state(), pcg.ws());
+        A.apply(u, pcg.q(), nullptr, pcg.ws(), s);
+        k_dot_uq<<<grid, kThreads, 0, s>>>(n, u, pcg.q(), pcg.state(), pcg.ws());
+        k_warm_start<<<grid, kThreads, 0, s>>>(n, u, b, pcg.q(), x, pcg.r(), pcg.state(), pcg.ws(), tol * tol, maxit);
+        MK_CHECK_LAUNCH();
+        SolveStats ss = pcg.solve(b, x, tol, maxit, true, 16, use_graph);
+        k_mnorm2<<<grid, kThreads, 0, s>>>(n, mass, x, pcg.state(), pcg.ws());
+        k_normalize_copy<<<grid, kThreads, 0, s>>>(n, x, u, pcg.state());
+        MK_CHECK_LAUNCH();
+        es.outer++;
+        es.inner_total += ss.iterations;
+        es.inner_max = std::max(es.inner_max, ss.iterations);
+        es.relres_max = std::max(es.relres_max, ss.relres);
+        if (ss.status != 0) es.status = ss.status;
+        es.launches += ss.launches + 5 + A.launches_per_apply();
+    }
+    pcg.fetch_state();
+    es.lambda = pcg.host_state().aux2 / pcg.host_state().aux0;
+    return es;
+}
+
+}  // namespace mk

@@ -1,0 +1,329 @@
+// Preconditioned conjugate gradients with every scalar device-resident (no host sync inside an iteration),
+// fused vector kernels with warp-shuffle reductions, and the iteration body replayed as a CUDA graph.
+// Replaces the direct factorisations of the reference (Eigen::SparseLU sls.h:42-47, CHOLMOD LDL^T
+// ss/suitesparse_pdefinite.h:26-41, Eigen::SimplicialLLT ir.h:14-20) with an HBM-bound iterative path.
+#pragma once
+#include <memory>
+#include <vector>
+
+#include "common.cuh"
+
+namespace mk {
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    explicit DevBuf(size_t n_) { alloc(n_); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void alloc(size_t n_) {
+        release();
+        n = n_;
+        if (n) MK_CUDA(cudaMalloc((void**)&p, n * sizeof(T)));
+    }
+    void zero(cudaStream_t s) { if (n) MK_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+    void upload(const T* h, size_t cnt, cudaStream_t s) { if (cnt) MK_CUDA(cudaMemcpyAsync(p, h, cnt * sizeof(T), cudaMemcpyHostToDevice, s)); }
+    void download(T* h, size_t cnt, cudaStream_t s) const { if (cnt) MK_CUDA(cudaMemcpyAsync(h, p, cnt * sizeof(T), cudaMemcpyDeviceToHost, s)); }
+};
+
+// Device-resident solver state. One instance per PCG object; kernels read alpha/beta from here.
+struct PcgState {
+    double rho;       // <r, z>
+    double pq;        // <p, A p>
+    double rr;        // <r, r>
+    double alpha, beta;
+    double bnorm2;    // <b, b>
+    double thresh;    // tol^2 * bnorm2
+    double aux0, aux1, aux2;  // scratch reductions for drivers (e.g. <u, M u>)
+    int iter;
+    int done;         // 1 = converged (kernels become no-ops), 2 = breakdown
+    int maxit;
+    int pad;
+};
+
+struct ReduceWs {
+    double* partials;      // kMaxPartials * 4 doubles
+    unsigned int* ticket;  // zero-initialised, reset by the last CTA
+};
+
+// ---------------------------------------------------------------------------------------------
+// fused vector kernels (grid-stride, one pass over each vector, reductions finished in-kernel)
+// ---------------------------------------------------------------------------------------------
+
+// x += alpha p ; r -= alpha q ; rr = <r,r>.  Without a preconditioner z == r, so rho/beta are finished here too.
+template <class T, bool PRECOND>
+__global__ void __launch_bounds__(kThreads) k_update_xr(int n, T* __restrict__ x, T* __restrict__ r, const T* __restrict__ p,
+                                                        const T* __restrict__ q, PcgState* st, ReduceWs ws) {
+    __shared__ double red[32];
+    if (st->done) return;
+    const double alpha = st->alpha;
+    double acc = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        T pi = ld_ro(p + i), qi = ld_ro(q + i);
+        T xi = ld_rw(x + i), ri = ld_rw(r + i);
+        xi = xi + ST<T>::scale(alpha, pi);
+        ri = ri - ST<T>::scale(alpha, qi);
+        st_rw(x + i, xi);
+        st_rw(r + i, ri);
+        acc += ST<T>::abs2(ri);
+    }
+    double v[1] = {acc};
+    grid_reduce<1>(v, ws.partials, ws.ticket, red, [&](const double* s) {
+        st->rr = s[0];
+        st->iter += 1;
+        if (!PRECOND) {
+            st->beta = s[0] / st->rho;
+            st->rho = s[0];
+        }
+        if (s[0] <= st->thresh) st->done = 1;
+        else if (st->iter >= st->maxit) st->done = 3;
+        else if (!(s[0] == s[0])) st->done = 2;
+    });
+}
+
+// rho_new = <r, z> ; beta = rho_new / rho
+template <class T>
+__global__ void __launch_bounds__(kThreads) k_dot_rz(int n, const T* __restrict__ r, const T* __restrict__ z, PcgState* st, ReduceWs ws) {
+    __shared__ double red[32];
+    if (st->done) return;
+    double acc = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) acc += ST<T>::hdot(ld_ro(r + i), ld_ro(z + i));
+    double v[1] = {acc};
+    grid_reduce<1>(v, ws.partials, ws.ticket, red, [&](const double* s) {
+        st->beta = s[0] / st->rho;
+        st->rho = s[0];
+    });
+}
+
+// p = z + beta p
+template <class T>
+__global__ void __launch_bounds__(kThreads) k_update_p(int n, T* __restrict__ p, const T* __restrict__ z, const PcgState* st) {
+    if (st->done) return;
+    const double beta = st->beta;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        T zi = ld_ro(z + i), pi = ld_rw(p + i);
+        st_rw(p + i, zi + ST<T>::scale(beta, pi));
+    }
+}
+
+// r = b - q (q = A x) ; rr = <r,r> ; bnorm2 = <b,b> ; resets the iteration state. If keep_bnorm, only rr is refreshed
+// (used for the true-residual restart).
+template <class T>
+__global__ void __launch_bounds__(kThreads) k_residual(int n, const T* __restrict__ b, const T* __restrict__ q, T* __restrict__ r,
+                                                       PcgState* st, ReduceWs ws, double tol2, int maxit, int keep_bnorm) {
+    __shared__ double red[32];
+    double a0 = 0.0, a1 = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        T bi = ld_ro(b + i), qi = ld_ro(q + i);
+        T ri = bi - qi;
+        st_rw(r + i, ri);
+        a0 += ST<T>::abs2(ri);
+        a1 += ST<T>::abs2(bi);
+    }
+    double v[2] = {a0, a1};
+    grid_reduce<2>(v, ws.partials, ws.ticket, red, [&](const double* s) {
+        st->rr = s[0];
+        if (!keep_bnorm) {
+            st->bnorm2 = s[1];
+            st->thresh = tol2 * s[1];
+            st->iter = 0;
+        }
+        st->maxit = maxit;
+        st->done = (s[0] <= st->thresh) ? 1 : 0;
+    });
+}
+
+// p = z ; rho = <r, z>   (start of a PCG run; with no preconditioner call with z == r)
+template <class T>
+__global__ void __launch_bounds__(kThreads) k_start_p(int n, const T* __restrict__ r, const T* __restrict__ z, T* __restrict__ p,
+                                                      PcgState* st, ReduceWs ws) {
+    __shared__ double red[32];
+    if (st->done) return;
+    double acc = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        T zi = ld_ro(z + i);
+        st_rw(p + i, zi);
+        acc += ST<T>::hdot(ld_ro(r + i), zi);
+    }
+    double v[1] = {acc};
+    grid_reduce<1>(v, ws.partials, ws.ticket, red, [&](const double* s) { st->rho = s[0]; });
+}
+
+// ---------------------------------------------------------------------------------------------
+// operator / preconditioner / projector interfaces
+// ---------------------------------------------------------------------------------------------
+template <class T>
+struct LinOp {
+    int n = 0;
+    virtual ~LinOp() = default;
+    // y = A x. st != nullptr: the launch is skipped once st->done is set (graph replay); if additionally `dot`, the
+    // kernel finishes the fused reduction pq = <x, y>, alpha = rho / pq (the PCG step).
+    virtual void apply(const T* x, T* y, PcgState* st, ReduceWs ws, cudaStream_t s, bool dot = true) = 0;
+    virtual int launches_per_apply() const { return 1; }
+};
+
+template <class T>
+struct Precond {
+    virtual ~Precond() = default;
+    virtual void apply(const T* r, T* z, const PcgState* st, cudaStream_t s) = 0;  // z = M^{-1} r
+    virtual int launches_per_apply() const = 0;
+};
+
+// In-place projection onto the feasible subspace (IGM constraint elimination); null for unconstrained solves.
+template <class T>
+struct Projector {
+    virtual ~Projector() = default;
+    virtual void apply(T* v, const PcgState* st, cudaStream_t s) = 0;
+};
+
+struct SolveStats {
+    int iterations = 0;
+    int restarts = 0;
+    double relres = 0.0;  // true ||b - A x|| / ||b|| at exit
+    int status = 0;       // 0 ok, 1 maxit, 2 breakdown
+    long launches = 0;
+};
+
+template <class T>
+class Pcg {
+public:
+    Pcg(int n, cudaStream_t stream) : n_(n), stream_(stream), r_(n), z_(n), p_(n), q_(n), st_(1), partials_(kMaxPartials * 4), ticket_(1) {
+        ticket_.zero(stream_);
+        st_.zero(stream_);
+        MK_CUDA(cudaMallocHost((void**)&h_st_, sizeof(PcgState)));
+        grid_ = stream_grid(n);
+    }
+    ~Pcg() {
+        if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
+        if (h_st_) cudaFreeHost(h_st_);
+    }
+    PcgState* state() { return st_.p; }
+    ReduceWs ws() { return ReduceWs{partials_.p, ticket_.p}; }
+    T* q() { return q_.p; }
+    T* r() { return r_.p; }
+    int grid() const { return grid_; }
+
+    void bind(LinOp<T>* A, Precond<T>* M, Projector<T>* P) {
+        if (A != A_ || M != M_ || P != P_) invalidate_graph();
+        A_ = A; M_ = M; P_ = P;
+    }
+    void invalidate_graph() {
+        if (graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
+    }
+
+    // Solve A x = b starting from the x passed in. If residual_ready, r() already holds b - A x and the state
+    // (rr, bnorm2, thresh, iter, maxit, done) was set by k_residual.
+    // With a projector the right-hand side is projected in place first (r = P b - P A x stays in the feasible subspace).
+    SolveStats solve(T* b, T* x, double tol, int maxit, bool residual_ready, int chunk = 16, bool use_graph = true) {
+        SolveStats out;
+        long launches = 0;
+        const double tol2 = tol * tol;
+        if (!residual_ready) {
+            if (P_) { P_->apply(b, nullptr, stream_); launches++; }
+            A_->apply(x, q_.p, nullptr, ws(), stream_);
+            if (P_) P_->apply(q_.p, nullptr, stream_);
+            launch_residual(b, tol2, maxit, 0);
+            launches += 1 + A_->launches_per_apply();
+        }
+        for (int attempt = 0; attempt < 4; attempt++) {
+            start_direction();
+            launches += 1 + (M_ ? M_->launches_per_apply() : 0);
+            while (true) {
+                for (int c = 0; c < chunk; c++) iteration(x, use_graph);
+                launches += (long)chunk * launches_per_iteration();
+                fetch_state();
+                if (h_st_->done) break;
+            }
+            // true residual check (recurrence residuals drift at the 1e-10 level)
+            A_->apply(x, q_.p, nullptr, ws(), stream_);
+            if (P_) P_->apply(q_.p, nullptr, stream_);
+            launch_residual(b, tol2, maxit, 1);
+            launches += 1 + A_->launches_per_apply();
+            fetch_state();
+            out.iterations = h_st_->iter;
+            out.relres = h_st_->bnorm2 > 0 ? std::sqrt(h_st_->rr / h_st_->bnorm2) : 0.0;
+            out.restarts = attempt;
+            if (h_st_->done == 1 || h_st_->iter >= maxit) break;
+        }
+        out.status = (out.relres <= tol * 1.0000001 || h_st_->bnorm2 == 0) ? 0 : (h_st_->iter >= maxit ? 1 : 2);
+        out.launches = launches;
+        return out;
+    }
+
+    int launches_per_iteration() const {
+        return A_->launches_per_apply() + (P_ ? (M_ ? 2 : 1) : 0) + 1 + (M_ ? M_->launches_per_apply() + 1 : 0) + 1;
+    }
+
+    void launch_residual(const T* b, double tol2, int maxit, int keep) {
+        k_residual<T><<<grid_, kThreads, 0, stream_>>>(n_, b, q_.p, r_.p, st_.p, ws(), tol2, maxit, keep);
+        MK_CHECK_LAUNCH();
+    }
+    void fetch_state() {
+        MK_CUDA(cudaMemcpyAsync(h_st_, st_.p, sizeof(PcgState), cudaMemcpyDeviceToHost, stream_));
+        MK_CUDA(cudaStreamSynchronize(stream_));
+    }
+    const PcgState& host_state() const { return *h_st_; }
+
+private:
+    void start_direction() {
+        if (M_) {
+            M_->apply(r_.p, z_.p, st_.p, stream_);
+            if (P_) P_->apply(z_.p, st_.p, stream_);
+            k_start_p<T><<<grid_, kThreads, 0, stream_>>>(n_, r_.p, z_.p, p_.p, st_.p, ws());
+        } else {
+            k_start_p<T><<<grid_, kThreads, 0, stream_>>>(n_, r_.p, r_.p, p_.p, st_.p, ws());
+        }
+        MK_CHECK_LAUNCH();
+    }
+    void iteration_body(T* x) {
+        A_->apply(p_.p, q_.p, st_.p, ws(), stream_);
+        if (P_) P_->apply(q_.p, st_.p, stream_);
+        if (M_) {
+            k_update_xr<T, true><<<grid_, kThreads, 0, stream_>>>(n_, x, r_.p, p_.p, q_.p, st_.p, ws());
+            M_->apply(r_.p, z_.p, st_.p, stream_);
+            if (P_) P_->apply(z_.p, st_.p, stream_);
+            k_dot_rz<T><<<grid_, kThreads, 0, stream_>>>(n_, r_.p, z_.p, st_.p, ws());
+            k_update_p<T><<<grid_, kThreads, 0, stream_>>>(n_, p_.p, z_.p, st_.p);
+        } else {
+            k_update_xr<T, false><<<grid_, kThreads, 0, stream_>>>(n_, x, r_.p, p_.p, q_.p, st_.p, ws());
+            k_update_p<T><<<grid_, kThreads, 0, stream_>>>(n_, p_.p, r_.p, st_.p);
+        }
+        MK_CHECK_LAUNCH();
+    }
+    void iteration(T* x, bool use_graph) {
+        if (!use_graph) { iteration_body(x); return; }
+        if (!graph_exec_ || graph_x_ != x) {
+            invalidate_graph();
+            cudaGraph_t g;
+            MK_CUDA(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+            iteration_body(x);
+            MK_CUDA(cudaStreamEndCapture(stream_, &g));
+            MK_CUDA(cudaGraphInstantiate(&graph_exec_, g, 0));
+            cudaGraphDestroy(g);
+            graph_x_ = x;
+        }
+        MK_CUDA(cudaGraphLaunch(graph_exec_, stream_));
+    }
+
+    int n_;
+    cudaStream_t stream_;
+    DevBuf<T> r_, z_, p_, q_;
+    DevBuf<PcgState> st_;
+    DevBuf<double> partials_;
+    DevBuf<unsigned int> ticket_;
+    PcgState* h_st_ = nullptr;
+    int grid_ = 1;
+    LinOp<T>* A_ = nullptr;
+    Precond<T>* M_ = nullptr;
+    Projector<T>* P_ = nullptr;
+    cudaGraphExec_t graph_exec_ = nullptr;
+    T* graph_x_ = nullptr;
+};
+
+}  // namespace mk

@@ -1,0 +1,244 @@
+"""Oracle: Integer-Grid-Map Poisson solve + iterative rounding. Restates
+include/metriko/core/igm/iterative_rounding/{iter_rounding.h:33-113, iter_rounding_init.h:60-72,173-232,
+iter_rounding_loop.h:29-124, iter_rounding_common.h:60-94} and solver/levenberg_marquardt.h:13-231
+with scipy's SuperLU standing in for Eigen::SparseLU / SimplicialLLT (test infrastructure, see
+oracle/__init__.py). `UFull` (ir_init.h:98-154, dense FullPivLU kernel of the node constraints) is taken
+as an input: it is host-side setup shared verbatim by the oracle and the CUDA path."""
+from __future__ import annotations
+
+import numpy as np
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+
+class _Factor:
+    """CholeskyWrapper (ir.h:14-20): factorize(A) + solve(rhs). SuperLU on the SPD normal matrix."""
+
+    def __init__(self):
+        self.lu = None
+        self.count = 0
+
+    def factorize(self, A) -> bool:
+        self.lu = spla.splu(sp.csc_matrix(A))
+        self.count += 1
+        return True
+
+    def solve(self, rhs):
+        return self.lu.solve(rhs)
+
+
+def lm_solve(objective, jacobian, x0, lam0=0.0, max_iterations=100, func_tol=10e-10, foo_tol=10e-10, post_iteration=None,
+             stats=None):
+    """LMSolver::solve (lm.h:140-231) with DiagonalDamping (lm.h:13-88), verbose = false.
+
+    objective(x) -> E vector; jacobian(x) -> sparse J. Quirks kept: the first-order-optimality test never
+    breaks when not verbose (lm.h:171-177); `|direction| < funcTol` returns True with x = prevx
+    (lm.h:193-197); a small energy change breaks and returns False (lm.h:208-211); lambda * 10 stays 0
+    when lam0 = 0 so a non-decreasing step re-solves the same system until maxIterations (lm.h:58-62)."""
+    LS = _Factor()
+    lam = lam0
+    prevx = np.array(x0, np.float64)
+    x = prevx.copy()
+
+    def damp(J):
+        # DiagonalDamping::init/update: dampJ = [J; diag(sqrt(lam * colsum(J.^2)))]
+        d = lam * np.asarray(J.multiply(J).sum(axis=0)).ravel()
+        return sp.vstack([J, sp.diags(np.sqrt(d))]).tocsc()
+
+    E = objective(prevx)
+    J = jacobian(prevx)
+    dampJ = damp(J)
+    it = 0
+    ret = False
+    while True:
+        rhs = -(J.T @ E)
+        if np.max(np.abs(rhs)) < foo_tol:
+            x = prevx.copy()  # no break unless verbose
+        if not LS.factorize((dampJ.T @ dampJ).tocsc()):
+            ret = False
+            break
+        direction = LS.solve(rhs)
+        if np.linalg.norm(direction) < func_tol:
+            x = prevx.copy()
+            ret = True
+            break
+        prevE2 = float(np.sum(objective(prevx) ** 2))
+        newE2 = float(np.sum(objective(prevx + direction) ** 2))
+        if prevE2 > newE2:
+            x = prevx + direction
+            if abs(prevE2 - newE2) < func_tol:
+                ret = False
+                break
+        else:
+            x = prevx.copy()
+        E = objective(x)
+        J = jacobian(x)
+        # DT->update (lm.h:43-83): re-evaluates both energies, lambda /= 10 on progress else *= 10
+        if prevE2 > newE2 and np.isfinite(newE2):
+            lam /= 10.0
+        else:
+            lam *= 10.0
+        dampJ = damp(J)
+        if post_iteration is not None and post_iteration(x):
+            ret = True
+            break
+        it += 1
+        prevx = x.copy()
+        if not (it <= max_iterations):
+            ret = False
+            break
+    if stats is not None:
+        stats["factorizations"] = stats.get("factorizations", 0) + LS.count
+        stats["lm_iterations"] = stats.get("lm_iterations", 0) + it
+    return x, ret
+
+
+def naive_poisson(G2p, UFull, F2, fixedIdcs, fixedVals, length):
+    """NaiveIntegration ctor, ir_init.h:173-212: X2F = (G2 UFull).pruned(); E = X2F^T X2F * length;
+    f = X2F^T F2; KKT [[E, C^T], [C, 0]] with C = UFull.rows(fixedIdcs); one sparse LU solve."""
+    UFull = sp.csr_matrix(UFull)
+    X2F = sp.csr_matrix(G2p @ UFull)
+    X2F.eliminate_zeros()
+    E = (X2F.T @ X2F) * length
+    f = X2F.T @ F2
+    C = UFull[np.asarray(fixedIdcs), :]
+    nc = C.shape[0]
+    big = sp.bmat([[E, C.T], [C, sp.csr_matrix((nc, nc))]], format="csc")
+    rhs = np.concatenate([f, np.asarray(fixedVals, np.float64)])
+    sol = spla.splu(big).solve(rhs)
+    return sol[: UFull.shape[1]], X2F
+
+
+def iterative_rounding(fixedIdcs, fixedVals, singularIdcs, integerIdcs, length, UFull, G2p, N, n, nF, seamless,
+                       roundSeams, F2, ni_mode="lm", stats=None):
+    """ir.h:33-113 for localInjectivity = false. Returns dict(success, fullx, x_small, fixedIdcs, fixedVals,
+    n_solves, min_margin).
+
+    ni_mode = "lm"     : the NI stage runs the reference's LM over [x_small; f] (ir.h:82-83, ir_init.h:60-72);
+    ni_mode = "closed" : uses the closed form the linear LM converges to:
+                         x = Poisson solution, f* = (1e8 * length * B x + F2) / (1e8 + 1). Agreement of the two
+                         modes is ~1e-8 relative (the reference's own round-off floor) and is tested on small inputs.
+    """
+    if stats is None:
+        stats = {}
+    UFull = sp.csr_matrix(UFull)
+    G2p = sp.csr_matrix(G2p)
+    F2 = np.asarray(F2, np.float64)
+    fixedIdcs = np.asarray(fixedIdcs)
+    fixedVals = np.asarray(fixedVals, np.float64)
+    cols = UFull.shape[1]
+    nfull = UFull.shape[0]
+    l1 = F2.shape[0]
+
+    XSmall, X2F_nolen = naive_poisson(G2p, UFull, F2, fixedIdcs, fixedVals, length)
+    x0_full = UFull @ XSmall
+    out = dict(success=True, fixedIdcs=[], fixedVals=[], n_solves=0, min_margin=np.inf, x0_full=x0_full, x_poisson=XSmall)
+    if not seamless:  # ir.h:78-81 (localInjectivity false)
+        out.update(fullx=x0_full, x_small=XSmall)
+        return out
+
+    # ---- NI stage (Integration weights ir_init.h:87: wInteg = 10e3, wConst = 10e3, wClose = 1)
+    wInteg, wConst, wClose = 10e3, 10e3, 1.0
+    B = X2F_nolen  # G2 * UFull
+    if ni_mode == "lm":
+        UExt = sp.block_diag([UFull, sp.identity(l1)], format="csr")  # ir_init.h:214-223
+        gInteg = sp.hstack([-length * G2p, sp.identity(l1)]).tocsr() @ UExt * wInteg  # ir_init.h:30-58
+        gClose = sp.hstack([sp.csr_matrix((l1, nfull)), sp.identity(l1)]).tocsr() @ UExt * wClose
+        sel = sp.csr_matrix((np.ones(len(fixedIdcs)), (np.arange(len(fixedIdcs)), fixedIdcs)), shape=(len(fixedIdcs), nfull + l1))
+        gConst = sel @ UExt * wConst
+        Jni = sp.vstack([gInteg, gClose, gConst]).tocsr()
+
+        def obj_ni(xf_):  # ir_init.h:60-72 + ir_common.h:87-93
+            xf = UExt @ xf_
+            x, f = xf[:nfull], xf[nfull:]
+            fInteg = f - length * (G2p @ x)
+            fClose = f - F2
+            fConst = x[fixedIdcs] - fixedVals
+            return np.concatenate([fInteg * wInteg, fClose * wClose, fConst * wConst])
+
+        xf, _ = lm_solve(obj_ni, lambda _x: Jni, np.concatenate([XSmall, F2]), 0.0, 100, 10e-10, 10e-10, stats=stats)
+        X_ = xf[:cols]
+        F2_ = xf[cols:]
+    else:
+        X_ = XSmall
+        F2_ = (1e8 * length * (B @ XSmall) + F2) / (1e8 + 1.0)
+    out["x_ni"] = X_
+    out["F2_ni"] = F2_
+
+    # ---- SI stage (ir_loop.h:102-124: wInteg = 1, wConst = 10e4, wClose = 0.01; X2F = G2 UFull length)
+    wInteg, wConst, wClose = 1.0, 10e4, 0.01
+    X2F = (B * length).tocsr()
+    X2F.eliminate_zeros()
+    integerIdcs = [int(v) for v in integerIdcs]
+    singularIdcs = [int(v) for v in singularIdcs]
+    left = list(integerIdcs if roundSeams else singularIdcs)
+    roundedSingulars = False
+    fixed_i: list[int] = []
+    fixed_v: list[int] = []
+    xCurr = X_.copy()
+    xInit = X_.copy()
+    x_last = None
+    success = True
+    rounded = False
+    gInteg = X2F * wInteg
+    gClose = sp.identity(cols, format="csr") * wClose
+    near_ties = []
+    while left:
+        # initFixedIndices (ir_loop.h:29-74)
+        xPrev = xCurr.copy()
+        X = UFull @ xCurr
+        minDif, minIdx = 3276700.0, -1
+        second = np.inf
+        for i, li in enumerate(left):
+            v = X[li]
+            d = abs(v - np.round(v))
+            if d < minDif:
+                second = minDif
+                minIdx, minDif = i, d
+            elif d < second:
+                second = d
+        idx = left[minIdx]
+        val = int(np.round(X[idx]))
+        frac_part = abs(X[idx] - np.floor(X[idx]) - 0.5)
+        fixed_i.append(idx)
+        fixed_v.append(val)
+        del left[minIdx]
+        if not left and not roundSeams and not roundedSingulars:
+            left = list(integerIdcs)
+            roundedSingulars = True
+        if not (minDif > 10e-7):
+            continue  # ir.h:100
+        out["min_margin"] = min(out["min_margin"], frac_part)
+        near_ties.append((idx, float(minDif), float(second)))
+        rounded = True
+        Cfix = UFull[np.asarray(fixed_i), :]
+        gConst = Cfix * wConst
+        Jsi = sp.vstack([gInteg, gClose, gConst]).tocsr()
+        fv = np.asarray(fixed_v, np.float64)
+        fi = np.asarray(fixed_i)
+
+        def obj_si(xs, xPrev=xPrev, fi=fi, fv=fv):  # ir_loop.h:77-86
+            Xf = UFull @ xs
+            return np.concatenate([(X2F @ xs - F2_) * wInteg, (xs - xPrev) * wClose, (Xf[fi] - fv) * wConst])
+
+        x_last, _ = lm_solve(obj_si, lambda _x, Jsi=Jsi: Jsi, xInit, 0.0, 100, 1e-7, 1e-7, stats=stats)
+        out["n_solves"] += 1
+        # post_checking (ir_loop.h:89-100)
+        fullx = UFull @ x_last
+        mx = max(abs(fullx[i] - np.round(fullx[i])) for i in fixed_i)
+        xCurr = x_last.copy()
+        xInit = x_last.copy()
+        if not (mx <= 10e-7):
+            success = False
+            break
+    out["success"] = success
+    out["fixedIdcs"] = fixed_i
+    out["fixedVals"] = fixed_v
+    out["selection"] = near_ties
+    if rounded:
+        out["fullx"] = UFull @ x_last
+        out["x_small"] = x_last
+    else:
+        out["fullx"] = x0_full  # ir.h:111
+        out["x_small"] = XSmall
+    return out
