@@ -220,8 +220,13 @@ inline EigStats inverse_iteration(Ctx& ctx, OpT& A, Precond<cdouble>* M, const d
         if (ss.status != 0) es.status = ss.status;
         es.launches += ss.launches + 5 + A.launches_per_apply();
     }
+    // Rayleigh quotient of the returned vector: x^H L x with x^H M x = 1
+    A.apply(x, pcg.q(), nullptr, pcg.ws(), s);
+    k_dot_uq<<<grid, kThreads, 0, s>>>(n, x, pcg.q(), pcg.state(), pcg.ws());
+    MK_CHECK_LAUNCH();
+    es.launches += 1 + A.launches_per_apply();
     pcg.fetch_state();
-    es.lambda = pcg.host_state().aux2 / pcg.host_state().aux0;
+    es.lambda = pcg.host_state().pq;
     return es;
 }
 

@@ -93,12 +93,11 @@ def lm_solve(objective, jacobian, x0, lam0=0.0, max_iterations=100, func_tol=10e
     return x, ret
 
 
-def naive_poisson(G2p, UFull, F2, fixedIdcs, fixedVals, length):
-    """NaiveIntegration ctor, ir_init.h:173-212: X2F = (G2 UFull).pruned(); E = X2F^T X2F * length;
+def naive_poisson(X2F, UFull, F2, fixedIdcs, fixedVals, length):
+    """NaiveIntegration ctor, ir_init.h:173-212 with X2F = (G2 UFull).pruned() given: E = X2F^T X2F * length;
     f = X2F^T F2; KKT [[E, C^T], [C, 0]] with C = UFull.rows(fixedIdcs); one sparse LU solve."""
     UFull = sp.csr_matrix(UFull)
-    X2F = sp.csr_matrix(G2p @ UFull)
-    X2F.eliminate_zeros()
+    X2F = sp.csr_matrix(X2F)
     E = (X2F.T @ X2F) * length
     f = X2F.T @ F2
     C = UFull[np.asarray(fixedIdcs), :]
@@ -111,8 +110,18 @@ def naive_poisson(G2p, UFull, F2, fixedIdcs, fixedVals, length):
 
 def iterative_rounding(fixedIdcs, fixedVals, singularIdcs, integerIdcs, length, UFull, G2p, N, n, nF, seamless,
                        roundSeams, F2, ni_mode="lm", stats=None):
-    """ir.h:33-113 for localInjectivity = false. Returns dict(success, fullx, x_small, fixedIdcs, fixedVals,
-    n_solves, min_margin).
+    """ir.h:33-113 for localInjectivity = false, taking G2p = G2 * fullx2Nfunc as the reference does (integ.ipp:72)."""
+    X2F = sp.csr_matrix(sp.csr_matrix(G2p) @ sp.csr_matrix(UFull))  # ir_init.h:173
+    X2F.eliminate_zeros()
+    return iterative_rounding_x2f(fixedIdcs, fixedVals, singularIdcs, integerIdcs, length, UFull, X2F, N, n, seamless, roundSeams, F2,
+                                  ni_mode=ni_mode, stats=stats)
+
+
+def iterative_rounding_x2f(fixedIdcs, fixedVals, singularIdcs, integerIdcs, length, UFull, X2F, N, n, seamless, roundSeams, F2,
+                           ni_mode="lm", stats=None):
+    """The body of ir.h:33-113. G2 enters the algorithm only through X2F = (G2 UFull).pruned() (ir_init.h:173,
+    ir_loop.h:123; gInteg * UExt = [-length X2F | I], ir_init.h:40-55), so X2F is the operator input here.
+    Returns dict(success, fullx, x_small, fixedIdcs, fixedVals, n_solves, min_margin, ...).
 
     ni_mode = "lm"     : the NI stage runs the reference's LM over [x_small; f] (ir.h:82-83, ir_init.h:60-72);
     ni_mode = "closed" : uses the closed form the linear LM converges to:
@@ -122,7 +131,6 @@ def iterative_rounding(fixedIdcs, fixedVals, singularIdcs, integerIdcs, length, 
     if stats is None:
         stats = {}
     UFull = sp.csr_matrix(UFull)
-    G2p = sp.csr_matrix(G2p)
     F2 = np.asarray(F2, np.float64)
     fixedIdcs = np.asarray(fixedIdcs)
     fixedVals = np.asarray(fixedVals, np.float64)
@@ -130,7 +138,7 @@ def iterative_rounding(fixedIdcs, fixedVals, singularIdcs, integerIdcs, length, 
     nfull = UFull.shape[0]
     l1 = F2.shape[0]
 
-    XSmall, X2F_nolen = naive_poisson(G2p, UFull, F2, fixedIdcs, fixedVals, length)
+    XSmall, X2F_nolen = naive_poisson(X2F, UFull, F2, fixedIdcs, fixedVals, length)
     x0_full = UFull @ XSmall
     out = dict(success=True, fixedIdcs=[], fixedVals=[], n_solves=0, min_margin=np.inf, x0_full=x0_full, x_poisson=XSmall)
     if not seamless:  # ir.h:78-81 (localInjectivity false)
@@ -142,8 +150,8 @@ def iterative_rounding(fixedIdcs, fixedVals, singularIdcs, integerIdcs, length, 
     B = X2F_nolen  # G2 * UFull
     if ni_mode == "lm":
         UExt = sp.block_diag([UFull, sp.identity(l1)], format="csr")  # ir_init.h:214-223
-        gInteg = sp.hstack([-length * G2p, sp.identity(l1)]).tocsr() @ UExt * wInteg  # ir_init.h:30-58
-        gClose = sp.hstack([sp.csr_matrix((l1, nfull)), sp.identity(l1)]).tocsr() @ UExt * wClose
+        gInteg = sp.hstack([-length * B, sp.identity(l1)]).tocsr() * wInteg  # ([-length G2 | I] UExt), ir_init.h:30-58
+        gClose = sp.hstack([sp.csr_matrix((l1, cols)), sp.identity(l1)]).tocsr() * wClose
         sel = sp.csr_matrix((np.ones(len(fixedIdcs)), (np.arange(len(fixedIdcs)), fixedIdcs)), shape=(len(fixedIdcs), nfull + l1))
         gConst = sel @ UExt * wConst
         Jni = sp.vstack([gInteg, gClose, gConst]).tocsr()
@@ -151,7 +159,7 @@ def iterative_rounding(fixedIdcs, fixedVals, singularIdcs, integerIdcs, length, 
         def obj_ni(xf_):  # ir_init.h:60-72 + ir_common.h:87-93
             xf = UExt @ xf_
             x, f = xf[:nfull], xf[nfull:]
-            fInteg = f - length * (G2p @ x)
+            fInteg = f - length * (B @ xf_[:cols])  # = f - length G2 x
             fClose = f - F2
             fConst = x[fixedIdcs] - fixedVals
             return np.concatenate([fInteg * wInteg, fClose * wClose, fConst * wConst])
