@@ -33,6 +33,10 @@ class FaceRosyField:
         ctx.check(ctx.L.mk_field_assemble(self.h))
         self.stats = None
 
+    def assemble(self):
+        """Re-run connectionLaplacian + galerkinMassMatrix assembly on the device (drops the cached hierarchy)."""
+        self.ctx.check(self.ctx.L.mk_field_assemble(self.h))
+
     def operator(self):
         """(L, M) as scipy CSR / diagonal, copied back from the device (tests)."""
         rowptr = np.empty(self.nF + 1, np.int32)
@@ -160,19 +164,27 @@ class CholeskyWrapper:
 class IgmProblem:
     """Device-resident IGM problem (mk_igm): A0 = length^2 X2F^T X2F assembled on the device, UFull, F2."""
 
-    def __init__(self, ctx: Context, X2F, UFull, F2, length: float, **opts):
+    def __init__(self, ctx: Context, X2F, UFull, F2, length: float, raw=None, **opts):
+        """`raw` = (x2f_ptr i64, x2f_col i32, x2f_val f64, uf_ptr i64, uf_col i32, uf_val f64, F2 f64): the C-ABI arrays
+        themselves (e.g. pinned buffers), used as they are; X2F / UFull then only give the shapes."""
         self.ctx = ctx
-        X = sp.csr_matrix(X2F, dtype=np.float64)
-        U = sp.csr_matrix(UFull, dtype=np.float64)
-        X.sort_indices()
-        U.sort_indices()
+        if raw is None:
+            X = sp.csr_matrix(X2F, dtype=np.float64)
+            U = sp.csr_matrix(UFull, dtype=np.float64)
+            X.sort_indices()
+            U.sort_indices()
+            a = [np.ascontiguousarray(X.indptr, np.int64), as_i32(X.indices), as_f64(X.data),
+                 np.ascontiguousarray(U.indptr, np.int64), as_i32(U.indices), as_f64(U.data), as_f64(F2)]
+        else:
+            X, U = X2F, UFull
+            a = list(raw)
+            assert a[0].dtype == np.int64 and a[1].dtype == np.int32 and a[2].dtype == np.float64
+            assert a[3].dtype == np.int64 and a[4].dtype == np.int32 and a[5].dtype == np.float64 and a[6].dtype == np.float64
         self.rows, self.cols = X.shape
         self.ufull_rows = U.shape[0]
         assert U.shape[1] == self.cols
         self.h = C.c_void_p()
         o = default_opts(**opts)
-        a = [np.ascontiguousarray(X.indptr, np.int64), as_i32(X.indices), as_f64(X.data),
-             np.ascontiguousarray(U.indptr, np.int64), as_i32(U.indices), as_f64(U.data), as_f64(F2)]
         ctx.check(ctx.L.mk_igm_create(ctx.h, self.rows, self.cols, ptr(a[0]), ptr(a[1]), ptr(a[2]), self.ufull_rows, ptr(a[3]), ptr(a[4]),
                                       ptr(a[5]), ptr(a[6]), float(length), C.byref(o), C.byref(self.h)))
         self.stats = None
