@@ -39,6 +39,8 @@ typedef struct mk_solve_opts {
     int max_iter;      /* per inner solve; default 100000 */
     int precond;       /* 0 = none, 1 = smoothed-aggregation multigrid (default) */
     int use_graph;     /* replay the PCG iteration as a CUDA graph (default 1) */
+    int recycle;       /* eigen-solve: how many earlier solution increments are kept as a Galerkin start space for the next
+                          inverse-iteration solve (default 32, 0 = plain warm start); n * 16 B each on the device */
 } mk_solve_opts;
 
 typedef struct mk_stats {
@@ -122,6 +124,17 @@ int mk_igm_round(mk_igm* g, int n_fixed, const int* fixedIdcs, const double* fix
 /* Copy A0 = length^2 X2F^T X2F (assembled on the device) back as CSR for tests: pass NULLs to query nnz. */
 int mk_igm_get_matrix(mk_igm* g, int64_t* nnz, int* rowptr, int* col, double* val);
 int mk_igm_spmv_bench(mk_igm* g, int reps, int fused_dot, double* ms_per_launch);
+
+/* ---- host-side multigrid set-up, exposed for CPU tests of the hierarchy (no device needed): builds the same
+ * smoothed-aggregation hierarchy the solvers use for a Hermitian (is_complex = 1, interleaved values) or symmetric CSR
+ * matrix. cand = near-kernel candidate (real operators) or NULL. which: 0 = A_l, 1 = P_l (level l -> l+1),
+ * 2 (level_get only) = the smoother's inverse diagonal of level l, written to val. ---- */
+typedef struct mk_amg_host mk_amg_host;
+int mk_amg_host_build(int n, const int* ptr, const int* col, const double* val, int is_complex, const double* cand, mk_amg_host** out);
+int mk_amg_host_num_levels(mk_amg_host* h);
+int mk_amg_host_level_info(mk_amg_host* h, int level, int which, int* rows, int* cols, int64_t* nnz, double* lmax);
+int mk_amg_host_level_get(mk_amg_host* h, int level, int which, int* ptr, int* col, double* val);
+int mk_amg_host_destroy(mk_amg_host* h);
 
 #ifdef __cplusplus
 }

@@ -25,7 +25,7 @@ class MkError(RuntimeError):
 
 
 class SolveOpts(C.Structure):
-    _fields_ = [("tol", C.c_double), ("max_iter", C.c_int), ("precond", C.c_int), ("use_graph", C.c_int)]
+    _fields_ = [("tol", C.c_double), ("max_iter", C.c_int), ("precond", C.c_int), ("use_graph", C.c_int), ("recycle", C.c_int)]
 
 
 class Stats(C.Structure):
@@ -85,6 +85,11 @@ def lib() -> C.CDLL:
         L.mk_igm_round.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp, ip, vp, vp, C.POINTER(Stats)]
         L.mk_igm_get_matrix.argtypes = [vp, i64p, vp, vp, vp]
         L.mk_igm_spmv_bench.argtypes = [vp, C.c_int, C.c_int, dp]
+        L.mk_amg_host_build.argtypes = [C.c_int, vp, vp, vp, C.c_int, vp, C.POINTER(vp)]
+        L.mk_amg_host_num_levels.argtypes = [vp]
+        L.mk_amg_host_level_info.argtypes = [vp, C.c_int, C.c_int, ip, ip, i64p, dp]
+        L.mk_amg_host_level_get.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
+        L.mk_amg_host_destroy.argtypes = [vp]
         _LIB = L
     return _LIB
 
@@ -144,3 +149,42 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+def amg_host_hierarchy(A, cand=None):
+    """Builds the solvers' smoothed-aggregation hierarchy on the host (no device) and returns
+    [(A_l, P_l or None, lmax_l, dinv_l)] (scipy CSR matrices, smoother diagonal) -- for CPU tests of the set-up."""
+    import scipy.sparse as sp
+    A = sp.csr_matrix(A)
+    A.sort_indices()
+    cx = np.iscomplexobj(A.data)
+    dt = np.complex128 if cx else np.float64
+    L = lib()
+    h = C.c_void_p()
+    val = np.ascontiguousarray(A.data, dt)
+    c = as_f64(cand) if cand is not None else None
+    rc = L.mk_amg_host_build(A.shape[0], ptr(as_i32(A.indptr)), ptr(as_i32(A.indices)), ptr(val), int(cx), ptr(c), C.byref(h))
+    if rc != MK_OK:
+        raise MkError(rc, "mk_amg_host_build")
+    out = []
+    try:
+        nl = L.mk_amg_host_num_levels(h)
+        for l in range(nl):
+            mats = []
+            lm = C.c_double()
+            for which in (0, 1):
+                r, cc, z = C.c_int(), C.c_int(), C.c_int64()
+                if L.mk_amg_host_level_info(h, l, which, C.byref(r), C.byref(cc), C.byref(z), C.byref(lm)) != MK_OK:
+                    mats.append(None)
+                    continue
+                p_ = np.empty(r.value + 1, np.int32)
+                c_ = np.empty(z.value, np.int32)
+                v_ = np.empty(z.value, dt)
+                L.mk_amg_host_level_get(h, l, which, ptr(p_), ptr(c_), ptr(v_))
+                mats.append(sp.csr_matrix((v_, c_, p_), shape=(r.value, cc.value)))
+            dinv = np.empty(mats[0].shape[0], dt)
+            L.mk_amg_host_level_get(h, l, 2, None, None, ptr(dinv))
+            out.append((mats[0], mats[1], lm.value, dinv))
+    finally:
+        L.mk_amg_host_destroy(h)
+    return out

@@ -36,15 +36,21 @@ struct AmgParams {
     int cheb_degree = 2;       // SpMVs per pre- and per post-smoothing
     double cheb_ratio = 8.0;   // smoother targets [lmax / ratio, lmax] of D^{-1} A
     double omega_scale = 4.0 / 3.0;  // prolongator smoothing omega = omega_scale / rho(D^{-1}A)
+    int dense_row = 64;        // fine-level rows longer than this are "dense dofs": never aggregated with others, carried
+                               // as singletons to the coarsest level (solved exactly there), l1-scaled in the smoother
 };
 
-inline AmgParams amg_params_from_env() {
+// real_op: the real symmetric IGM / LM operators use a strength threshold (drops weak and wrong-signed cotan couplings
+// from the aggregation graph); the complex face operator has unit-modulus off-diagonals and keeps theta = 0.
+inline AmgParams amg_params_from_env(bool real_op = false) {
     AmgParams p;
+    if (real_op) p.theta = 0.1;
     if (const char* e = getenv("MK_AMG_DEG")) p.cheb_degree = atoi(e);
     if (const char* e = getenv("MK_AMG_RATIO")) p.cheb_ratio = atof(e);
     if (const char* e = getenv("MK_AMG_THETA")) p.theta = atof(e);
     if (const char* e = getenv("MK_AMG_COARSE")) p.coarse_max = atoi(e);
     if (const char* e = getenv("MK_AMG_OMEGA")) p.omega_scale = atof(e);
+    if (const char* e = getenv("MK_AMG_DENSE")) p.dense_row = atoi(e);
     return p;
 }
 
@@ -87,16 +93,20 @@ inline S unit_phase(S v) {
 }
 
 // Greedy root-plus-neighbours aggregation (Vanek). Returns the aggregate id per node and the tentative value per node.
+// `dense` (may be empty): rows that must stay alone. They are skipped by all passes, ignored as neighbours, and appended
+// as singleton aggregates at the end; their coarse ids are returned in `dense_coarse`.
 template <class S>
-inline int aggregate(const HostCsr<S>& A, double theta, const std::vector<S>* cand, std::vector<int>& agg, std::vector<S>& tval) {
+inline int aggregate(const HostCsr<S>& A, double theta, const std::vector<S>* cand, const std::vector<char>& dense, std::vector<int>& agg,
+                     std::vector<S>& tval, std::vector<int>& dense_coarse) {
     const int n = A.rows;
+    const bool has_dense = !dense.empty();
     std::vector<double> dabs(n, 0.0);
     for (int i = 0; i < n; i++)
         for (int k = A.ptr[i]; k < A.ptr[i + 1]; k++)
             if (A.col[k] == i) dabs[i] = std::abs(A.val[k]);
     auto strong = [&](int i, int k) {
         const int j = A.col[k];
-        if (j == i) return false;
+        if (j == i || (has_dense && dense[j])) return false;
         const double a = std::abs(A.val[k]);
         return a > 0 && a * a >= theta * theta * dabs[i] * dabs[j];
     };
@@ -104,8 +114,9 @@ inline int aggregate(const HostCsr<S>& A, double theta, const std::vector<S>* ca
     tval.assign(n, S(0));
     int nagg = 0;
     // pass 1: roots whose whole strong neighbourhood is free
+    auto skip = [&](int i) { return agg[i] != -1 || (has_dense && dense[i]); };
     for (int i = 0; i < n; i++) {
-        if (agg[i] != -1) continue;
+        if (skip(i)) continue;
         bool ok = true, any = false;
         for (int k = A.ptr[i]; k < A.ptr[i + 1] && ok; k++)
             if (strong(i, k)) { any = true; if (agg[A.col[k]] != -1) ok = false; }
@@ -123,7 +134,7 @@ inline int aggregate(const HostCsr<S>& A, double theta, const std::vector<S>* ca
     // pass 2: attach the rest to the strongest neighbouring pass-1 aggregate
     std::vector<int> agg1 = agg;
     for (int i = 0; i < n; i++) {
-        if (agg[i] != -1) continue;
+        if (skip(i)) continue;
         double best = -1;
         int bk = -1;
         for (int k = A.ptr[i]; k < A.ptr[i + 1]; k++)
@@ -136,7 +147,7 @@ inline int aggregate(const HostCsr<S>& A, double theta, const std::vector<S>* ca
     }
     // pass 3: leftovers (isolated or surrounded by pass-2 nodes) form their own aggregates
     for (int i = 0; i < n; i++) {
-        if (agg[i] != -1) continue;
+        if (skip(i)) continue;
         agg[i] = nagg;
         tval[i] = S(1);
         for (int k = A.ptr[i]; k < A.ptr[i + 1]; k++)
@@ -147,6 +158,10 @@ inline int aggregate(const HostCsr<S>& A, double theta, const std::vector<S>* ca
             }
         nagg++;
     }
+    dense_coarse.clear();
+    if (has_dense)
+        for (int i = 0; i < n; i++)
+            if (dense[i]) { agg[i] = nagg; tval[i] = S(1); dense_coarse.push_back(nagg); nagg++; }
     if (cand) tval = *cand;  // global-candidate mode: tentative values are the candidate itself
     return nagg;
 }
@@ -154,18 +169,40 @@ inline int aggregate(const HostCsr<S>& A, double theta, const std::vector<S>* ca
 template <class S>
 inline std::vector<AmgHostLevel<S>> build_hierarchy(HostCsr<S> A, std::vector<S> cand, bool use_cand, const AmgParams& prm) {
     std::vector<AmgHostLevel<S>> lv;
+    // dense dofs (e.g. the seam-translation / constraint-kernel columns of the IGM operator: a few rows with thousands of
+    // entries) are detected once on the finest level
+    std::vector<char> dense;
+    int n_dense = 0;
+    if (prm.dense_row > 0 && A.rows > prm.coarse_max) {
+        for (int i = 0; i < A.rows; i++)
+            if (A.ptr[i + 1] - A.ptr[i] > prm.dense_row) {
+                if (dense.empty()) dense.assign(A.rows, 0);
+                dense[i] = 1;
+                n_dense++;
+            }
+    }
     while (true) {
         AmgHostLevel<S> L;
         L.A = std::move(A);
         const int n = L.A.rows;
         std::vector<S> d = diagonal(L.A);
         L.dinv.resize(n);
-        for (int i = 0; i < n; i++) L.dinv[i] = std::abs(d[i]) > 0 ? S(1) / d[i] : S(1);
+#pragma omp parallel for schedule(static)
+        for (int i = 0; i < n; i++) {
+            if (n_dense && dense[i]) {
+                // l1 scaling: keeps rho(D^{-1}A) (hence the Chebyshev interval and the prolongator damping) governed by the sparse rows
+                double l1 = 0;
+                for (int k = L.A.ptr[i]; k < L.A.ptr[i + 1]; k++) l1 += std::abs(L.A.val[k]);
+                L.dinv[i] = l1 > 0 ? S(1.0 / l1) : S(1);
+            } else {
+                L.dinv[i] = std::abs(d[i]) > 0 ? S(1) / d[i] : S(1);
+            }
+        }
         L.lmax = 1.1 * estimate_rho_dinvA(L.A, L.dinv);
-        if (n <= prm.coarse_max || (int)lv.size() + 1 >= prm.max_levels) { lv.push_back(std::move(L)); break; }
-        std::vector<int> agg;
+        if (n - n_dense <= prm.coarse_max || (int)lv.size() + 1 >= prm.max_levels) { lv.push_back(std::move(L)); break; }
+        std::vector<int> agg, dense_coarse;
         std::vector<S> tv;
-        const int nc = aggregate(L.A, prm.theta, use_cand ? &cand : nullptr, agg, tv);
+        const int nc = aggregate(L.A, prm.theta, use_cand ? &cand : nullptr, dense, agg, tv, dense_coarse);
         if (nc >= n * 0.8 || nc == 0) { lv.push_back(std::move(L)); break; }  // stagnation: stop here
         // normalise the tentative columns; the column norms are the coarse candidate
         std::vector<double> nrm(nc, 0.0);
@@ -213,6 +250,10 @@ inline std::vector<AmgHostLevel<S>> build_hierarchy(HostCsr<S> A, std::vector<S>
         HostCsr<S> AP = matmul(L.A, L.P);
         A = matmul(L.R, AP);
         cand = std::move(ccand);
+        if (n_dense) {
+            dense.assign(nc, 0);
+            for (int c : dense_coarse) dense[c] = 1;
+        }
         lv.push_back(std::move(L));
     }
     return lv;

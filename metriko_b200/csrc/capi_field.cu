@@ -21,6 +21,7 @@ struct mk_field {
     std::unique_ptr<Pcg<cdouble>> pcg;
     std::unique_ptr<AmgPrecond<cdouble>> amg;
     DevBuf<cdouble> u, x, b;
+    RecycleSpace rec;
     bool has_solution = false;
 };
 
@@ -31,6 +32,7 @@ void mk_default_opts(mk_solve_opts* o) {
     o->max_iter = 100000;
     o->precond = 1;
     o->use_graph = 1;
+    o->recycle = 32;
 }
 
 int mk_device_count(void) {
@@ -184,8 +186,9 @@ static int field_solve_impl(mk_field* f, const cdouble* u0_dev, int n_iter, cons
     auto t1 = std::chrono::steady_clock::now();
     MK_CUDA(cudaMemcpyAsync(f->u.p, u0_dev, sizeof(cdouble) * f->nF, cudaMemcpyDeviceToDevice, s));
     MK_CUDA(cudaMemcpyAsync(f->x.p, u0_dev, sizeof(cdouble) * f->nF, cudaMemcpyDeviceToDevice, s));
+    f->rec.init(f->nF, std::min(o.recycle, n_iter), s);
     EigStats es = inverse_iteration(f->ctx->c, *f->op, o.precond == 1 ? f->amg.get() : nullptr, f->S.mass.p, f->nF, f->u.p, f->x.p,
-                                    f->b.p, *f->pcg, n_iter, o.tol, o.max_iter, o.use_graph != 0);
+                                    f->b.p, *f->pcg, n_iter, o.tol, o.max_iter, o.use_graph != 0, &f->rec);
     MK_CUDA(cudaStreamSynchronize(s));
     auto t2 = std::chrono::steady_clock::now();
     f->has_solution = true;

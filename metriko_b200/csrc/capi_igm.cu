@@ -62,7 +62,9 @@ extern "C" int mk_solve_smallest_eig_csc(mk_ctx* ctx, int n, const int* L_outer,
     MK_CUDA(cudaStreamSynchronize(s));
     const double setup_ms = ms_since(t0);
     auto t1 = hclock::now();
-    EigStats es = inverse_iteration(ctx->c, op, amg.get(), dmass.p, n, u.p, xx.p, b.p, pcg, n_iter, o.tol, o.max_iter, o.use_graph != 0);
+    RecycleSpace rec;
+    rec.init(n, std::min(o.recycle, n_iter), s);
+    EigStats es = inverse_iteration(ctx->c, op, amg.get(), dmass.p, n, u.p, xx.p, b.p, pcg, n_iter, o.tol, o.max_iter, o.use_graph != 0, &rec);
     xx.download((cdouble*)x, n, s);
     MK_CUDA(cudaStreamSynchronize(s));
     if (stats) {
@@ -96,19 +98,6 @@ struct mk_spd {
     double setup_ms = 0;
 };
 
-// near-kernel candidate for the real operators: constants relaxed by a few Jacobi sweeps on A b = 0
-static std::vector<double> smoothed_constant_candidate(const HostCsr<double>& A, int sweeps) {
-    const int n = A.rows;
-    std::vector<double> b(n, 1.0), Ab, d = diagonal(A);
-    for (int it = 0; it < sweeps; it++) {
-        matvec(A, b, Ab);
-#pragma omp parallel for
-        for (int i = 0; i < n; i++)
-            if (d[i] != 0) b[i] -= (2.0 / 3.0) * Ab[i] / d[i];
-    }
-    return b;
-}
-
 extern "C" int mk_spd_factorize(mk_ctx* ctx, int n, const int* outer, const int* inner, const double* values, const mk_solve_opts* opts,
                                 mk_spd** out) {
     if (!ctx || !out || n <= 0 || !outer || !inner || !values) return MK_ERR_ARG;
@@ -130,10 +119,9 @@ extern "C" int mk_spd_factorize(mk_ctx* ctx, int n, const int* outer, const int*
     h->pcg = std::make_unique<Pcg<double>>(n, s);
     h->b.alloc(n);
     h->x.alloc(n);
-    if (h->o.precond == 1) {
-        std::vector<double> cand = smoothed_constant_candidate(A, 6);
-        h->amg = build_amg<double>(s, std::move(A), std::move(cand), true, h->op.get(), amg_params_from_env());
-    }
+    // tentative prolongator by sign transport along the matrix' own couplings (amg.cuh): the constants are NOT a near-kernel
+    // of these operators across seams (u, v rotate by k 90 degrees there), so no global candidate is used
+    if (h->o.precond == 1) h->amg = build_amg<double>(s, std::move(A), {}, false, h->op.get(), amg_params_from_env(true));
     MK_CUDA(cudaStreamSynchronize(s));
     h->setup_ms = ms_since(t0);
     *out = h.release();
@@ -257,8 +245,7 @@ extern "C" int mk_igm_create(mk_ctx* ctx, int rows, int cols, const int64_t* x2f
         for (int i = 0; i < As.rows; i++)
             for (int k = As.ptr[i]; k < As.ptr[i + 1]; k++)
                 if (As.col[k] == i) As.val[k] += 1e-4;
-        std::vector<double> cand = smoothed_constant_candidate(As, 6);
-        g->amg = build_amg<double>(s, std::move(As), std::move(cand), true, g->opA.get(), amg_params_from_env());
+        g->amg = build_amg<double>(s, std::move(As), {}, false, g->opA.get(), amg_params_from_env(true));
     }
     MK_CUDA(cudaStreamSynchronize(s));
     g->setup_ms = ms_since(t0);

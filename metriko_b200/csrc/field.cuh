@@ -184,6 +184,96 @@ static __global__ void __launch_bounds__(kThreads) k_decode(int nF, int N, const
     }
 }
 
+// ---- solution recycling across the outer iterations (Galerkin projection onto earlier solution increments) ----
+// The right-hand sides M u_k of successive inverse-iteration steps converge to the span of the few slowest eigenvectors,
+// which earlier solves already contain. E holds L-orthonormal increments e_j (e_i^H L e_j = delta_ij), so the
+// energy-optimal start in span(E) is x0 = sum_j (e_j^H b) e_j and only b - L x0 is left for PCG.
+constexpr int kRecycleChunk = 8;
+
+// coef[j0 + j] = <E_{j0+j}, v> (complex, conj on the basis vector) for j < cnt <= kRecycleChunk
+static __global__ void __launch_bounds__(kThreads) k_multi_dot(int n, int j0, int cnt, const cdouble* __restrict__ E, const cdouble* __restrict__ v,
+                                                        cdouble* __restrict__ coef, ReduceWs ws) {
+    __shared__ double red[32];
+    double acc[2 * kRecycleChunk];
+#pragma unroll
+    for (int j = 0; j < 2 * kRecycleChunk; j++) acc[j] = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const cdouble vi = ldc_nc(v + i);
+#pragma unroll
+        for (int j = 0; j < kRecycleChunk; j++)
+            if (j < cnt) {
+                const cdouble e = ldc_nc(E + (size_t)(j0 + j) * n + i);
+                acc[2 * j] += e.x * vi.x + e.y * vi.y;
+                acc[2 * j + 1] += e.x * vi.y - e.y * vi.x;
+            }
+    }
+    grid_reduce<2 * kRecycleChunk>(acc, ws.partials, ws.ticket, red, [&](const double* s) {
+        for (int j = 0; j < cnt; j++) coef[j0 + j] = make_c(s[2 * j], s[2 * j + 1]);
+    });
+}
+
+// x (+)= sign * sum_{j < cnt} coef[j0 + j] E_{j0+j}
+static __global__ void __launch_bounds__(kThreads) k_multi_axpy(int n, int j0, int cnt, const cdouble* __restrict__ E, const cdouble* __restrict__ coef,
+                                                         cdouble* __restrict__ x, double sign, int accumulate) {
+    __shared__ cdouble c[kRecycleChunk];
+    if (threadIdx.x < cnt) c[threadIdx.x] = coef[j0 + threadIdx.x];
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        cdouble a = accumulate ? ldc(x + i) : make_c(0.0, 0.0);
+#pragma unroll
+        for (int j = 0; j < kRecycleChunk; j++)
+            if (j < cnt) {
+                const cdouble e = ldc_nc(E + (size_t)(j0 + j) * n + i);
+                a = ST<cdouble>::fma_(make_c(sign * c[j].x, sign * c[j].y), e, a);
+            }
+        stc(x + i, a);
+    }
+}
+
+// e = x - e (the slot holds the start vector x0 on entry)
+static __global__ void __launch_bounds__(kThreads) k_increment(int n, const cdouble* __restrict__ x, cdouble* __restrict__ e) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) stc(e + i, ldc_nc(x + i) - ldc(e + i));
+}
+
+// e *= 1 / sqrt(<e, L e>) with <e, L e> in st->pq; a vanishing or invalid norm zeroes the slot (it then contributes nothing)
+static __global__ void __launch_bounds__(kThreads) k_scale_energy(int n, cdouble* __restrict__ e, const PcgState* st, double floor2) {
+    const double p = st->pq;
+    const double s = (p > floor2 && p == p) ? rsqrt(p) : 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const cdouble v = ldc(e + i);
+        stc(e + i, make_c(v.x * s, v.y * s));
+    }
+}
+
+struct RecycleSpace {
+    int n = 0, cap = 0, count = 0;  // `count` of `cap` slots filled
+    DevBuf<cdouble> E, coef;
+    DevBuf<double> partials;
+    DevBuf<unsigned int> ticket;
+    void init(int n_, int cap_, cudaStream_t s) {
+        n = n_; cap = cap_; count = 0;
+        if (cap <= 0) return;
+        if (E.n != (size_t)n * cap) E.alloc((size_t)n * cap);
+        if (!coef.p) coef.alloc(cap);
+        if (!partials.p) { partials.alloc((size_t)kMaxPartials * 2 * kRecycleChunk); ticket.alloc(1); ticket.zero(s); }
+    }
+    ReduceWs ws() { return ReduceWs{partials.p, ticket.p}; }
+    int valid() const { return count < cap ? count : cap; }
+    // coef = E^H v over the filled slots
+    int dots(const cdouble* v, int grid, cudaStream_t s) {
+        int l = 0;
+        for (int j0 = 0; j0 < valid(); j0 += kRecycleChunk, l++)
+            k_multi_dot<<<grid, kThreads, 0, s>>>(n, j0, std::min(kRecycleChunk, valid() - j0), E.p, v, coef.p, ws());
+        return l;
+    }
+    int combine(cdouble* x, double sign, bool accumulate, int grid, cudaStream_t s) {
+        int l = 0;
+        for (int j0 = 0; j0 < valid(); j0 += kRecycleChunk, l++)
+            k_multi_axpy<<<grid, kThreads, 0, s>>>(n, j0, std::min(kRecycleChunk, valid() - j0), E.p, coef.p, x, sign, (accumulate || j0 > 0) ? 1 : 0);
+        return l;
+    }
+};
+
 struct EigStats {
     int outer = 0;
     long inner_total = 0;
@@ -198,18 +288,52 @@ struct EigStats {
 // (the reference draws VecXc::Random from an unseeded std::rand).
 template <class OpT>
 inline EigStats inverse_iteration(Ctx& ctx, OpT& A, Precond<cdouble>* M, const double* mass, int n, cdouble* u, cdouble* x, cdouble* b,
-                                  Pcg<cdouble>& pcg, int n_iter, double tol, int maxit, bool use_graph) {
+                                  Pcg<cdouble>& pcg, int n_iter, double tol, int maxit, bool use_graph, RecycleSpace* rec = nullptr) {
     EigStats es;
     cudaStream_t s = ctx.stream;
     pcg.bind(&A, M, nullptr);
     const int grid = pcg.grid();
+    int hint = 0;
     for (int it = 0; it < n_iter; it++) {
+        const bool recycle = rec && rec->cap > 0;
+        const bool add = recycle && rec->count < rec->cap;  // once the space is full it is frozen (late increments are ~0 anyway)
+        cdouble* slot = add ? rec->E.p + (size_t)rec->count * n : nullptr;
         k_mass_rhs<<<grid, kThreads, 0, s>>>(n, mass, u, b, pcg.state(), pcg.ws());
-        A.apply(u, pcg.q(), nullptr, pcg.ws(), s);
-        k_dot_uq<<<grid, kThreads, 0, s>>>(n, u, pcg.q(), pcg.state(), pcg.ws());
-        k_warm_start<<<grid, kThreads, 0, s>>>(n, u, b, pcg.q(), x, pcg.r(), pcg.state(), pcg.ws(), tol * tol, maxit);
+        if (recycle && rec->valid() > 0) {
+            // x0 = sum_j (e_j^H b) e_j ; r = b - L x0
+            es.launches += rec->dots(b, grid, s);
+            es.launches += rec->combine(x, 1.0, false, grid, s);
+            A.apply(x, pcg.q(), nullptr, pcg.ws(), s);
+            pcg.launch_residual(b, tol * tol, maxit, 0);
+            if (add) MK_CUDA(cudaMemcpyAsync(slot, x, sizeof(cdouble) * n, cudaMemcpyDeviceToDevice, s));
+            es.launches += 1 + A.launches_per_apply();
+        } else {
+            A.apply(u, pcg.q(), nullptr, pcg.ws(), s);
+            k_dot_uq<<<grid, kThreads, 0, s>>>(n, u, pcg.q(), pcg.state(), pcg.ws());
+            k_warm_start<<<grid, kThreads, 0, s>>>(n, u, b, pcg.q(), x, pcg.r(), pcg.state(), pcg.ws(), tol * tol, maxit);
+            if (add) MK_CUDA(cudaMemsetAsync(slot, 0, sizeof(cdouble) * n, s));  // first increment = the solution itself
+            es.launches += 2 + A.launches_per_apply();
+        }
         MK_CHECK_LAUNCH();
-        SolveStats ss = pcg.solve(b, x, tol, maxit, true, 16, use_graph);
+        SolveStats ss = pcg.solve(b, x, tol, maxit, true, 16, use_graph, hint);
+        hint = ss.iterations + 1;
+        if (add) {
+            // new basis vector: e = x - x0, L-orthogonalised against the others (it already is, up to the solve tolerance),
+            // normalised in the energy norm with an explicit L e so that the Galerkin relation stays exact to round-off
+            k_increment<<<grid, kThreads, 0, s>>>(n, x, slot);
+            A.apply(slot, pcg.q(), nullptr, pcg.ws(), s);
+            es.launches += 1 + A.launches_per_apply();
+            if (rec->valid() > 0) {
+                es.launches += rec->dots(pcg.q(), grid, s);
+                es.launches += rec->combine(slot, -1.0, true, grid, s);
+                A.apply(slot, pcg.q(), nullptr, pcg.ws(), s);
+                es.launches += A.launches_per_apply();
+            }
+            k_dot_uq<<<grid, kThreads, 0, s>>>(n, slot, pcg.q(), pcg.state(), pcg.ws());
+            k_scale_energy<<<grid, kThreads, 0, s>>>(n, slot, pcg.state(), 0.0);
+            es.launches += 2;
+            rec->count++;
+        }
         k_mnorm2<<<grid, kThreads, 0, s>>>(n, mass, x, pcg.state(), pcg.ws());
         k_normalize_copy<<<grid, kThreads, 0, s>>>(n, x, u, pcg.state());
         MK_CHECK_LAUNCH();
@@ -218,7 +342,7 @@ inline EigStats inverse_iteration(Ctx& ctx, OpT& A, Precond<cdouble>* M, const d
         es.inner_max = std::max(es.inner_max, ss.iterations);
         es.relres_max = std::max(es.relres_max, ss.relres);
         if (ss.status != 0) es.status = ss.status;
-        es.launches += ss.launches + 5 + A.launches_per_apply();
+        es.launches += ss.launches + 3;
     }
     // Rayleigh quotient of the returned vector: x^H L x with x^H M x = 1
     A.apply(x, pcg.q(), nullptr, pcg.ws(), s);

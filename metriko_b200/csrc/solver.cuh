@@ -220,7 +220,10 @@ public:
     // Solve A x = b starting from the x passed in. If residual_ready, r() already holds b - A x and the state
     // (rr, bnorm2, thresh, iter, maxit, done) was set by k_residual.
     // With a projector the right-hand side is projected in place first (r = P b - P A x stays in the feasible subspace).
-    SolveStats solve(T* b, T* x, double tol, int maxit, bool residual_ready, int chunk = 16, bool use_graph = true) {
+    // `hint`: expected iteration count (e.g. that of the previous, similar solve) -- sizes the first batch of iterations
+    // issued before the host looks at the state; later batches are `chunk` long. Iterations issued after convergence
+    // are no-ops on the device (every kernel returns on st->done) but still cost launch latency.
+    SolveStats solve(T* b, T* x, double tol, int maxit, bool residual_ready, int chunk = 16, bool use_graph = true, int hint = 0) {
         SolveStats out;
         long launches = 0;
         const double tol2 = tol * tol;
@@ -234,11 +237,13 @@ public:
         for (int attempt = 0; attempt < 4; attempt++) {
             start_direction();
             launches += 1 + (M_ ? M_->launches_per_apply() : 0);
+            int batch = hint > 0 ? std::min(std::max(hint, 1), 4 * chunk) : chunk;
             while (true) {
-                for (int c = 0; c < chunk; c++) iteration(x, use_graph);
-                launches += (long)chunk * launches_per_iteration();
+                for (int c = 0; c < batch; c++) iteration(x, use_graph);
+                launches += (long)batch * launches_per_iteration();
                 fetch_state();
                 if (h_st_->done) break;
+                batch = hint > 0 ? std::max(2, chunk / 4) : chunk;
             }
             // true residual check (recurrence residuals drift at the 1e-10 level)
             A_->apply(x, q_.p, nullptr, ws(), stream_);

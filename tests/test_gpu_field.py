@@ -33,12 +33,15 @@ def test_assembly_and_spmv_match_oracle(ctx, ico4, N):
     assert np.abs(y - L @ x).max() < 1e-13 * np.abs(x).max() * 8
 
 
+@pytest.mark.parametrize("recycle", [0, 8, 32])
 @pytest.mark.parametrize("precond", [0, 1])
 @pytest.mark.parametrize("name", ["sphere_ico3", "torus_24x16", "sphere_octa4_roundseams"])
-def test_field_matches_golden(ctx, name, precond):
+def test_field_matches_golden(ctx, name, precond, recycle):
+    """recycle = size of the Galerkin start space built from earlier solution increments (0: plain warm start); the
+    result must not depend on it beyond the inner tolerance."""
     g = load_golden(name)
     F = _mk(ctx, g)
-    z = F.solveSmallestEig(g["u0"], 50, precond=precond)
+    z = F.solveSmallestEig(g["u0"], 50, precond=precond, recycle=recycle)
     assert field_angle_error(z, g["z50"], 4).max() < ANGLE_TOL
     assert F.stats["relres_max"] <= 1e-10 * 1.001 and F.stats["status"] == 0
     assert abs(F.stats["lambda_"] - float(g["lam"])) < 1e-6
@@ -115,3 +118,8 @@ def test_full_size_properties(ctx):
     # residual eps * kappa at this size, so the comparison goes the other way)
     z2 = F.solveSmallestEig(u0, 50, tol=1e-9)
     assert field_angle_error(z, z2, 4).max() < ANGLE_TOL
+    # recycling earlier solves only changes the PCG start vectors: same field, far fewer inner iterations
+    z3 = F.solveSmallestEig(u0, 50, recycle=0)
+    st3 = dict(F.stats)
+    assert field_angle_error(z, z3, 4).max() < ANGLE_TOL
+    assert st["inner_iterations"] < 0.6 * st3["inner_iterations"]
