@@ -19,7 +19,7 @@ LIB_HOST = os.path.join(HOSTGLUE, "libmetriko_hostglue.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CUDA_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp", "-Xcompiler", "-O3",
+    "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp", "-Xcompiler", "-O3", "-Xcompiler", "-fcx-limited-range",
 ]
 
 

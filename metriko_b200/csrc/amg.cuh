@@ -169,6 +169,7 @@ inline int aggregate(const HostCsr<S>& A, double theta, const std::vector<S>* ca
 template <class S>
 inline std::vector<AmgHostLevel<S>> build_hierarchy(HostCsr<S> A, std::vector<S> cand, bool use_cand, const AmgParams& prm) {
     std::vector<AmgHostLevel<S>> lv;
+    StageTimer tm("build_hierarchy");
     // dense dofs (e.g. the seam-translation / constraint-kernel columns of the IGM operator: a few rows with thousands of
     // entries) are detected once on the finest level
     std::vector<char> dense;
@@ -181,6 +182,7 @@ inline std::vector<AmgHostLevel<S>> build_hierarchy(HostCsr<S> A, std::vector<S>
                 n_dense++;
             }
     }
+    tm.lap("dense detection");
     while (true) {
         AmgHostLevel<S> L;
         L.A = std::move(A);
@@ -198,11 +200,14 @@ inline std::vector<AmgHostLevel<S>> build_hierarchy(HostCsr<S> A, std::vector<S>
                 L.dinv[i] = std::abs(d[i]) > 0 ? S(1) / d[i] : S(1);
             }
         }
+        tm.lap("dinv");
         L.lmax = 1.1 * estimate_rho_dinvA(L.A, L.dinv);
+        tm.lap("rho estimate");
         if (n - n_dense <= prm.coarse_max || (int)lv.size() + 1 >= prm.max_levels) { lv.push_back(std::move(L)); break; }
         std::vector<int> agg, dense_coarse;
         std::vector<S> tv;
         const int nc = aggregate(L.A, prm.theta, use_cand ? &cand : nullptr, dense, agg, tv, dense_coarse);
+        tm.lap("aggregate");
         if (nc >= n * 0.8 || nc == 0) { lv.push_back(std::move(L)); break; }  // stagnation: stop here
         // normalise the tentative columns; the column norms are the coarse candidate
         std::vector<double> nrm(nc, 0.0);
@@ -223,6 +228,7 @@ inline std::vector<AmgHostLevel<S>> build_hierarchy(HostCsr<S> A, std::vector<S>
         T.ptr[n] = n;
         // P = (I - omega D^{-1} A) T
         HostCsr<S> AT = matmul(L.A, T);
+        tm.lap("A T");
         const double omega = prm.omega_scale / (L.lmax / 1.1);
         {
             // merge T (one entry per row) into -omega dinv AT
@@ -246,9 +252,13 @@ inline std::vector<AmgHostLevel<S>> build_hierarchy(HostCsr<S> A, std::vector<S>
                 P.ptr[i + 1] = (int)P.col.size();
             }
         }
+        tm.lap("P");
         L.R = transpose(L.P, true);
+        tm.lap("R = P^H");
         HostCsr<S> AP = matmul(L.A, L.P);
+        tm.lap("A P");
         A = matmul(L.R, AP);
+        tm.lap("R (A P)");
         cand = std::move(ccand);
         if (n_dense) {
             dense.assign(nc, 0);
@@ -468,7 +478,9 @@ inline std::unique_ptr<AmgPrecond<T>> build_amg(cudaStream_t s, HostCsr<typename
     amg->prm = prm;
     amg->fine_op = fine_op;
     const double nnz0 = (double)A.nnz(), n0 = (double)A.rows;
+    StageTimer tm("build_amg");
     std::vector<AmgHostLevel<S>> H = build_hierarchy<S>(std::move(A), std::move(cand), use_cand, prm);
+    tm.lap("hierarchy (host)");
     amg->lv.resize(H.size());
     double nnz_sum = 0, n_sum = 0;
     for (size_t l = 0; l < H.size(); l++) {
@@ -488,6 +500,7 @@ inline std::unique_ptr<AmgPrecond<T>> build_amg(cudaStream_t s, HostCsr<typename
         if (l > 0) { D.x.alloc(D.n); D.b.alloc(D.n); }
         MK_CUDA(cudaStreamSynchronize(s));
     }
+    tm.lap("upload levels");
     amg->op_complexity = nnz_sum / nnz0;
     amg->grid_complexity = n_sum / n0;
     const AmgHostLevel<S>& last = H.back();
@@ -498,6 +511,12 @@ inline std::unique_ptr<AmgPrecond<T>> build_amg(cudaStream_t s, HostCsr<typename
         amg->coarse_inv.upload((const T*)inv.data(), inv.size(), s);
         MK_CUDA(cudaStreamSynchronize(s));
         amg->coarse_dense = true;
+        tm.lap("coarse dense inverse");
+    }
+    if (tm.on) {
+        fprintf(stderr, "[mk] build_amg: levels");
+        for (auto& l : H) fprintf(stderr, " %d(%.1f)", l.A.rows, (double)l.A.nnz() / l.A.rows);
+        fprintf(stderr, " op_cx %.2f grid_cx %.2f\n", amg->op_complexity, amg->grid_complexity);
     }
     return amg;
 }

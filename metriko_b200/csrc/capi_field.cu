@@ -146,11 +146,13 @@ int mk_field_get_operator(mk_field* f, int* rowptr, int* col, double* val, doubl
 static std::unique_ptr<AmgPrecond<cdouble>> build_face_amg(mk_field* f) {
     cudaStream_t s = f->ctx->c.stream;
     const int nF = f->nF;
+    StageTimer tm("field_amg");
     std::vector<int> nbr((size_t)3 * nF);
     std::vector<std::complex<double>> v((size_t)3 * nF);
     f->S.nbr.download(nbr.data(), nbr.size(), s);
     MK_CUDA(cudaMemcpyAsync(v.data(), f->S.val.p, v.size() * sizeof(cdouble), cudaMemcpyDeviceToHost, s));
     MK_CUDA(cudaStreamSynchronize(s));
+    tm.lap("download stencil");
     HostCsr<std::complex<double>> A;
     A.rows = A.cols = nF;
     A.ptr.resize(nF + 1);
@@ -168,6 +170,7 @@ static std::unique_ptr<AmgPrecond<cdouble>> build_face_amg(mk_field* f) {
         for (int j = 0; j < 4; j++) { A.col[(size_t)4 * i + j] = e[j].first; A.val[(size_t)4 * i + j] = e[j].second; }
     }
     A.ptr[nF] = 4 * nF;
+    tm.lap("host CSR");
     return build_amg<cdouble>(s, std::move(A), {}, false, f->op.get(), amg_params_from_env());
 }
 

@@ -220,11 +220,15 @@ extern "C" int mk_igm_create(mk_ctx* ctx, int rows, int cols, const int64_t* x2f
     g->rows = rows; g->cols = cols; g->ufull_rows = ufull_rows;
     g->length = length;
     g->o = opts_or_default(opts);
+    StageTimer tm("igm_create");
     HostCsr<double> X = csr_from_abi(rows, cols, x2f_ptr, x2f_col, x2f_val);
     g->UFull = csr_from_abi(ufull_rows, cols, uf_ptr, uf_col, uf_val);
+    tm.lap("copy inputs");
     // A0 = length^2 X^T X (host SpGEMM at set-up, as the reference's E = X2F^T X2F, ir_init.h:174); rhs0 = length X^T F2
     HostCsr<double> Xt = transpose(X, false);
+    tm.lap("transpose X");
     HostCsr<double> A0 = matmul(Xt, X);
+    tm.lap("A0 = Xt X");
     const double l2 = length * length;
 #pragma omp parallel for
     for (int64_t k = 0; k < (int64_t)A0.val.size(); k++) A0.val[k] *= l2;
@@ -240,12 +244,15 @@ extern "C" int mk_igm_create(mk_ctx* ctx, int rows, int cols, const int64_t* x2f
     g->pcg = std::make_unique<Pcg<double>>(cols, s);
     g->x.alloc(cols); g->xprev.alloc(cols); g->b.alloc(cols); g->tmp.alloc(std::max(cols, ufull_rows));
     MK_CUDA(cudaStreamSynchronize(s));
+    tm.lap("rhs0 + uploads");
     if (g->o.precond == 1) {
         HostCsr<double> As = A0;
         for (int i = 0; i < As.rows; i++)
             for (int k = As.ptr[i]; k < As.ptr[i + 1]; k++)
                 if (As.col[k] == i) As.val[k] += 1e-4;
+        tm.lap("shifted copy");
         g->amg = build_amg<double>(s, std::move(As), {}, false, g->opA.get(), amg_params_from_env(true));
+        tm.lap("build_amg");
     }
     MK_CUDA(cudaStreamSynchronize(s));
     g->setup_ms = ms_since(t0);

@@ -7,10 +7,26 @@
 #include <cmath>
 #include <complex>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <numeric>
 #include <vector>
 
 namespace mk {
+
+// MK_VERBOSE=1: set-up stage timers on stderr
+struct StageTimer {
+    bool on;
+    double t0;
+    const char* what;
+    explicit StageTimer(const char* w) : on(getenv("MK_VERBOSE") != nullptr), t0(omp_get_wtime()), what(w) {}
+    void lap(const char* stage) {
+        if (!on) return;
+        const double t = omp_get_wtime();
+        fprintf(stderr, "[mk] %s: %-28s %8.1f ms\n", what, stage, (t - t0) * 1e3);
+        t0 = t;
+    }
+};
 
 template <class S>
 struct HostCsr {
