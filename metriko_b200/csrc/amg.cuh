@@ -343,39 +343,10 @@ __global__ void __launch_bounds__(kThreads) k_dense_matvec(int n, const T* __res
     if (lane == 0) st_rw(x + row, acc);
 }
 
-// y (+)= A x, G lanes per row, no reduction; honours the done flag (graph replay)
-template <class T, int G>
-__global__ void __launch_bounds__(kThreads) k_spmv_plain(int n, const int* __restrict__ ptr, const int* __restrict__ col, const T* __restrict__ val,
-                                                         const T* __restrict__ x, T* __restrict__ y, int accumulate, const PcgState* st) {
-    if (st && st->done) return;
-    const int gl = threadIdx.x & (G - 1);
-    const int rows_per_pass = (gridDim.x * blockDim.x) / G;
-    for (int base = (blockIdx.x * blockDim.x + (threadIdx.x & ~31)) / G; base < n; base += rows_per_pass) {
-        const int row = base + ((threadIdx.x & 31) / G);
-        T acc = ST<T>::zero();
-        if (row < n) {
-            const int b = ptr[row], e = ptr[row + 1];
-            for (int k = b + gl; k < e; k += G) acc = ST<T>::fma_(ld_ro(val + k), ld_ro(x + col[k]), acc);
-        }
-        acc = group_sum<T>(acc, G);
-        if (gl == 0 && row < n) {
-            if (accumulate) acc = acc + ld_rw(y + row);
-            st_rw(y + row, acc);
-        }
-    }
-}
-
+// y (+)= A x inside the V-cycle (no reduction; honours the done flag for graph replay)
 template <class T>
 inline void spmv_plain(const DeviceCsr<T>& A, const T* x, T* y, bool accumulate, const PcgState* st, cudaStream_t s) {
-    const int grid = stream_grid((int64_t)A.rows * A.group, kThreads, 16);
-    switch (A.group) {
-        case 2: k_spmv_plain<T, 2><<<grid, kThreads, 0, s>>>(A.rows, A.ptr.p, A.col.p, A.val.p, x, y, accumulate, st); break;
-        case 4: k_spmv_plain<T, 4><<<grid, kThreads, 0, s>>>(A.rows, A.ptr.p, A.col.p, A.val.p, x, y, accumulate, st); break;
-        case 8: k_spmv_plain<T, 8><<<grid, kThreads, 0, s>>>(A.rows, A.ptr.p, A.col.p, A.val.p, x, y, accumulate, st); break;
-        case 16: k_spmv_plain<T, 16><<<grid, kThreads, 0, s>>>(A.rows, A.ptr.p, A.col.p, A.val.p, x, y, accumulate, st); break;
-        default: k_spmv_plain<T, 32><<<grid, kThreads, 0, s>>>(A.rows, A.ptr.p, A.col.p, A.val.p, x, y, accumulate, st); break;
-    }
-    MK_CHECK_LAUNCH();
+    spmv<T>(A, x, y, 0.0, accumulate, false, const_cast<PcgState*>(st), ReduceWs{nullptr, nullptr}, s);
 }
 
 template <class T>

@@ -221,13 +221,12 @@ extern "C" int mk_igm_create(mk_ctx* ctx, int rows, int cols, const int64_t* x2f
     g->length = length;
     g->o = opts_or_default(opts);
     StageTimer tm("igm_create");
-    HostCsr<double> X = csr_from_abi(rows, cols, x2f_ptr, x2f_col, x2f_val);
     g->UFull = csr_from_abi(ufull_rows, cols, uf_ptr, uf_col, uf_val);
-    tm.lap("copy inputs");
-    // A0 = length^2 X^T X (host SpGEMM at set-up, as the reference's E = X2F^T X2F, ir_init.h:174); rhs0 = length X^T F2
-    HostCsr<double> Xt = transpose(X, false);
+    // A0 = length^2 X^T X (host SpGEMM at set-up, as the reference's E = X2F^T X2F, ir_init.h:174); rhs0 = length X^T F2.
+    // X2F (48 M entries at 1M vertices) is read in place through the ABI pointers.
+    HostCsr<double> Xt = transpose_raw<double>(rows, cols, x2f_ptr, x2f_col, x2f_val);
     tm.lap("transpose X");
-    HostCsr<double> A0 = matmul(Xt, X);
+    HostCsr<double> A0 = matmul_raw<double>(Xt, cols, x2f_ptr, x2f_col, x2f_val);
     tm.lap("A0 = Xt X");
     const double l2 = length * length;
 #pragma omp parallel for
@@ -246,12 +245,12 @@ extern "C" int mk_igm_create(mk_ctx* ctx, int rows, int cols, const int64_t* x2f
     MK_CUDA(cudaStreamSynchronize(s));
     tm.lap("rhs0 + uploads");
     if (g->o.precond == 1) {
-        HostCsr<double> As = A0;
-        for (int i = 0; i < As.rows; i++)
-            for (int k = As.ptr[i]; k < As.ptr[i + 1]; k++)
-                if (As.col[k] == i) As.val[k] += 1e-4;
-        tm.lap("shifted copy");
-        g->amg = build_amg<double>(s, std::move(As), {}, false, g->opA.get(), amg_params_from_env(true));
+        // the host copy of A0 is no longer needed unshifted (the device holds it): shift in place, hand it to the set-up
+#pragma omp parallel for schedule(static)
+        for (int i = 0; i < A0.rows; i++)
+            for (int k = A0.ptr[i]; k < A0.ptr[i + 1]; k++)
+                if (A0.col[k] == i) A0.val[k] += 1e-4;
+        g->amg = build_amg<double>(s, std::move(A0), {}, false, g->opA.get(), amg_params_from_env(true));
         tm.lap("build_amg");
     }
     MK_CUDA(cudaStreamSynchronize(s));

@@ -13,14 +13,22 @@ template <class T>
 struct DeviceCsr {
     int rows = 0, cols = 0;
     int64_t nnz = 0;
-    DevBuf<int> ptr, col;
+    DevBuf<int> ptr, col;   // CSR as given (long rows are served from it; also what the get_matrix entry points return)
     DevBuf<T> val;
-    DevBuf<int> long_rows;  // rows with more than kLongRow entries: one CTA each
+    // SELL-32: rows in slices of one warp; slice s stores width_s x 32 entries column-major (entry k of lane l at
+    // sl_ptr[s] + 32 k + l), padded with (a valid column, 0). One thread per row, every load coalesced across the warp.
+    int n_slices = 0;
+    DevBuf<int> sl_ptr, sl_col;
+    DevBuf<T> sl_val;
+    double padding = 1.0;   // stored / true entries
+    // rows with more than kLongRow entries (dense dofs): empty in the SELL part, one CTA each, results parked in ylong[row]
+    DevBuf<int> long_rows;
+    DevBuf<unsigned int> long_bits;  // bit (row & 31) of word (row >> 5)
+    DevBuf<T> ylong;
     int n_long = 0;
-    int group = 8;          // lanes per row in the vector kernel
 };
 
-constexpr int kLongRow = 512;
+constexpr int kLongRow = 256;
 
 template <class T>
 inline void upload_csr(DeviceCsr<T>& A, int rows, int cols, const std::vector<int>& ptr, const std::vector<int>& col,
@@ -34,24 +42,67 @@ inline void upload_csr(DeviceCsr<T>& A, int rows, int cols, const std::vector<in
     A.ptr.upload(ptr.data(), rows + 1, s);
     A.col.upload(col.data(), col.size(), s);
     A.val.upload(val.data(), val.size(), s);
+    // ---- SELL-32 conversion (host, once per operator)
+    const int ns = (rows + 31) / 32;
+    A.n_slices = ns;
     std::vector<int> lr;
+    std::vector<unsigned int> bits(ns, 0u);
     for (int i = 0; i < rows; i++)
-        if (ptr[i + 1] - ptr[i] > kLongRow) lr.push_back(i);
+        if (ptr[i + 1] - ptr[i] > kLongRow) { lr.push_back(i); bits[i >> 5] |= 1u << (i & 31); }
     A.n_long = (int)lr.size();
+    std::vector<int> slp(ns + 1, 0);
+#pragma omp parallel for schedule(static)
+    for (int sl = 0; sl < ns; sl++) {
+        int w = 0;
+        for (int i = sl * 32; i < std::min(rows, sl * 32 + 32); i++) {
+            const int len = ptr[i + 1] - ptr[i];
+            if (len <= kLongRow) w = std::max(w, len);
+        }
+        slp[sl + 1] = w * 32;
+    }
+    int64_t tot = 0;
+    for (int sl = 0; sl < ns; sl++) { tot += slp[sl + 1]; slp[sl + 1] = (int)tot; }
+    if (tot > 2000000000LL) throw std::invalid_argument("upload_csr: matrix too large for 32-bit SELL offsets");
+    std::vector<int> scol((size_t)tot);
+    std::vector<T> sval((size_t)tot);
+#pragma omp parallel for schedule(static)
+    for (int sl = 0; sl < ns; sl++) {
+        const int base = slp[sl], w = (slp[sl + 1] - base) / 32;
+        for (int l = 0; l < 32; l++) {
+            const int i = sl * 32 + l;
+            int b = 0, len = 0;
+            if (i < rows) { b = ptr[i]; len = ptr[i + 1] - ptr[i]; if (len > kLongRow) len = 0; }
+            const int padc = len > 0 ? col[b] : 0;
+            for (int k = 0; k < w; k++) {
+                const size_t o = (size_t)base + (size_t)k * 32 + l;
+                if (k < len) { scol[o] = col[b + k]; sval[o] = val[b + k]; }
+                else { scol[o] = padc; sval[o] = T{}; }
+            }
+        }
+    }
+    A.padding = A.nnz ? (double)tot / (double)A.nnz : 1.0;
+    A.sl_ptr.alloc(ns + 1);
+    A.sl_col.alloc((size_t)tot);
+    A.sl_val.alloc((size_t)tot);
+    A.sl_ptr.upload(slp.data(), ns + 1, s);
+    A.sl_col.upload(scol.data(), (size_t)tot, s);
+    A.sl_val.upload(sval.data(), (size_t)tot, s);
     if (A.n_long) {
         A.long_rows.alloc(lr.size());
         A.long_rows.upload(lr.data(), lr.size(), s);
+        A.long_bits.alloc(ns);
+        A.long_bits.upload(bits.data(), ns, s);
+        A.ylong.alloc(rows);
+        A.ylong.zero(s);
     }
-    double avg = rows ? (double)A.nnz / rows : 0;
-    A.group = avg <= 3 ? 2 : avg <= 6 ? 4 : avg <= 12 ? 8 : avg <= 24 ? 16 : 32;
     MK_CUDA(cudaStreamSynchronize(s));  // host vectors may die after return
 }
 
-// one CTA per long row
+// one CTA per long row: ylong[row] = sum_k val_k x[col_k]
 template <class T>
 __global__ void __launch_bounds__(kThreads) k_spmv_long(const int* __restrict__ rows, const int* __restrict__ ptr,
                                                         const int* __restrict__ col, const T* __restrict__ val,
-                                                        const T* __restrict__ x, T* __restrict__ y, const PcgState* st) {
+                                                        const T* __restrict__ x, T* __restrict__ ylong, const PcgState* st) {
     __shared__ double red[32];
     if (st && st->done) return;
     const int row = rows[blockIdx.x];
@@ -61,11 +112,11 @@ __global__ void __launch_bounds__(kThreads) k_spmv_long(const int* __restrict__ 
     if constexpr (sizeof(T) == 16) {
         const cdouble* a = reinterpret_cast<const cdouble*>(&acc);
         double re = block_sum(a->x, red), im = block_sum(a->y, red);
-        if (threadIdx.x == 0) { cdouble o = make_c(re, im); st_rw(reinterpret_cast<cdouble*>(y) + row, o); }
+        if (threadIdx.x == 0) { cdouble o = make_c(re, im); st_rw(reinterpret_cast<cdouble*>(ylong) + row, o); }
     } else {
         const double* a = reinterpret_cast<const double*>(&acc);
         double v = block_sum(*a, red);
-        if (threadIdx.x == 0) reinterpret_cast<double*>(y)[row] = v;
+        if (threadIdx.x == 0) reinterpret_cast<double*>(ylong)[row] = v;
     }
 }
 
@@ -85,34 +136,45 @@ __device__ __forceinline__ cdouble group_sum<cdouble>(cdouble v, int G) {
     return v;
 }
 
-// y = A x with G lanes per row; DOT: pq = <x, y>, alpha = rho / pq finished by the last CTA.
-// SHIFT: y = A x + shift * x (used for A0 + 1e-4 I without touching the stored values).
-template <class T, int G, bool DOT>
-__global__ void __launch_bounds__(kThreads) k_spmv_csr(int n, const int* __restrict__ ptr, const int* __restrict__ col,
-                                                       const T* __restrict__ val, const T* __restrict__ x, T* __restrict__ y,
-                                                       double shift, PcgState* st, ReduceWs ws) {
+// y (+)= A x (+ shift x) on the SELL-32 layout, one thread per row, one warp per slice.
+// DOT: pq = <x, y>, alpha = rho / pq finished by the last CTA (the PCG step). ACC: y += (prolongation).
+template <class T, bool DOT, bool ACC>
+__global__ void __launch_bounds__(kThreads, 4) k_spmv_sell(int n, int n_slices, const int* __restrict__ sl_ptr, const int* __restrict__ sl_col,
+                                                        const T* __restrict__ sl_val, const unsigned int* __restrict__ long_bits,
+                                                        const T* __restrict__ ylong, const T* __restrict__ x, T* __restrict__ y, double shift,
+                                                        PcgState* st, ReduceWs ws) {
     __shared__ double red[32];
     if (st && st->done) return;
-    const int gl = threadIdx.x & (G - 1);
-    const int rows_per_pass = (gridDim.x * blockDim.x) / G;
+    const int lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
     double dot = 0.0;
-    for (int base = (blockIdx.x * blockDim.x + (threadIdx.x & ~31)) / G; base < n; base += rows_per_pass) {
-        const int row = base + ((threadIdx.x & 31) / G);
+    for (int sl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; sl < n_slices; sl += nwarps) {
+        const int base = __ldg(sl_ptr + sl);
+        const int w = (__ldg(sl_ptr + sl + 1) - base) >> 5;
+        const int* cp = sl_col + base + lane;
+        const T* vp = sl_val + base + lane;
         T acc = ST<T>::zero();
-        bool is_long = false;
-        if (row < n) {
-            const int b = ptr[row], e = ptr[row + 1];
-            is_long = (e - b) > kLongRow;
-            if (!is_long)
-                for (int k = b + gl; k < e; k += G) acc = ST<T>::fma_(ld_ro(val + k), ld_ro(x + col[k]), acc);
+        int k = 0;
+        for (; k + 4 <= w; k += 4) {
+            const int c0 = __ldg(cp + 32 * k), c1 = __ldg(cp + 32 * (k + 1)), c2 = __ldg(cp + 32 * (k + 2)), c3 = __ldg(cp + 32 * (k + 3));
+            const T v0 = ld_ro(vp + 32 * k), v1 = ld_ro(vp + 32 * (k + 1)), v2 = ld_ro(vp + 32 * (k + 2)), v3 = ld_ro(vp + 32 * (k + 3));
+            const T x0 = ld_ro(x + c0), x1 = ld_ro(x + c1), x2 = ld_ro(x + c2), x3 = ld_ro(x + c3);
+            acc = ST<T>::fma_(v0, x0, acc);
+            acc = ST<T>::fma_(v1, x1, acc);
+            acc = ST<T>::fma_(v2, x2, acc);
+            acc = ST<T>::fma_(v3, x3, acc);
         }
-        acc = group_sum<T>(acc, G);
-        if (gl == 0 && row < n) {
-            T xr = ld_ro(x + row);
-            if (is_long) acc = ld_rw(y + row);  // written by k_spmv_long, launched before this kernel
-            else if (shift != 0.0) acc = acc + ST<T>::scale(shift, xr);
-            if (!is_long) st_rw(y + row, acc);
-            if (DOT) dot += ST<T>::hdot(xr, acc);
+        for (; k < w; k++) acc = ST<T>::fma_(ld_ro(vp + 32 * k), ld_ro(x + __ldg(cp + 32 * k)), acc);
+        const int row = sl * 32 + lane;
+        if (row < n) {
+            if (long_bits != nullptr && ((__ldg(long_bits + sl) >> lane) & 1u)) acc = acc + ld_rw(ylong + row);
+            if (DOT || shift != 0.0) {
+                const T xr = ld_ro(x + row);
+                if (shift != 0.0) acc = acc + ST<T>::scale(shift, xr);
+                if (DOT) dot += ST<T>::hdot(xr, acc);
+            }
+            if (ACC) acc = acc + ld_rw(y + row);
+            st_rw(y + row, acc);
         }
     }
     if (DOT) {
@@ -125,51 +187,30 @@ __global__ void __launch_bounds__(kThreads) k_spmv_csr(int n, const int* __restr
     }
 }
 
+// y (+)= A x (+ shift x); st != nullptr: skipped once st->done is set; dot: fused <x, y> reduction (needs st)
+template <class T>
+inline void spmv(const DeviceCsr<T>& A, const T* x, T* y, double shift, bool accumulate, bool dot, PcgState* st, ReduceWs ws, cudaStream_t s) {
+    if (A.n_long) k_spmv_long<T><<<A.n_long, kThreads, 0, s>>>(A.long_rows.p, A.ptr.p, A.col.p, A.val.p, x, A.ylong.p, st);
+    const int grid = stream_grid((int64_t)A.n_slices * 32, kThreads, 16);
+    const unsigned int* lb = A.n_long ? A.long_bits.p : nullptr;
+    if (dot && st)
+        k_spmv_sell<T, true, false><<<grid, kThreads, 0, s>>>(A.rows, A.n_slices, A.sl_ptr.p, A.sl_col.p, A.sl_val.p, lb, A.ylong.p, x, y, shift, st, ws);
+    else if (accumulate)
+        k_spmv_sell<T, false, true><<<grid, kThreads, 0, s>>>(A.rows, A.n_slices, A.sl_ptr.p, A.sl_col.p, A.sl_val.p, lb, A.ylong.p, x, y, shift, st, ws);
+    else
+        k_spmv_sell<T, false, false><<<grid, kThreads, 0, s>>>(A.rows, A.n_slices, A.sl_ptr.p, A.sl_col.p, A.sl_val.p, lb, A.ylong.p, x, y, shift, st, ws);
+    MK_CHECK_LAUNCH();
+}
+
 template <class T>
 struct CsrOp : LinOp<T> {
     const DeviceCsr<T>* A = nullptr;
     double shift = 0.0;
     explicit CsrOp(const DeviceCsr<T>* A_, double shift_ = 0.0) : A(A_), shift(shift_) { this->n = A_->rows; }
-    int launches_per_apply() const override { return A->n_long ? (shift != 0.0 ? 3 : 2) : 1; }
-
-    template <int G>
-    void launch(const T* x, T* y, PcgState* st, ReduceWs ws, cudaStream_t s, bool dot) {
-        int64_t threads = (int64_t)A->rows * G;
-        int grid = stream_grid(threads, kThreads, 16);
-        if (st && dot) k_spmv_csr<T, G, true><<<grid, kThreads, 0, s>>>(A->rows, A->ptr.p, A->col.p, A->val.p, x, y, shift, st, ws);
-        else k_spmv_csr<T, G, false><<<grid, kThreads, 0, s>>>(A->rows, A->ptr.p, A->col.p, A->val.p, x, y, shift, st, ws);
-    }
+    int launches_per_apply() const override { return A->n_long ? 2 : 1; }
     void apply(const T* x, T* y, PcgState* st, ReduceWs ws, cudaStream_t s, bool dot = true) override {
-        if (A->n_long) {
-            // long rows first; the shift is added here so the main kernel can just pick the value up
-            k_spmv_long<T><<<A->n_long, kThreads, 0, s>>>(A->long_rows.p, A->ptr.p, A->col.p, A->val.p, x, y, st);
-            if (shift != 0.0) add_shift_long(x, y, st, s);
-        }
-        switch (A->group) {
-            case 2: launch<2>(x, y, st, ws, s, dot); break;
-            case 4: launch<4>(x, y, st, ws, s, dot); break;
-            case 8: launch<8>(x, y, st, ws, s, dot); break;
-            case 16: launch<16>(x, y, st, ws, s, dot); break;
-            default: launch<32>(x, y, st, ws, s, dot); break;
-        }
-        MK_CHECK_LAUNCH();
+        spmv<T>(*A, x, y, shift, false, dot && st != nullptr, st, ws, s);
     }
-    void add_shift_long(const T* x, T* y, PcgState* st, cudaStream_t s);
 };
-
-template <class T>
-__global__ void k_shift_rows(int m, const int* __restrict__ rows, const T* __restrict__ x, T* __restrict__ y, double shift,
-                             const PcgState* st) {
-    if (st && st->done) return;
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < m) {
-        int r = rows[i];
-        st_rw(y + r, ld_rw(y + r) + ST<T>::scale(shift, ld_ro(x + r)));
-    }
-}
-template <class T>
-void CsrOp<T>::add_shift_long(const T* x, T* y, PcgState* st, cudaStream_t s) {
-    k_shift_rows<T><<<(A->n_long + 127) / 128, 128, 0, s>>>(A->n_long, A->long_rows.p, x, y, shift, st);
-}
 
 }  // namespace mk
