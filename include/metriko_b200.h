@@ -125,6 +125,29 @@ int mk_igm_round(mk_igm* g, int n_fixed, const int* fixedIdcs, const double* fix
 int mk_igm_get_matrix(mk_igm* g, int64_t* nnz, int* rowptr, int* col, double* val);
 int mk_igm_spmv_bench(mk_igm* g, int reps, int fused_dot, double* ms_per_launch);
 
+/* ---- partitioned face operator: one process per GPU, NCCL over NVLink (BASELINE configs[3]). The reference has no
+ * distributed code; these entry points serve the same recurrence (sls.h:44-51) on a row-partitioned L. The host-side plan
+ * (contiguous row blocks, interior-first local order, halo slots grouped by peer) is metriko_b200/partition.py. ---- */
+typedef struct mk_dist mk_dist;       /* communicator of the partitioned mode (rank, world, NCCL) */
+typedef struct mk_dfield mk_dfield;   /* this rank's rows of the face operator + halo plan + distributed PCG state */
+/* id: MK_DIST_ID_BYTES bytes from rank 0's mk_dist_unique_id, distributed by the host application (MPI, torch.distributed, a file). */
+#define MK_DIST_ID_BYTES 128
+int mk_dist_unique_id(char* id, int id_bytes);
+int mk_dist_create(mk_ctx* ctx, int rank, int world, const char* id, int id_bytes, mk_dist** out);
+int mk_dist_destroy(mk_dist* d);
+/* nbr_local[3][n_local]: column indices into x_ext = [owned rows | halo slots]; val[3][n_local] complex; rows [0, n_interior)
+ * reference no halo slot; send_counts / recv_counts[world]; send_idx: local rows to pack, grouped by peer. */
+int mk_dfield_create(mk_dist* d, int n_local, int n_interior, int n_halo, const int* nbr_local, const double* val, const double* mass,
+                     const int* send_counts, const int* recv_counts, const int* send_idx, mk_dfield** out);
+int mk_dfield_destroy(mk_dfield* f);
+/* y = (L x) on the owned rows: pack -> NCCL send/recv (own stream) overlapped with the interior rows -> boundary rows. Collective. */
+int mk_dfield_spmv(mk_dfield* f, const double* x_local, double* y_local);
+int mk_dfield_spmv_bench(mk_dfield* f, int reps, int overlap, double* ms_per_launch);
+/* one distributed PCG solve L x = b, and the 50-step inverse iteration; preconditioner = multigrid V-cycle on each rank's diagonal
+ * block (block-Jacobi across ranks). Collective: every rank calls with its rows. */
+int mk_dfield_pcg(mk_dfield* f, const double* b_local, const double* x0_local, const mk_solve_opts* opts, double* x_local, mk_stats* stats);
+int mk_dfield_solve(mk_dfield* f, const double* u0_local, int n_iter, const mk_solve_opts* opts, double* x_local, mk_stats* stats);
+
 /* ---- host-side multigrid set-up, exposed for CPU tests of the hierarchy (no device needed): builds the same
  * smoothed-aggregation hierarchy the solvers use for a Hermitian (is_complex = 1, interleaved values) or symmetric CSR
  * matrix. cand = near-kernel candidate (real operators) or NULL. which: 0 = A_l, 1 = P_l (level l -> l+1),

@@ -85,6 +85,15 @@ def lib() -> C.CDLL:
         L.mk_igm_round.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp, ip, vp, vp, C.POINTER(Stats)]
         L.mk_igm_get_matrix.argtypes = [vp, i64p, vp, vp, vp]
         L.mk_igm_spmv_bench.argtypes = [vp, C.c_int, C.c_int, dp]
+        L.mk_dist_unique_id.argtypes = [C.c_char_p, C.c_int]
+        L.mk_dist_create.argtypes = [vp, C.c_int, C.c_int, C.c_char_p, C.c_int, C.POINTER(vp)]
+        L.mk_dist_destroy.argtypes = [vp]
+        L.mk_dfield_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]
+        L.mk_dfield_destroy.argtypes = [vp]
+        L.mk_dfield_spmv.argtypes = [vp, vp, vp]
+        L.mk_dfield_spmv_bench.argtypes = [vp, C.c_int, C.c_int, dp]
+        L.mk_dfield_pcg.argtypes = [vp, vp, vp, C.POINTER(SolveOpts), vp, C.POINTER(Stats)]
+        L.mk_dfield_solve.argtypes = [vp, vp, C.c_int, C.POINTER(SolveOpts), vp, C.POINTER(Stats)]
         L.mk_amg_host_build.argtypes = [C.c_int, vp, vp, vp, C.c_int, vp, C.POINTER(vp)]
         L.mk_amg_host_num_levels.argtypes = [vp]
         L.mk_amg_host_level_info.argtypes = [vp, C.c_int, C.c_int, ip, ip, i64p, dp]

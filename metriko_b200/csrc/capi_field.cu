@@ -12,6 +12,8 @@ using namespace mk;
 
 struct mk_field {
     mk_ctx* ctx = nullptr;
+    cudaStream_t stream = nullptr;  // copies, so that destruction does not depend on the context object
+    int device = 0;
     int nF = 0, nH = 0, N = 4;
     DevBuf<int> face2half, next, twin, face;
     DevBuf<double> farg;
@@ -50,6 +52,12 @@ int mk_ctx_create(int device, void* stream, mk_ctx** out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return MK_ERR_CUDA;
     if (prop.major != 10) return MK_ERR_CUDA;  // sm_100a cubin only: no other architecture can run it
+    // keep freed blocks in the stream-ordered pool instead of returning them to the driver between steps
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long thresh = ~0ULL;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
+    }
     mk_ctx* c = new mk_ctx();
     c->c.device = device;
     if (stream) {
@@ -85,6 +93,8 @@ int mk_field_create(mk_ctx* ctx, int nF, int nH, int N, const int* face2half, co
     cudaStream_t s = ctx->c.stream;
     auto f = std::make_unique<mk_field>();
     f->ctx = ctx;
+    f->stream = s;
+    f->device = ctx->c.device;
     f->nF = nF; f->nH = nH; f->N = N;
     f->face2half.alloc(nF); f->next.alloc(nH); f->twin.alloc(nH); f->face.alloc(nH); f->farg.alloc(nH);
     f->S.nF = nF;
@@ -98,6 +108,9 @@ int mk_field_create(mk_ctx* ctx, int nF, int nH, int N, const int* face2half, co
 }
 
 int mk_field_destroy(mk_field* f) {
+    if (!f) return MK_OK;
+    AllocStreamScope sc(f->stream);
+    cudaSetDevice(f->device);
     delete f;
     return MK_OK;
 }

@@ -88,6 +88,8 @@ extern "C" int mk_solve_smallest_eig_csc(mk_ctx* ctx, int n, const int* L_outer,
 // ------------------------------------------------------------------------------------------------
 struct mk_spd {
     mk_ctx* ctx = nullptr;
+    cudaStream_t stream = nullptr;
+    int device = 0;
     int n = 0;
     mk_solve_opts o;
     DeviceCsr<double> A;
@@ -107,6 +109,8 @@ extern "C" int mk_spd_factorize(mk_ctx* ctx, int n, const int* outer, const int*
     auto t0 = hclock::now();
     auto h = std::make_unique<mk_spd>();
     h->ctx = ctx;
+    h->stream = s;
+    h->device = ctx->c.device;
     h->n = n;
     h->o = opts_or_default(opts);
     HostCsr<double> A;  // symmetric: CSC arrays are CSR arrays
@@ -158,6 +162,9 @@ extern "C" int mk_spd_solve(mk_spd* h, const double* rhs, const double* x_guess,
 }
 
 extern "C" int mk_spd_destroy(mk_spd* h) {
+    if (!h) return MK_OK;
+    AllocStreamScope sc(h->stream);
+    cudaSetDevice(h->device);
     delete h;
     return MK_OK;
 }
@@ -182,6 +189,8 @@ extern "C" int mk_spd_spmv_bench(mk_spd* h, int reps, int fused_dot, double* ms_
 // ------------------------------------------------------------------------------------------------
 struct mk_igm {
     mk_ctx* ctx = nullptr;
+    cudaStream_t stream = nullptr;
+    int device = 0;
     int rows = 0, cols = 0, ufull_rows = 0;
     double length = 1.0;
     mk_solve_opts o;
@@ -217,6 +226,8 @@ extern "C" int mk_igm_create(mk_ctx* ctx, int rows, int cols, const int64_t* x2f
     auto t0 = hclock::now();
     auto g = std::make_unique<mk_igm>();
     g->ctx = ctx;
+    g->stream = s;
+    g->device = ctx->c.device;
     g->rows = rows; g->cols = cols; g->ufull_rows = ufull_rows;
     g->length = length;
     g->o = opts_or_default(opts);
@@ -260,6 +271,9 @@ extern "C" int mk_igm_create(mk_ctx* ctx, int rows, int cols, const int64_t* x2f
 }
 
 extern "C" int mk_igm_destroy(mk_igm* g) {
+    if (!g) return MK_OK;
+    AllocStreamScope sc(g->stream);
+    cudaSetDevice(g->device);
     delete g;
     return MK_OK;
 }

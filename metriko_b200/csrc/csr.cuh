@@ -30,6 +30,74 @@ struct DeviceCsr {
 
 constexpr int kLongRow = 256;
 
+// ---- CSR -> SELL-32 conversion on the device (once per operator) ----
+// one warp per slice: width = longest non-long row, long rows flagged in a bit word and appended to the long-row list
+static __global__ void k_sell_width(int rows, int n_slices, const int* __restrict__ ptr, int* __restrict__ width32, unsigned int* __restrict__ long_bits,
+                                    int* __restrict__ long_rows, int* __restrict__ n_long) {
+    const int lane = threadIdx.x & 31;
+    const int sl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (sl >= n_slices) return;
+    const int row = sl * 32 + lane;
+    int len = 0;
+    if (row < rows) len = ptr[row + 1] - ptr[row];
+    const bool is_long = len > kLongRow;
+    const unsigned int bits = __ballot_sync(0xffffffffu, is_long);
+    if (is_long) {
+        long_rows[atomicAdd(n_long, 1)] = row;
+        len = 0;
+    }
+    for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+    if (lane == 0) { width32[sl] = len * 32; long_bits[sl] = bits; }
+}
+
+// exclusive scan of n ints by one CTA (n = number of slices: 65k at 2M rows); out[n] = total
+static __global__ void __launch_bounds__(1024) k_scan_exclusive(int n, const int* __restrict__ in, int* __restrict__ out) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < n ? in[i] : 0;
+        int x = v;
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) warp_tot[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            int t = warp_tot[lane];
+            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += y; }
+            warp_tot[lane] = t;
+        }
+        __syncthreads();
+        const int carry = carry_s;
+        const int incl = carry + x + (wid ? warp_tot[wid - 1] : 0);
+        if (i < n) out[i] = incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[n] = carry_s;
+}
+
+template <class T>
+static __global__ void k_sell_fill(int rows, int n_slices, const int* __restrict__ ptr, const int* __restrict__ col, const T* __restrict__ val,
+                                   const int* __restrict__ sl_ptr, int* __restrict__ sl_col, T* __restrict__ sl_val) {
+    const int lane = threadIdx.x & 31;
+    const int sl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (sl >= n_slices) return;
+    const int row = sl * 32 + lane;
+    const int base = sl_ptr[sl], w = (sl_ptr[sl + 1] - base) >> 5;
+    int b = 0, len = 0;
+    if (row < rows) { b = ptr[row]; len = ptr[row + 1] - b; if (len > kLongRow) len = 0; }
+    const int padc = len > 0 ? col[b] : 0;
+    for (int k = 0; k < w; k++) {
+        const size_t o = (size_t)base + (size_t)k * 32 + lane;
+        if (k < len) { sl_col[o] = col[b + k]; st_rw(sl_val + o, ld_ro(val + b + k)); }
+        else { sl_col[o] = padc; st_rw(sl_val + o, ST<T>::zero()); }
+    }
+}
+
 template <class T>
 inline void upload_csr(DeviceCsr<T>& A, int rows, int cols, const std::vector<int>& ptr, const std::vector<int>& col,
                        const std::vector<T>& val, cudaStream_t s) {
@@ -42,60 +110,32 @@ inline void upload_csr(DeviceCsr<T>& A, int rows, int cols, const std::vector<in
     A.ptr.upload(ptr.data(), rows + 1, s);
     A.col.upload(col.data(), col.size(), s);
     A.val.upload(val.data(), val.size(), s);
-    // ---- SELL-32 conversion (host, once per operator)
     const int ns = (rows + 31) / 32;
     A.n_slices = ns;
-    std::vector<int> lr;
-    std::vector<unsigned int> bits(ns, 0u);
-    for (int i = 0; i < rows; i++)
-        if (ptr[i + 1] - ptr[i] > kLongRow) { lr.push_back(i); bits[i >> 5] |= 1u << (i & 31); }
-    A.n_long = (int)lr.size();
-    std::vector<int> slp(ns + 1, 0);
-#pragma omp parallel for schedule(static)
-    for (int sl = 0; sl < ns; sl++) {
-        int w = 0;
-        for (int i = sl * 32; i < std::min(rows, sl * 32 + 32); i++) {
-            const int len = ptr[i + 1] - ptr[i];
-            if (len <= kLongRow) w = std::max(w, len);
-        }
-        slp[sl + 1] = w * 32;
-    }
-    int64_t tot = 0;
-    for (int sl = 0; sl < ns; sl++) { tot += slp[sl + 1]; slp[sl + 1] = (int)tot; }
-    if (tot > 2000000000LL) throw std::invalid_argument("upload_csr: matrix too large for 32-bit SELL offsets");
-    std::vector<int> scol((size_t)tot);
-    std::vector<T> sval((size_t)tot);
-#pragma omp parallel for schedule(static)
-    for (int sl = 0; sl < ns; sl++) {
-        const int base = slp[sl], w = (slp[sl + 1] - base) / 32;
-        for (int l = 0; l < 32; l++) {
-            const int i = sl * 32 + l;
-            int b = 0, len = 0;
-            if (i < rows) { b = ptr[i]; len = ptr[i + 1] - ptr[i]; if (len > kLongRow) len = 0; }
-            const int padc = len > 0 ? col[b] : 0;
-            for (int k = 0; k < w; k++) {
-                const size_t o = (size_t)base + (size_t)k * 32 + l;
-                if (k < len) { scol[o] = col[b + k]; sval[o] = val[b + k]; }
-                else { scol[o] = padc; sval[o] = T{}; }
-            }
-        }
-    }
-    A.padding = A.nnz ? (double)tot / (double)A.nnz : 1.0;
+    DevBuf<int> width(ns), counter(1);
     A.sl_ptr.alloc(ns + 1);
-    A.sl_col.alloc((size_t)tot);
-    A.sl_val.alloc((size_t)tot);
-    A.sl_ptr.upload(slp.data(), ns + 1, s);
-    A.sl_col.upload(scol.data(), (size_t)tot, s);
-    A.sl_val.upload(sval.data(), (size_t)tot, s);
+    A.long_bits.alloc(ns);
+    A.long_rows.alloc(std::max(1, std::min(rows, 1 << 16)));  // more than 65k dense rows would not be a sparse operator
+    counter.zero(s);
+    const int wg = (ns * 32 + kThreads - 1) / kThreads;
+    k_sell_width<<<wg, kThreads, 0, s>>>(rows, ns, A.ptr.p, width.p, A.long_bits.p, A.long_rows.p, counter.p);
+    k_scan_exclusive<<<1, 1024, 0, s>>>(ns, width.p, A.sl_ptr.p);
+    MK_CHECK_LAUNCH();
+    int tot = 0, nl = 0;
+    MK_CUDA(cudaMemcpyAsync(&tot, A.sl_ptr.p + ns, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MK_CUDA(cudaMemcpyAsync(&nl, counter.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MK_CUDA(cudaStreamSynchronize(s));  // also: host vectors may die after return
+    if (tot < 0 || nl > (1 << 16)) throw std::invalid_argument("upload_csr: matrix too large / too many dense rows for the SELL layout");
+    A.n_long = nl;
+    A.sl_col.alloc((size_t)std::max(tot, 1));
+    A.sl_val.alloc((size_t)std::max(tot, 1));
+    k_sell_fill<T><<<wg, kThreads, 0, s>>>(rows, ns, A.ptr.p, A.col.p, A.val.p, A.sl_ptr.p, A.sl_col.p, A.sl_val.p);
+    MK_CHECK_LAUNCH();
+    A.padding = A.nnz ? (double)tot / (double)A.nnz : 1.0;
     if (A.n_long) {
-        A.long_rows.alloc(lr.size());
-        A.long_rows.upload(lr.data(), lr.size(), s);
-        A.long_bits.alloc(ns);
-        A.long_bits.upload(bits.data(), ns, s);
         A.ylong.alloc(rows);
         A.ylong.zero(s);
     }
-    MK_CUDA(cudaStreamSynchronize(s));  // host vectors may die after return
 }
 
 // one CTA per long row: ylong[row] = sum_k val_k x[col_k]

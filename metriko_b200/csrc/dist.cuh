@@ -1,0 +1,339 @@
+// Partitioned (one process per GPU) face operator: halo exchange over NCCL overlapped with the interior-row SpMV, and a
+// distributed PCG / inverse iteration whose scalars stay on the device (NCCL all-reduce of 1-2 doubles per reduction).
+// The reference has no distributed code; the host-side plan comes from metriko_b200/partition.py.
+//
+// NCCL is bound at run time (dlopen of libnccl.so.2, reusing the copy a host application such as PyTorch already loaded),
+// so libmetriko_b200.so itself has no link-time dependency on it and single-GPU users never touch it.
+#pragma once
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <memory>
+#include <vector>
+
+#include "amg.cuh"
+#include "field.cuh"
+
+namespace mk {
+
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+
+    static NcclApi& get() {
+        static NcclApi api;
+        if (!api.handle) {
+            void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);  // the copy already in the process, if any
+            if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+            if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+            if (!h) throw std::runtime_error(std::string("cannot load libnccl.so.2: ") + dlerror());
+            auto sym = [&](const char* n) {
+                void* p = dlsym(h, n);
+                if (!p) throw std::runtime_error(std::string("libnccl: missing symbol ") + n);
+                return p;
+            };
+            api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+            api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+            api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+            api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+            api.Send = (decltype(api.Send))sym("ncclSend");
+            api.Recv = (decltype(api.Recv))sym("ncclRecv");
+            api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+            api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+            api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+            api.handle = h;
+        }
+        return api;
+    }
+};
+
+#define MK_NCCL(expr)                                                                                               \
+    do {                                                                                                            \
+        ncclResult_t _r = (expr);                                                                                   \
+        if (_r != ncclSuccess)                                                                                      \
+            throw mk::CudaError(std::string(#expr) + " failed: " + mk::NcclApi::get().GetErrorString(_r));          \
+    } while (0)
+
+struct DistComm {
+    int rank = 0, world = 1;
+    ncclComm_t comm = nullptr;
+    cudaStream_t comm_stream = nullptr;  // halo exchange runs here, next to the interior SpMV on the main stream
+    ~DistComm() {
+        if (comm) NcclApi::get().CommDestroy(comm);
+        if (comm_stream) cudaStreamDestroy(comm_stream);
+    }
+    void allreduce_sum(double* buf, int n, cudaStream_t s) {
+        if (world > 1) MK_NCCL(NcclApi::get().AllReduce(buf, buf, (size_t)n, ncclDouble, ncclSum, comm, s));
+    }
+};
+
+// ---- kernels ----
+
+// out[k] = x[idx[k]]  (boundary values each peer needs, grouped by peer)
+static __global__ void __launch_bounds__(kThreads) k_halo_pack(int m, const int* __restrict__ idx, const cdouble* __restrict__ x, cdouble* __restrict__ out,
+                                                        const PcgState* st) {
+    if (st && st->done) return;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < m; k += gridDim.x * blockDim.x) stc(out + k, ldc_nc(x + __ldg(idx + k)));
+}
+
+// y = L x on the rows [r0, r1) of the local block; x = [owned | halo]; stencil arrays strided by `stride` (= owned rows)
+static __global__ void __launch_bounds__(kThreads) k_spmv_face_rows(int stride, int r0, int r1, double diag, const int* __restrict__ nbr,
+                                                             const cdouble* __restrict__ val, const cdouble* __restrict__ x, cdouble* __restrict__ y,
+                                                             const PcgState* st) {
+    if (st && st->done) return;
+    for (int f = r0 + blockIdx.x * blockDim.x + threadIdx.x; f < r1; f += gridDim.x * blockDim.x) {
+        const int n0 = __ldg(nbr + f), n1 = __ldg(nbr + (size_t)stride + f), n2 = __ldg(nbr + 2 * (size_t)stride + f);
+        const cdouble v0 = ldc_nc(val + f), v1 = ldc_nc(val + (size_t)stride + f), v2 = ldc_nc(val + 2 * (size_t)stride + f);
+        const cdouble xf = ldc_nc(x + f);
+        const cdouble x0 = ldc_nc(x + n0), x1 = ldc_nc(x + n1), x2 = ldc_nc(x + n2);
+        cdouble acc = make_c(diag * xf.x, diag * xf.y);
+        acc = ST<cdouble>::fma_(v0, x0, acc);
+        acc = ST<cdouble>::fma_(v1, x1, acc);
+        acc = ST<cdouble>::fma_(v2, x2, acc);
+        stc(y + f, acc);
+    }
+}
+
+// out[0] = Re<a, b>, out[1] = Re<c, d> (c == nullptr: only the first), optionally weighted by w (mass): local partial sums
+static __global__ void __launch_bounds__(kThreads) k_dist_dots(int n, const cdouble* __restrict__ a, const cdouble* __restrict__ b,
+                                                        const cdouble* __restrict__ c, const cdouble* __restrict__ d, const double* __restrict__ w,
+                                                        double* __restrict__ out, ReduceWs ws, const PcgState* st) {
+    __shared__ double red[32];
+    if (st && st->done) return;
+    double s0 = 0.0, s1 = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double wi = w ? __ldg(w + i) : 1.0;
+        const cdouble ai = ldc_nc(a + i), bi = ldc_nc(b + i);
+        s0 += wi * (ai.x * bi.x + ai.y * bi.y);
+        if (c) {
+            const cdouble ci = ldc_nc(c + i), di = ldc_nc(d + i);
+            s1 += wi * (ci.x * di.x + ci.y * di.y);
+        }
+    }
+    double v[2] = {s0, s1};
+    grid_reduce<2>(v, ws.partials, ws.ticket, red, [&](const double* s) { out[0] = s[0]; out[1] = s[1]; });
+}
+
+// x += alpha p ; r -= alpha q with alpha = rho / <p, q> (part[0], already all-reduced); part[1] = local <r, r>
+static __global__ void __launch_bounds__(kThreads) k_dist_update_xr(int n, cdouble* __restrict__ x, cdouble* __restrict__ r, const cdouble* __restrict__ p,
+                                                             const cdouble* __restrict__ q, const PcgState* st, double* __restrict__ part, ReduceWs ws) {
+    __shared__ double red[32];
+    if (st->done) return;
+    const double alpha = st->rho / part[0];
+    double acc = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const cdouble pi = ldc_nc(p + i), qi = ldc_nc(q + i);
+        cdouble xi = ldc(x + i), ri = ldc(r + i);
+        xi = make_c(xi.x + alpha * pi.x, xi.y + alpha * pi.y);
+        ri = make_c(ri.x - alpha * qi.x, ri.y - alpha * qi.y);
+        stc(x + i, xi);
+        stc(r + i, ri);
+        acc += ri.x * ri.x + ri.y * ri.y;
+    }
+    double v[1] = {acc};
+    grid_reduce<1>(v, ws.partials, ws.ticket, red, [&](const double* s) { part[1] = s[0]; });
+}
+
+// p = z + beta p with beta = <r, z>_new / rho_old (part[2] all-reduced; st->rho still holds the old value)
+static __global__ void __launch_bounds__(kThreads) k_dist_update_p(int n, cdouble* __restrict__ p, const cdouble* __restrict__ z, const PcgState* st,
+                                                            const double* __restrict__ part) {
+    if (st->done) return;
+    const double beta = part[2] / st->rho;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const cdouble zi = ldc_nc(z + i), pi = ldc(p + i);
+        stc(p + i, make_c(zi.x + beta * pi.x, zi.y + beta * pi.y));
+    }
+}
+
+// one thread: fold the all-reduced partials of an iteration into the state (after every kernel that read the old values)
+static __global__ void k_dist_state(PcgState* st, const double* part) {
+    if (st->done) return;
+    st->pq = part[0];
+    st->alpha = st->rho / part[0];
+    st->rr = part[1];
+    st->beta = part[2] / st->rho;
+    st->rho = part[2];
+    st->iter += 1;
+    if (!(part[0] > 0.0) || !(part[1] == part[1])) st->done = 2;
+    else if (part[1] <= st->thresh) st->done = 1;
+    else if (st->iter >= st->maxit) st->done = 3;
+}
+
+// start of a solve: part = {<r,r>, <b,b>, <r,z>} all-reduced
+static __global__ void k_dist_start(PcgState* st, const double* part, double tol2, int maxit, int keep_bnorm) {
+    st->rr = part[0];
+    if (!keep_bnorm) {
+        st->bnorm2 = part[1];
+        st->thresh = tol2 * part[1];
+        st->iter = 0;
+    }
+    st->rho = part[2];
+    st->maxit = maxit;
+    st->done = (part[0] <= st->thresh) ? 1 : 0;
+}
+
+// r = b - q
+static __global__ void __launch_bounds__(kThreads) k_dist_residual(int n, const cdouble* __restrict__ b, const cdouble* __restrict__ q, cdouble* __restrict__ r) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) stc(r + i, ldc_nc(b + i) - ldc_nc(q + i));
+}
+
+// y = a * m .* x (a read from the device: scale[0], or 1 / sqrt|scale[0]| when inv_sqrt)
+static __global__ void __launch_bounds__(kThreads) k_dist_scale(int n, const double* __restrict__ m, const cdouble* __restrict__ x, cdouble* __restrict__ y,
+                                                         const double* __restrict__ scale, int inv_sqrt) {
+    double a = scale ? scale[0] : 1.0;
+    if (scale && inv_sqrt) a = 1.0 / sqrt(fabs(a));
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double mi = m ? a * __ldg(m + i) : a;
+        const cdouble xi = ldc_nc(x + i);
+        stc(y + i, make_c(mi * xi.x, mi * xi.y));
+    }
+}
+
+// ---- the partitioned operator ----
+struct DistFaceOp {
+    DistComm* dc = nullptr;
+    int nloc = 0, nint = 0, nhalo = 0;
+    FaceStencil S;      // nbr indexes x_ext = [owned | halo]
+    FaceStencil Sblk;   // the diagonal block only (halo couplings dropped): level 0 of the local preconditioner
+    DevBuf<int> send_idx;
+    DevBuf<cdouble> sendbuf;
+    std::vector<int> send_counts, recv_counts, send_off, recv_off;
+    int nsend = 0;
+    cudaEvent_t ev_pack = nullptr, ev_halo = nullptr;
+    bool overlap = true;
+
+    ~DistFaceOp() {
+        if (ev_pack) cudaEventDestroy(ev_pack);
+        if (ev_halo) cudaEventDestroy(ev_halo);
+    }
+
+    // y[0:nloc) = (L x)[owned rows]; x_ext's halo part is refreshed from the peers
+    void apply(cdouble* x_ext, cdouble* y, const PcgState* st, cudaStream_t s) {
+        NcclApi& nc = NcclApi::get();
+        const bool comm = dc->world > 1 && (nsend > 0 || nhalo > 0);
+        cudaStream_t cs = overlap ? dc->comm_stream : s;
+        if (comm) {
+            if (nsend) k_halo_pack<<<stream_grid(nsend), kThreads, 0, s>>>(nsend, send_idx.p, x_ext, sendbuf.p, st);
+            if (overlap) {
+                MK_CUDA(cudaEventRecord(ev_pack, s));
+                MK_CUDA(cudaStreamWaitEvent(cs, ev_pack, 0));
+            }
+            MK_NCCL(nc.GroupStart());
+            for (int p = 0; p < dc->world; p++) {
+                if (p == dc->rank) continue;
+                if (send_counts[p]) MK_NCCL(nc.Send(sendbuf.p + send_off[p], 2 * (size_t)send_counts[p], ncclDouble, p, dc->comm, cs));
+                if (recv_counts[p]) MK_NCCL(nc.Recv(x_ext + nloc + recv_off[p], 2 * (size_t)recv_counts[p], ncclDouble, p, dc->comm, cs));
+            }
+            MK_NCCL(nc.GroupEnd());
+            if (overlap) MK_CUDA(cudaEventRecord(ev_halo, cs));
+        }
+        if (nint > 0) k_spmv_face_rows<<<stream_grid(nint), kThreads, 0, s>>>(nloc, 0, nint, S.diag, S.nbr.p, S.val.p, x_ext, y, st);
+        if (comm && overlap) MK_CUDA(cudaStreamWaitEvent(s, ev_halo, 0));
+        if (nloc > nint) k_spmv_face_rows<<<stream_grid(nloc - nint), kThreads, 0, s>>>(nloc, nint, nloc, S.diag, S.nbr.p, S.val.p, x_ext, y, st);
+        MK_CHECK_LAUNCH();
+    }
+    int launches_per_apply() const { return 3; }
+};
+
+// Distributed PCG: A = DistFaceOp, M = local multigrid V-cycle on the diagonal block (block-Jacobi over ranks) or identity.
+// Two all-reduces per iteration (<p,Ap>; {<r,r>, <r,z>}); the host looks at the state every `chunk` iterations.
+struct DistPcg {
+    int n = 0, next = 0;
+    cudaStream_t s = nullptr;
+    DistComm* dc = nullptr;
+    DevBuf<cdouble> r, z, p_ext, q;
+    DevBuf<PcgState> st;
+    DevBuf<double> part, partials;
+    DevBuf<unsigned int> ticket;
+    PcgState* h_st = nullptr;
+    int grid = 1;
+
+    DistPcg(int n_, int next_, DistComm* dc_, cudaStream_t s_) : n(n_), next(next_), s(s_), dc(dc_), r(n_), z(n_), p_ext(next_), q(n_), st(1), part(8),
+                                                                  partials(kMaxPartials * 4), ticket(1) {
+        ticket.zero(s);
+        st.zero(s);
+        part.zero(s);
+        p_ext.zero(s);
+        MK_CUDA(cudaMallocHost((void**)&h_st, sizeof(PcgState)));
+        grid = stream_grid(n);
+    }
+    ~DistPcg() { if (h_st) cudaFreeHost(h_st); }
+    ReduceWs ws() { return ReduceWs{partials.p, ticket.p}; }
+    void fetch() {
+        MK_CUDA(cudaMemcpyAsync(h_st, st.p, sizeof(PcgState), cudaMemcpyDeviceToHost, s));
+        MK_CUDA(cudaStreamSynchronize(s));
+    }
+    void precond(Precond<cdouble>* M, const cdouble* rr, cdouble* zz) {
+        if (M) M->apply(rr, zz, st.p, s);
+    }
+    // part = {<r,r>, <b,b>, <r,z>} -> state; p = z
+    void start(DistFaceOp& A, Precond<cdouble>* M, const cdouble* b, double tol, int maxit, int keep) {
+        precond(M, r.p, z.p);
+        const cdouble* zz = M ? z.p : r.p;
+        k_dist_dots<<<grid, kThreads, 0, s>>>(n, r.p, r.p, b, b, nullptr, part.p, ws(), nullptr);
+        k_dist_dots<<<grid, kThreads, 0, s>>>(n, r.p, zz, nullptr, nullptr, nullptr, part.p + 2, ws(), nullptr);
+        dc->allreduce_sum(part.p, 3, s);
+        k_dist_start<<<1, 1, 0, s>>>(st.p, part.p, tol * tol, maxit, keep);
+        MK_CUDA(cudaMemcpyAsync(p_ext.p, zz, sizeof(cdouble) * n, cudaMemcpyDeviceToDevice, s));
+        MK_CHECK_LAUNCH();
+    }
+    void iteration(DistFaceOp& A, Precond<cdouble>* M, cdouble* x) {
+        A.apply(p_ext.p, q.p, st.p, s);
+        k_dist_dots<<<grid, kThreads, 0, s>>>(n, p_ext.p, q.p, nullptr, nullptr, nullptr, part.p, ws(), st.p);
+        dc->allreduce_sum(part.p, 1, s);
+        k_dist_update_xr<<<grid, kThreads, 0, s>>>(n, x, r.p, p_ext.p, q.p, st.p, part.p, ws());
+        precond(M, r.p, z.p);
+        const cdouble* zz = M ? z.p : r.p;
+        k_dist_dots<<<grid, kThreads, 0, s>>>(n, r.p, zz, nullptr, nullptr, nullptr, part.p + 2, ws(), st.p);
+        dc->allreduce_sum(part.p + 1, 2, s);
+        k_dist_update_p<<<grid, kThreads, 0, s>>>(n, p_ext.p, zz, st.p, part.p);
+        k_dist_state<<<1, 1, 0, s>>>(st.p, part.p);
+        MK_CHECK_LAUNCH();
+    }
+    // solves L x = b from the x passed in (x_ext layout: halo part is scratch). Returns stats like Pcg::solve.
+    SolveStats solve(DistFaceOp& A, Precond<cdouble>* M, const cdouble* b, cdouble* x_ext, double tol, int maxit, int chunk = 8, int hint = 0) {
+        SolveStats out;
+        long launches = 0;
+        A.apply(x_ext, q.p, nullptr, s);
+        k_dist_residual<<<grid, kThreads, 0, s>>>(n, b, q.p, r.p);
+        int keep = 0;
+        for (int attempt = 0; attempt < 4; attempt++) {
+            start(A, M, b, tol, maxit, keep);
+            keep = 1;
+            int batch = hint > 0 ? std::min(std::max(hint, 1), 4 * chunk) : chunk;
+            while (true) {
+                for (int c = 0; c < batch; c++) iteration(A, M, x_ext);
+                launches += (long)batch * (8 + (M ? M->launches_per_apply() : 0));
+                fetch();
+                if (h_st->done) break;
+                batch = chunk;
+            }
+            // true residual
+            A.apply(x_ext, q.p, nullptr, s);
+            k_dist_residual<<<grid, kThreads, 0, s>>>(n, b, q.p, r.p);
+            k_dist_dots<<<grid, kThreads, 0, s>>>(n, r.p, r.p, nullptr, nullptr, nullptr, part.p + 4, ws(), nullptr);
+            dc->allreduce_sum(part.p + 4, 1, s);
+            double rr = 0;
+            MK_CUDA(cudaMemcpyAsync(&rr, part.p + 4, sizeof(double), cudaMemcpyDeviceToHost, s));
+            fetch();
+            out.iterations = h_st->iter;
+            out.relres = h_st->bnorm2 > 0 ? std::sqrt(rr / h_st->bnorm2) : 0.0;
+            out.restarts = attempt;
+            launches += 6;
+            if (out.relres <= tol * 1.0000001 || h_st->iter >= maxit || h_st->done == 2) break;
+        }
+        out.status = (out.relres <= tol * 1.0000001 || h_st->bnorm2 == 0) ? 0 : (h_st->iter >= maxit ? 1 : 2);
+        out.launches = launches;
+        return out;
+    }
+};
+
+}  // namespace mk

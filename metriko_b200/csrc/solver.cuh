@@ -10,6 +10,19 @@
 
 namespace mk {
 
+// Device allocations go through the stream-ordered pool (cudaMallocAsync) on the calling context's stream: a solve step
+// allocates and frees gigabytes of operators / hierarchies, and cudaMalloc / cudaFree round trips to the driver cost
+// hundreds of ms per step. Every C-ABI entry point sets the stream (AllocStreamScope) before touching a DevBuf.
+inline cudaStream_t& alloc_stream() {
+    static thread_local cudaStream_t s = nullptr;
+    return s;
+}
+struct AllocStreamScope {
+    cudaStream_t prev;
+    explicit AllocStreamScope(cudaStream_t s) : prev(alloc_stream()) { alloc_stream() = s; }
+    ~AllocStreamScope() { alloc_stream() = prev; }
+};
+
 template <class T>
 struct DevBuf {
     T* p = nullptr;
@@ -21,11 +34,11 @@ struct DevBuf {
     DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
     DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
     ~DevBuf() { release(); }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() { if (p) cudaFreeAsync(p, alloc_stream()); p = nullptr; n = 0; }
     void alloc(size_t n_) {
         release();
         n = n_;
-        if (n) MK_CUDA(cudaMalloc((void**)&p, n * sizeof(T)));
+        if (n) MK_CUDA(cudaMallocAsync((void**)&p, n * sizeof(T), alloc_stream()));
     }
     void zero(cudaStream_t s) { if (n) MK_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
     void upload(const T* h, size_t cnt, cudaStream_t s) { if (cnt) MK_CUDA(cudaMemcpyAsync(p, h, cnt * sizeof(T), cudaMemcpyHostToDevice, s)); }
