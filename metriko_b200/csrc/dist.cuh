@@ -271,12 +271,12 @@ struct DistPcg {
         MK_CUDA(cudaMemcpyAsync(h_st, st.p, sizeof(PcgState), cudaMemcpyDeviceToHost, s));
         MK_CUDA(cudaStreamSynchronize(s));
     }
-    void precond(Precond<cdouble>* M, const cdouble* rr, cdouble* zz) {
-        if (M) M->apply(rr, zz, st.p, s);
+    void precond(Precond<cdouble>* M, const cdouble* rr, cdouble* zz, bool unconditional = false) {
+        if (M) M->apply(rr, zz, unconditional ? nullptr : st.p, s);
     }
     // part = {<r,r>, <b,b>, <r,z>} -> state; p = z
     void start(DistFaceOp& A, Precond<cdouble>* M, const cdouble* b, double tol, int maxit, int keep) {
-        precond(M, r.p, z.p);
+        precond(M, r.p, z.p, true);  // the state still carries the previous solve's `done` flag here
         const cdouble* zz = M ? z.p : r.p;
         k_dist_dots<<<grid, kThreads, 0, s>>>(n, r.p, r.p, b, b, nullptr, part.p, ws(), nullptr);
         k_dist_dots<<<grid, kThreads, 0, s>>>(n, r.p, zz, nullptr, nullptr, nullptr, part.p + 2, ws(), nullptr);
