@@ -410,6 +410,9 @@ struct IgmRun {
         st.relres_max = std::max(st.relres_max, ss.relres);
         st.kernel_launches += ss.launches;
         if (ss.status != 0 && st.status == MK_OK) st.status = status_of(ss.status);
+        if (getenv("MK_VERBOSE"))
+            fprintf(stderr, "[mk] igm solve #%d: constraints %d, iterations %d (restarts %d), relres %.2e\n", st.outer_iterations, proj.k, ss.iterations,
+                    ss.restarts, ss.relres);
         return ss;
     }
     // Poisson stage: min ||length X2F x - F2|| s.t. UFull[fixed] x = vals  (ir_init.h:173-212)
