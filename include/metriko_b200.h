@@ -148,12 +148,19 @@ int mk_dfield_spmv_bench(mk_dfield* f, int reps, int overlap, double* ms_per_lau
 int mk_dfield_pcg(mk_dfield* f, const double* b_local, const double* x0_local, const mk_solve_opts* opts, double* x_local, mk_stats* stats);
 int mk_dfield_solve(mk_dfield* f, const double* u0_local, int n_iter, const mk_solve_opts* opts, double* x_local, mk_stats* stats);
 
-/* ---- host-side multigrid set-up, exposed for CPU tests of the hierarchy (no device needed): builds the same
- * smoothed-aggregation hierarchy the solvers use for a Hermitian (is_complex = 1, interleaved values) or symmetric CSR
+/* ---- multigrid set-up, exposed for tests. mk_amg_host_build is the host mirror (no device needed) of the device set-up the solvers
+ * run: it builds the same smoothed-aggregation hierarchy for a Hermitian (is_complex = 1, interleaved values) or symmetric CSR
  * matrix. cand = near-kernel candidate (real operators) or NULL. which: 0 = A_l, 1 = P_l (level l -> l+1),
  * 2 (level_get only) = the smoother's inverse diagonal of level l, written to val. ---- */
 typedef struct mk_amg_host mk_amg_host;
 int mk_amg_host_build(int n, const int* ptr, const int* col, const double* val, int is_complex, const double* cand, mk_amg_host** out);
+/* The same hierarchy built by the device set-up (what the solvers run); its levels are copied back into the same container so the
+ * accessors below serve both. Rows must have strictly increasing columns. */
+int mk_amg_dev_build(mk_ctx* ctx, int n, const int* ptr, const int* col, const double* val, int is_complex, mk_amg_host** out);
+/* The device set-up algebra, exposed for tests: op 0: C = A B (symbolic/numeric SpGEMM), op 1: C = A^T, op 2: C = A^H. CSR with
+ * strictly increasing columns per row; the result is level 0 / which 0 of the returned container (B ignored for op 1, 2). */
+int mk_dev_sparse_op(mk_ctx* ctx, int op, int is_complex, int a_rows, int a_cols, const int* a_ptr, const int* a_col, const double* a_val, int b_rows,
+                     int b_cols, const int* b_ptr, const int* b_col, const double* b_val, mk_amg_host** out);
 int mk_amg_host_num_levels(mk_amg_host* h);
 int mk_amg_host_level_info(mk_amg_host* h, int level, int which, int* rows, int* cols, int64_t* nnz, double* lmax);
 int mk_amg_host_level_get(mk_amg_host* h, int level, int which, int* ptr, int* col, double* val);

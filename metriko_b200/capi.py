@@ -95,6 +95,8 @@ def lib() -> C.CDLL:
         L.mk_dfield_pcg.argtypes = [vp, vp, vp, C.POINTER(SolveOpts), vp, C.POINTER(Stats)]
         L.mk_dfield_solve.argtypes = [vp, vp, C.c_int, C.POINTER(SolveOpts), vp, C.POINTER(Stats)]
         L.mk_amg_host_build.argtypes = [C.c_int, vp, vp, vp, C.c_int, vp, C.POINTER(vp)]
+        L.mk_amg_dev_build.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, C.POINTER(vp)]
+        L.mk_dev_sparse_op.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, C.POINTER(vp)]
         L.mk_amg_host_num_levels.argtypes = [vp]
         L.mk_amg_host_level_info.argtypes = [vp, C.c_int, C.c_int, ip, ip, i64p, dp]
         L.mk_amg_host_level_get.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
@@ -160,21 +162,8 @@ class Context:
             pass
 
 
-def amg_host_hierarchy(A, cand=None):
-    """Builds the solvers' smoothed-aggregation hierarchy on the host (no device) and returns
-    [(A_l, P_l or None, lmax_l, dinv_l)] (scipy CSR matrices, smoother diagonal) -- for CPU tests of the set-up."""
+def _read_hierarchy(L, h, dt):
     import scipy.sparse as sp
-    A = sp.csr_matrix(A)
-    A.sort_indices()
-    cx = np.iscomplexobj(A.data)
-    dt = np.complex128 if cx else np.float64
-    L = lib()
-    h = C.c_void_p()
-    val = np.ascontiguousarray(A.data, dt)
-    c = as_f64(cand) if cand is not None else None
-    rc = L.mk_amg_host_build(A.shape[0], ptr(as_i32(A.indptr)), ptr(as_i32(A.indices)), ptr(val), int(cx), ptr(c), C.byref(h))
-    if rc != MK_OK:
-        raise MkError(rc, "mk_amg_host_build")
     out = []
     try:
         nl = L.mk_amg_host_num_levels(h)
@@ -192,8 +181,65 @@ def amg_host_hierarchy(A, cand=None):
                 L.mk_amg_host_level_get(h, l, which, ptr(p_), ptr(c_), ptr(v_))
                 mats.append(sp.csr_matrix((v_, c_, p_), shape=(r.value, cc.value)))
             dinv = np.empty(mats[0].shape[0], dt)
-            L.mk_amg_host_level_get(h, l, 2, None, None, ptr(dinv))
+            if L.mk_amg_host_level_get(h, l, 2, None, None, ptr(dinv)) != MK_OK:
+                dinv = None
             out.append((mats[0], mats[1], lm.value, dinv))
     finally:
         L.mk_amg_host_destroy(h)
     return out
+
+
+def _canonical_csr(A):
+    import scipy.sparse as sp
+    A = sp.csr_matrix(A)
+    A.sum_duplicates()
+    A.sort_indices()
+    cx = np.iscomplexobj(A.data)
+    return A, cx, (np.complex128 if cx else np.float64)
+
+
+def amg_host_hierarchy(A, cand=None):
+    """Builds the solvers' smoothed-aggregation hierarchy with the host mirror (no device) and returns
+    [(A_l, P_l or None, lmax_l, dinv_l)] (scipy CSR matrices, smoother diagonal) -- for CPU tests of the set-up."""
+    A, cx, dt = _canonical_csr(A)
+    L = lib()
+    h = C.c_void_p()
+    val = np.ascontiguousarray(A.data, dt)
+    c = as_f64(cand) if cand is not None else None
+    rc = L.mk_amg_host_build(A.shape[0], ptr(as_i32(A.indptr)), ptr(as_i32(A.indices)), ptr(val), int(cx), ptr(c), C.byref(h))
+    if rc != MK_OK:
+        raise MkError(rc, "mk_amg_host_build")
+    return _read_hierarchy(L, h, dt)
+
+
+def amg_dev_hierarchy(ctx: "Context", A):
+    """The same hierarchy built by the device set-up (what the solvers run), copied back level by level."""
+    A, cx, dt = _canonical_csr(A)
+    h = C.c_void_p()
+    val = np.ascontiguousarray(A.data, dt)
+    ctx.check(ctx.L.mk_amg_dev_build(ctx.h, A.shape[0], ptr(as_i32(A.indptr)), ptr(as_i32(A.indices)), ptr(val), int(cx), C.byref(h)))
+    return _read_hierarchy(ctx.L, h, dt)
+
+
+def dev_sparse_op(ctx: "Context", op: str, A, B=None):
+    """Device set-up algebra for tests: op = 'matmul' (A @ B), 'T' (A^T) or 'H' (A^H); returns scipy CSR."""
+    A, cxa, _ = _canonical_csr(A)
+    cx = cxa
+    if B is not None:
+        B, cxb, _ = _canonical_csr(B)
+        cx = cxa or cxb
+    dt = np.complex128 if cx else np.float64
+    code = {"matmul": 0, "T": 1, "H": 2}[op]
+    h = C.c_void_p()
+    av = np.ascontiguousarray(A.data, dt)
+    args = [ctx.h, code, int(cx), A.shape[0], A.shape[1], ptr(as_i32(A.indptr)), ptr(as_i32(A.indices)), ptr(av)]
+    keep = []
+    if B is not None:
+        bv = np.ascontiguousarray(B.data, dt)
+        bp, bc = as_i32(B.indptr), as_i32(B.indices)
+        keep = [bv, bp, bc]
+        args += [B.shape[0], B.shape[1], ptr(bp), ptr(bc), ptr(bv)]
+    else:
+        args += [0, 0, None, None, None]
+    ctx.check(ctx.L.mk_dev_sparse_op(*args, C.byref(h)))
+    return _read_hierarchy(ctx.L, h, dt)[0][0]

@@ -38,6 +38,7 @@ struct AmgParams {
     double omega_scale = 4.0 / 3.0;  // prolongator smoothing omega = omega_scale / rho(D^{-1}A)
     int dense_row = 64;        // fine-level rows longer than this are "dense dofs": never aggregated with others, carried
                                // as singletons to the coarsest level (solved exactly there), l1-scaled in the smoother
+    int agg = 1;               // 0 = sequential greedy (Vanek), 1 = MIS(2) roots (parallel; what the device set-up runs)
 };
 
 // real_op: the real symmetric IGM / LM operators use a strength threshold (drops weak and wrong-signed cotan couplings
@@ -51,7 +52,14 @@ inline AmgParams amg_params_from_env(bool real_op = false) {
     if (const char* e = getenv("MK_AMG_COARSE")) p.coarse_max = atoi(e);
     if (const char* e = getenv("MK_AMG_OMEGA")) p.omega_scale = atof(e);
     if (const char* e = getenv("MK_AMG_DENSE")) p.dense_row = atoi(e);
+    if (const char* e = getenv("MK_AMG_AGG")) p.agg = atoi(e);
     return p;
+}
+
+// MK_SETUP=host: build hierarchies (and the IGM normal matrix) with the host mirror instead of the device set-up
+inline bool setup_on_host() {
+    const char* e = getenv("MK_SETUP");
+    return e && std::strcmp(e, "host") == 0;
 }
 
 template <class S>
@@ -166,6 +174,116 @@ inline int aggregate(const HostCsr<S>& A, double theta, const std::vector<S>* ca
     return nagg;
 }
 
+
+// ---- MIS(2) aggregation (Bell, Dalton, Olson 2012): the parallel aggregation the device set-up runs; this host version
+// executes the same synchronous rounds (every round reads the previous round's arrays only), so both produce the same
+// aggregates bit for bit and the host build stays the CPU mirror of the device build.
+__host__ __device__ inline uint32_t mis_hash(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+// key = state (2 bits: 0 removed, 1 undecided, 2 root) | 30 priority bits | 32 bits of ~index (ties go to the smaller index).
+// The first kMisIndexRounds rounds use priority 0, i.e. the smallest index wins: that is the lexicographically-first MIS(2) =
+// the sequential greedy root choice, which tiles structured mesh numberings regularly (fewer PCG iterations) and needs only a
+// handful of rounds on them; numberings with long dependency chains fall through to hashed priorities (O(log n) rounds).
+constexpr int kMisIndexRounds = 24;
+constexpr int kMisMaxRounds = 256;
+// a coupling must be stronger by this factor to displace an earlier candidate: equal-modulus couplings (the face operator's are all 1
+// up to an ulp of hypot) tie towards the smaller column on the host and on the device alike
+constexpr double kStrongerBy = 1.0 + 1e-12;
+__host__ __device__ inline uint64_t mis_key(int state, int i, bool hashed) {
+    return ((uint64_t)state << 62) | ((uint64_t)(hashed ? (mis_hash((uint32_t)i) & 0x3fffffffU) : 0u) << 32) | (uint32_t)(~(uint32_t)i);
+}
+__host__ __device__ inline int mis_key_index(uint64_t k) { return (int)(~(uint32_t)k); }
+
+template <class S>
+inline int aggregate_mis2(const HostCsr<S>& A, double theta, const std::vector<char>& dense, std::vector<int>& agg, std::vector<S>& tval,
+                          std::vector<int>& dense_coarse) {
+    const int n = A.rows;
+    const bool has_dense = !dense.empty();
+    std::vector<double> dabs(n, 0.0);
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; i++)
+        for (int k = A.ptr[i]; k < A.ptr[i + 1]; k++)
+            if (A.col[k] == i) dabs[i] = std::abs(A.val[k]);
+    auto strong = [&](int i, int k) {
+        const int j = A.col[k];
+        if (j == i || (has_dense && (dense[j] || dense[i]))) return false;
+        const double a = std::abs(A.val[k]);
+        return a > 0 && a * a >= theta * theta * dabs[i] * dabs[j];
+    };
+    std::vector<int> state(n);
+    std::vector<uint64_t> t1(n), t2(n);
+    for (int i = 0; i < n; i++) state[i] = (has_dense && dense[i]) ? 0 : 1;
+    for (int round = 0; round < kMisMaxRounds; round++) {
+        const bool hashed = round >= kMisIndexRounds;
+        long undecided = 0;
+#pragma omp parallel for schedule(static)
+        for (int i = 0; i < n; i++) {
+            uint64_t m = mis_key(state[i], i, hashed);
+            for (int k = A.ptr[i]; k < A.ptr[i + 1]; k++)
+                if (strong(i, k)) m = std::max(m, mis_key(state[A.col[k]], A.col[k], hashed));
+            t1[i] = m;
+        }
+#pragma omp parallel for schedule(static)
+        for (int i = 0; i < n; i++) {
+            uint64_t m = t1[i];
+            for (int k = A.ptr[i]; k < A.ptr[i + 1]; k++)
+                if (strong(i, k)) m = std::max(m, t1[A.col[k]]);
+            t2[i] = m;
+        }
+#pragma omp parallel for schedule(static) reduction(+ : undecided)
+        for (int i = 0; i < n; i++) {
+            if (state[i] != 1) continue;
+            if (mis_key_index(t2[i]) == i) state[i] = 2;
+            else if ((t2[i] >> 62) == 2) state[i] = 0;
+            else undecided++;
+        }
+        if (!undecided || round == kMisMaxRounds - 1) {
+            if (getenv("MK_VERBOSE")) fprintf(stderr, "[mk] mis2: n %d rounds %d undecided %ld\n", n, round + 1, undecided);
+            break;
+        }
+    }
+    // roots are numbered in index order
+    agg.assign(n, -1);
+    tval.assign(n, S(0));
+    int nagg = 0;
+    for (int i = 0; i < n; i++)
+        if (state[i] == 2) { agg[i] = nagg++; tval[i] = S(1); }
+    // round 1: neighbours of a root join it (strongest coupling, then smallest index)
+    std::vector<int> agg1 = agg;
+    std::vector<S> tv1 = tval;
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; i++) {
+        if (state[i] == 2 || (has_dense && dense[i])) continue;
+        double best = -1;
+        int bk = -1;
+        for (int k = A.ptr[i]; k < A.ptr[i + 1]; k++)
+            if (strong(i, k) && state[A.col[k]] == 2 && std::abs(A.val[k]) > best * kStrongerBy) { best = std::abs(A.val[k]); bk = k; }
+        if (bk >= 0) { agg1[i] = agg[A.col[bk]]; tv1[i] = unit_phase(S(-1) * A.val[bk]); }
+    }
+    // round 2: the rest (distance 2 from a root) join through their strongest assigned neighbour
+    agg = agg1;
+    tval = tv1;
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; i++) {
+        if (agg1[i] != -1 || (has_dense && dense[i])) continue;
+        double best = -1;
+        int bk = -1;
+        for (int k = A.ptr[i]; k < A.ptr[i + 1]; k++)
+            if (strong(i, k) && agg1[A.col[k]] != -1 && std::abs(A.val[k]) > best * kStrongerBy) { best = std::abs(A.val[k]); bk = k; }
+        if (bk >= 0) { agg[i] = agg1[A.col[bk]]; tval[i] = unit_phase(S(-1) * A.val[bk]) * tv1[A.col[bk]]; }
+    }
+    // leftovers (none when the strength graph is symmetric) and dense dofs become singletons, in index order
+    dense_coarse.clear();
+    for (int i = 0; i < n; i++)
+        if (agg[i] == -1 && !(has_dense && dense[i])) { agg[i] = nagg++; tval[i] = S(1); }
+    if (has_dense)
+        for (int i = 0; i < n; i++)
+            if (dense[i]) { agg[i] = nagg; tval[i] = S(1); dense_coarse.push_back(nagg); nagg++; }
+    return nagg;
+}
+
 template <class S>
 inline std::vector<AmgHostLevel<S>> build_hierarchy(HostCsr<S> A, std::vector<S> cand, bool use_cand, const AmgParams& prm) {
     std::vector<AmgHostLevel<S>> lv;
@@ -206,7 +324,8 @@ inline std::vector<AmgHostLevel<S>> build_hierarchy(HostCsr<S> A, std::vector<S>
         if (n - n_dense <= prm.coarse_max || (int)lv.size() + 1 >= prm.max_levels) { lv.push_back(std::move(L)); break; }
         std::vector<int> agg, dense_coarse;
         std::vector<S> tv;
-        const int nc = aggregate(L.A, prm.theta, use_cand ? &cand : nullptr, dense, agg, tv, dense_coarse);
+        const int nc = (prm.agg == 1 && !use_cand) ? aggregate_mis2(L.A, prm.theta, dense, agg, tv, dense_coarse)
+                                                   : aggregate(L.A, prm.theta, use_cand ? &cand : nullptr, dense, agg, tv, dense_coarse);
         tm.lap("aggregate");
         if (nc >= n * 0.8 || nc == 0) { lv.push_back(std::move(L)); break; }  // stagnation: stop here
         // normalise the tentative columns; the column norms are the coarse candidate

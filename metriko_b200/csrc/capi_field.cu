@@ -3,7 +3,7 @@
 #include <complex>
 #include <cstring>
 
-#include "amg.cuh"
+#include "amg_dev.cuh"
 #include "capi_util.cuh"
 #include "field.cuh"
 #include "metriko_b200.h"
@@ -154,9 +154,34 @@ int mk_field_get_operator(mk_field* f, int* rowptr, int* col, double* val, doubl
     MK_API_END(f->ctx)
 }
 
-// Multigrid hierarchy for the face operator: the assembled stencil is copied back once (126 MB at 1M vertices),
-// coarsened on the host, and level 0 keeps applying the device stencil kernel.
-static std::unique_ptr<AmgPrecond<cdouble>> build_face_amg(mk_field* f) {
+// CSR copy of the face stencil for the set-up algebra: row f = {diagonal, three neighbours} with sorted columns, one thread
+// per face. Two faces sharing two edges would give a repeated column; that is flagged (degenerate input) rather than merged.
+static __global__ void __launch_bounds__(kThreads) k_face_to_csr(int nF, double diag, const int* __restrict__ nbr, const cdouble* __restrict__ val,
+                                                                 int* __restrict__ ptr, int* __restrict__ col, cdouble* __restrict__ cval, int* __restrict__ dup) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f > nF) return;
+    ptr[f] = 4 * f;
+    if (f == nF) return;
+    int c[4] = {f, nbr[f], nbr[(size_t)nF + f], nbr[2 * (size_t)nF + f]};
+    cdouble v[4] = {make_c(diag, 0.0), ldc_nc(val + f), ldc_nc(val + (size_t)nF + f), ldc_nc(val + 2 * (size_t)nF + f)};
+#pragma unroll
+    for (int a = 1; a < 4; a++)  // insertion sort of 4 entries
+#pragma unroll
+        for (int b = a; b > 0; b--)
+            if (c[b] < c[b - 1]) {
+                const int tc = c[b]; c[b] = c[b - 1]; c[b - 1] = tc;
+                const cdouble tv = v[b]; v[b] = v[b - 1]; v[b - 1] = tv;
+            }
+    if (c[0] == c[1] || c[1] == c[2] || c[2] == c[3]) *dup = 1;
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        col[(size_t)4 * f + a] = c[a];
+        stc(cval + (size_t)4 * f + a, v[a]);
+    }
+}
+
+// host set-up (the CPU mirror; also the fallback for degenerate stencils with repeated neighbours)
+static std::unique_ptr<AmgPrecond<cdouble>> build_face_amg_host(mk_field* f) {
     cudaStream_t s = f->ctx->c.stream;
     const int nF = f->nF;
     StageTimer tm("field_amg");
@@ -173,7 +198,6 @@ static std::unique_ptr<AmgPrecond<cdouble>> build_face_amg(mk_field* f) {
     A.val.resize((size_t)4 * nF);
 #pragma omp parallel for schedule(static)
     for (int i = 0; i < nF; i++) {
-        // sorted columns within the row (duplicates summed would need care: two faces sharing two edges are not expected)
         std::pair<int, std::complex<double>> e[4] = {{i, {f->S.diag, 0.0}},
                                                      {nbr[i], v[i]},
                                                      {nbr[(size_t)nF + i], v[(size_t)nF + i]},
@@ -185,6 +209,26 @@ static std::unique_ptr<AmgPrecond<cdouble>> build_face_amg(mk_field* f) {
     A.ptr[nF] = 4 * nF;
     tm.lap("host CSR");
     return build_amg<cdouble>(s, std::move(A), {}, false, f->op.get(), amg_params_from_env());
+}
+
+// Multigrid hierarchy for the face operator, built on the device from a CSR copy of the stencil; level 0 keeps applying the
+// stencil kernel. MK_SETUP=host selects the host mirror.
+static std::unique_ptr<AmgPrecond<cdouble>> build_face_amg(mk_field* f) {
+    if (setup_on_host()) return build_face_amg_host(f);
+    cudaStream_t s = f->ctx->c.stream;
+    const int nF = f->nF;
+    DeviceCsr<cdouble> A;
+    A.rows = A.cols = nF;
+    A.nnz = (int64_t)4 * nF;
+    A.ptr.alloc((size_t)nF + 1);
+    A.col.alloc((size_t)4 * nF);
+    A.val.alloc((size_t)4 * nF);
+    DevBuf<int> dup(1);
+    dup.zero(s);
+    k_face_to_csr<<<(nF + kThreads) / kThreads, kThreads, 0, s>>>(nF, f->S.diag, f->S.nbr.p, f->S.val.p, A.ptr.p, A.col.p, A.val.p, dup.p);
+    MK_CHECK_LAUNCH();
+    if (dev_read_int(dup.p, s)) return build_face_amg_host(f);
+    return build_amg_device<cdouble>(s, std::move(A), f->op.get(), amg_params_from_env());
 }
 
 static void field_setup_solver(mk_field* f, const mk_solve_opts& o) {

@@ -5,7 +5,7 @@
 #include <cstring>
 #include <set>
 
-#include "amg.cuh"
+#include "amg_dev.cuh"
 #include "capi_util.cuh"
 #include "csr.cuh"
 #include "field.cuh"
@@ -49,7 +49,9 @@ extern "C" int mk_solve_smallest_eig_csc(mk_ctx* ctx, int n, const int* L_outer,
         for (int k = M_outer[c]; k < M_outer[c + 1]; k++)
             if (M_inner[k] == c) mass[c] += M_values[2 * k];
     DeviceCsr<cdouble> dA;
-    upload_host_csr<cdouble>(dA, A, s);
+    upload_csr_plain<cdouble>(dA, n, n, A.ptr.data(), A.col.data(), (const cdouble*)A.val.data(), nnz, s);
+    const bool dev_setup = !setup_on_host() && rows_sorted_strict(dA, s);
+    build_sell(dA, s);
     CsrOp<cdouble> op(&dA);
     DevBuf<double> dmass(n);
     dmass.upload(mass.data(), n, s);
@@ -58,7 +60,15 @@ extern "C" int mk_solve_smallest_eig_csc(mk_ctx* ctx, int n, const int* L_outer,
     MK_CUDA(cudaMemcpyAsync(xx.p, u.p, sizeof(cdouble) * n, cudaMemcpyDeviceToDevice, s));
     Pcg<cdouble> pcg(n, s);
     std::unique_ptr<AmgPrecond<cdouble>> amg;
-    if (o.precond == 1) amg = build_amg<cdouble>(s, std::move(A), {}, false, &op, amg_params_from_env());
+    if (o.precond == 1) {
+        if (dev_setup) {
+            DeviceCsr<cdouble> Ac;
+            copy_csr(dA, Ac, s);
+            amg = build_amg_device<cdouble>(s, std::move(Ac), &op, amg_params_from_env());
+        } else {
+            amg = build_amg<cdouble>(s, std::move(A), {}, false, &op, amg_params_from_env());
+        }
+    }
     MK_CUDA(cudaStreamSynchronize(s));
     const double setup_ms = ms_since(t0);
     auto t1 = hclock::now();
@@ -118,14 +128,24 @@ extern "C" int mk_spd_factorize(mk_ctx* ctx, int n, const int* outer, const int*
     A.ptr.assign(outer, outer + n + 1);
     A.col.assign(inner, inner + outer[n]);
     A.val.assign(values, values + outer[n]);
-    upload_host_csr<double>(h->A, A, s);
+    upload_csr_plain<double>(h->A, n, n, A.ptr.data(), A.col.data(), A.val.data(), (int64_t)A.col.size(), s);
+    const bool dev_setup = !setup_on_host() && rows_sorted_strict(h->A, s);
+    build_sell(h->A, s);
     h->op = std::make_unique<CsrOp<double>>(&h->A);
     h->pcg = std::make_unique<Pcg<double>>(n, s);
     h->b.alloc(n);
     h->x.alloc(n);
     // tentative prolongator by sign transport along the matrix' own couplings (amg.cuh): the constants are NOT a near-kernel
     // of these operators across seams (u, v rotate by k 90 degrees there), so no global candidate is used
-    if (h->o.precond == 1) h->amg = build_amg<double>(s, std::move(A), {}, false, h->op.get(), amg_params_from_env(true));
+    if (h->o.precond == 1) {
+        if (dev_setup) {
+            DeviceCsr<double> Ac;
+            copy_csr(h->A, Ac, s);
+            h->amg = build_amg_device<double>(s, std::move(Ac), h->op.get(), amg_params_from_env(true));
+        } else {
+            h->amg = build_amg<double>(s, std::move(A), {}, false, h->op.get(), amg_params_from_env(true));
+        }
+    }
     MK_CUDA(cudaStreamSynchronize(s));
     h->setup_ms = ms_since(t0);
     *out = h.release();
@@ -233,36 +253,85 @@ extern "C" int mk_igm_create(mk_ctx* ctx, int rows, int cols, const int64_t* x2f
     g->o = opts_or_default(opts);
     StageTimer tm("igm_create");
     g->UFull = csr_from_abi(ufull_rows, cols, uf_ptr, uf_col, uf_val);
-    // A0 = length^2 X^T X (host SpGEMM at set-up, as the reference's E = X2F^T X2F, ir_init.h:174); rhs0 = length X^T F2.
-    // X2F (48 M entries at 1M vertices) is read in place through the ABI pointers.
-    HostCsr<double> Xt = transpose_raw<double>(rows, cols, x2f_ptr, x2f_col, x2f_val);
-    tm.lap("transpose X");
-    HostCsr<double> A0 = matmul_raw<double>(Xt, cols, x2f_ptr, x2f_col, x2f_val);
-    tm.lap("A0 = Xt X");
-    const double l2 = length * length;
-#pragma omp parallel for
-    for (int64_t k = 0; k < (int64_t)A0.val.size(); k++) A0.val[k] *= l2;
-    std::vector<double> f2(F2, F2 + rows), rhs0;
-    matvec(Xt, f2, rhs0);
-    for (double& v : rhs0) v *= length;
-    upload_host_csr<double>(g->A0, A0, s);
     upload_host_csr<double>(g->dUFull, g->UFull, s);
     g->rhs0.alloc(cols);
-    g->rhs0.upload(rhs0.data(), cols, s);
-    g->opA0 = std::make_unique<CsrOp<double>>(&g->A0, 0.0);
-    g->opA = std::make_unique<CsrOp<double>>(&g->A0, 1e-4);  // wClose^2 = 0.01^2 (ir_loop.h:109)
     g->pcg = std::make_unique<Pcg<double>>(cols, s);
     g->x.alloc(cols); g->xprev.alloc(cols); g->b.alloc(cols); g->tmp.alloc(std::max(cols, ufull_rows));
-    MK_CUDA(cudaStreamSynchronize(s));
-    tm.lap("rhs0 + uploads");
-    if (g->o.precond == 1) {
-        // the host copy of A0 is no longer needed unshifted (the device holds it): shift in place, hand it to the set-up
+    const int64_t xnnz = x2f_ptr[rows];
+    // ---- device set-up: X^T by transposition, A0 = length^2 X^T X by the atomic-free symbolic/numeric SpGEMM (the assembly of the
+    // Poisson normal matrix E = X2F^T X2F, ir_init.h:174), rhs0 = length X^T F2, multigrid hierarchy of A0 + 1e-4 I.
+    bool dev_setup = !setup_on_host();
+    if (dev_setup) {
+        DeviceCsr<double> X;
+        X.rows = rows; X.cols = cols; X.nnz = xnnz;
+        X.ptr.alloc((size_t)rows + 1);
+        X.col.alloc((size_t)std::max<int64_t>(xnnz, 1));
+        X.val.alloc((size_t)std::max<int64_t>(xnnz, 1));
+        {
+            DevBuf<int64_t> p64((size_t)rows + 1);
+            p64.upload(x2f_ptr, (size_t)rows + 1, s);
+            k_narrow_ptr<<<(rows + 256) / 256, 256, 0, s>>>(rows + 1, p64.p, X.ptr.p);
+            MK_CHECK_LAUNCH();
+            X.col.upload(x2f_col, (size_t)xnnz, s);
+            X.val.upload(x2f_val, (size_t)xnnz, s);
+            MK_CUDA(cudaStreamSynchronize(s));
+        }
+        dev_setup = rows_sorted_strict(X, s);
+        if (dev_setup) {
+            tm.lap("upload X2F");
+            DeviceCsr<double> Xt;
+            transpose_dev<double>(X, Xt, false, s);
+            tm.lap("transpose X (device)");
+            spgemm<double>(Xt, X, g->A0, s);
+            k_scale_values<double><<<stream_grid(g->A0.nnz), kThreads, 0, s>>>(g->A0.nnz, g->A0.val.p, length * length);
+            tm.lap("A0 = Xt X (device)");
+            DevBuf<double> f2((size_t)rows);
+            f2.upload(F2, (size_t)rows, s);
+            csr_matvec<double>(Xt, f2.p, g->rhs0.p, length, s);
+            MK_CUDA(cudaStreamSynchronize(s));
+            DeviceCsr<double> As;
+            if (g->o.precond == 1) {
+                copy_csr(g->A0, As, s);
+                k_shift_diagonal<double><<<(cols + 255) / 256, 256, 0, s>>>(cols, As.ptr.p, As.col.p, As.val.p, 1e-4);
+                MK_CHECK_LAUNCH();
+            }
+            build_sell(g->A0, s);
+            g->opA0 = std::make_unique<CsrOp<double>>(&g->A0, 0.0);
+            g->opA = std::make_unique<CsrOp<double>>(&g->A0, 1e-4);  // wClose^2 = 0.01^2 (ir_loop.h:109)
+            tm.lap("rhs0 + layouts");
+            if (g->o.precond == 1) {
+                g->amg = build_amg_device<double>(s, std::move(As), g->opA.get(), amg_params_from_env(true));
+                tm.lap("build_amg_device");
+            }
+        }
+    }
+    if (!dev_setup) {
+        // host mirror (MK_SETUP=host, or X2F rows not sorted): A0 = length^2 X^T X by host SpGEMM, X2F read in place through the ABI pointers
+        HostCsr<double> Xt = transpose_raw<double>(rows, cols, x2f_ptr, x2f_col, x2f_val);
+        tm.lap("transpose X");
+        HostCsr<double> A0 = matmul_raw<double>(Xt, cols, x2f_ptr, x2f_col, x2f_val);
+        tm.lap("A0 = Xt X");
+        const double l2 = length * length;
+#pragma omp parallel for
+        for (int64_t k = 0; k < (int64_t)A0.val.size(); k++) A0.val[k] *= l2;
+        std::vector<double> f2(F2, F2 + rows), rhs0;
+        matvec(Xt, f2, rhs0);
+        for (double& v : rhs0) v *= length;
+        upload_host_csr<double>(g->A0, A0, s);
+        g->rhs0.upload(rhs0.data(), cols, s);
+        g->opA0 = std::make_unique<CsrOp<double>>(&g->A0, 0.0);
+        g->opA = std::make_unique<CsrOp<double>>(&g->A0, 1e-4);  // wClose^2 = 0.01^2 (ir_loop.h:109)
+        MK_CUDA(cudaStreamSynchronize(s));
+        tm.lap("rhs0 + uploads");
+        if (g->o.precond == 1) {
+            // the host copy of A0 is no longer needed unshifted (the device holds it): shift in place, hand it to the set-up
 #pragma omp parallel for schedule(static)
-        for (int i = 0; i < A0.rows; i++)
-            for (int k = A0.ptr[i]; k < A0.ptr[i + 1]; k++)
-                if (A0.col[k] == i) A0.val[k] += 1e-4;
-        g->amg = build_amg<double>(s, std::move(A0), {}, false, g->opA.get(), amg_params_from_env(true));
-        tm.lap("build_amg");
+            for (int i = 0; i < A0.rows; i++)
+                for (int k = A0.ptr[i]; k < A0.ptr[i + 1]; k++)
+                    if (A0.col[k] == i) A0.val[k] += 1e-4;
+            g->amg = build_amg<double>(s, std::move(A0), {}, false, g->opA.get(), amg_params_from_env(true));
+            tm.lap("build_amg");
+        }
     }
     MK_CUDA(cudaStreamSynchronize(s));
     g->setup_ms = ms_since(t0);

@@ -98,34 +98,26 @@ static __global__ void k_sell_fill(int rows, int n_slices, const int* __restrict
     }
 }
 
+// SELL-32 layout (+ long-row list) from the plain CSR arrays already on the device (rows, cols, nnz, ptr, col, val set)
 template <class T>
-inline void upload_csr(DeviceCsr<T>& A, int rows, int cols, const std::vector<int>& ptr, const std::vector<int>& col,
-                       const std::vector<T>& val, cudaStream_t s) {
-    A.rows = rows;
-    A.cols = cols;
-    A.nnz = (int64_t)col.size();
-    A.ptr.alloc(rows + 1);
-    A.col.alloc(col.size());
-    A.val.alloc(val.size());
-    A.ptr.upload(ptr.data(), rows + 1, s);
-    A.col.upload(col.data(), col.size(), s);
-    A.val.upload(val.data(), val.size(), s);
+inline void build_sell(DeviceCsr<T>& A, cudaStream_t s) {
+    const int rows = A.rows;
     const int ns = (rows + 31) / 32;
     A.n_slices = ns;
-    DevBuf<int> width(ns), counter(1);
-    A.sl_ptr.alloc(ns + 1);
-    A.long_bits.alloc(ns);
+    DevBuf<int> width(std::max(ns, 1)), counter(1);
+    A.sl_ptr.alloc((size_t)ns + 1);
+    A.long_bits.alloc(std::max(ns, 1));
     A.long_rows.alloc(std::max(1, std::min(rows, 1 << 16)));  // more than 65k dense rows would not be a sparse operator
     counter.zero(s);
-    const int wg = (ns * 32 + kThreads - 1) / kThreads;
+    const int wg = std::max(1, (ns * 32 + kThreads - 1) / kThreads);
     k_sell_width<<<wg, kThreads, 0, s>>>(rows, ns, A.ptr.p, width.p, A.long_bits.p, A.long_rows.p, counter.p);
     k_scan_exclusive<<<1, 1024, 0, s>>>(ns, width.p, A.sl_ptr.p);
     MK_CHECK_LAUNCH();
     int tot = 0, nl = 0;
     MK_CUDA(cudaMemcpyAsync(&tot, A.sl_ptr.p + ns, sizeof(int), cudaMemcpyDeviceToHost, s));
     MK_CUDA(cudaMemcpyAsync(&nl, counter.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-    MK_CUDA(cudaStreamSynchronize(s));  // also: host vectors may die after return
-    if (tot < 0 || nl > (1 << 16)) throw std::invalid_argument("upload_csr: matrix too large / too many dense rows for the SELL layout");
+    MK_CUDA(cudaStreamSynchronize(s));
+    if (tot < 0 || nl > (1 << 16)) throw std::invalid_argument("build_sell: matrix too large / too many dense rows for the SELL layout");
     A.n_long = nl;
     A.sl_col.alloc((size_t)std::max(tot, 1));
     A.sl_val.alloc((size_t)std::max(tot, 1));
@@ -136,6 +128,27 @@ inline void upload_csr(DeviceCsr<T>& A, int rows, int cols, const std::vector<in
         A.ylong.alloc(rows);
         A.ylong.zero(s);
     }
+}
+
+// plain CSR arrays only (operands of the device set-up algebra, devcsr.cuh)
+template <class T>
+inline void upload_csr_plain(DeviceCsr<T>& A, int rows, int cols, const int* ptr, const int* col, const T* val, int64_t nnz, cudaStream_t s) {
+    A.rows = rows;
+    A.cols = cols;
+    A.nnz = nnz;
+    A.ptr.alloc((size_t)rows + 1);
+    A.col.alloc((size_t)std::max<int64_t>(nnz, 1));
+    A.val.alloc((size_t)std::max<int64_t>(nnz, 1));
+    A.ptr.upload(ptr, (size_t)rows + 1, s);
+    A.col.upload(col, (size_t)nnz, s);
+    A.val.upload(val, (size_t)nnz, s);
+}
+
+template <class T>
+inline void upload_csr(DeviceCsr<T>& A, int rows, int cols, const std::vector<int>& ptr, const std::vector<int>& col,
+                       const std::vector<T>& val, cudaStream_t s) {
+    upload_csr_plain<T>(A, rows, cols, ptr.data(), col.data(), val.data(), (int64_t)col.size(), s);
+    build_sell(A, s);  // synchronises the stream: the host vectors may die after return
 }
 
 // one CTA per long row: ylong[row] = sum_k val_k x[col_k]
