@@ -196,6 +196,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     # device-resident inputs for `value`
     u0_t = torch.from_numpy(u0).to(dev)
     x_t = torch.empty_like(u0_t)
+    x2f_dev = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (X2F.indptr.astype(np.int64), X2F.indices.astype(np.int32),
+                                                                            X2F.data.astype(np.float64), np.asarray(inp["F2"], np.float64))]
+    dev_ptrs = tuple(int(t.data_ptr()) for t in x2f_dev)
 
     # pinned host copies for `e2e`
     keep = []
@@ -213,13 +216,14 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     stage = {}
 
     def step_resident():
-        """inputs in HBM: field arrays uploaded once (F), u0/x device tensors, IGM operator inputs device-resident"""
+        """inputs in HBM: field arrays uploaded once (F), u0 / x device tensors, X2F and F2 device tensors (mk_igm_create_dev);
+        UFull is read on the host by the rounding loop (candidate rows) and uploaded by the library"""
         ta = time.perf_counter()
         F.assemble()
         st_f = F.solve_dev(u0_t.data_ptr(), 50, x_t.data_ptr())
         tb = time.perf_counter()
         prob = api.IgmProblem(ctx, X2F, UFull, inp["F2"], inp["length"], raw=(host["x2f_ptr"], host["x2f_col"], host["x2f_val"],
-                                                                             host["uf_ptr"], host["uf_col"], host["uf_val"], host["F2"]))
+                                                                             host["uf_ptr"], host["uf_col"], host["uf_val"], host["F2"]), dev=dev_ptrs)
         out = prob.round(inp["fixedIdcs"], inp["fixedVals"], inp["singularIdcs"], inp["integerIdcs"], True, False)
         prob.close()
         tc = time.perf_counter()

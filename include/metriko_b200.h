@@ -109,6 +109,11 @@ int mk_spd_spmv_bench(mk_spd* s, int reps, int fused_dot, double* ms_per_launch)
 int mk_igm_create(mk_ctx* ctx, int rows, int cols, const int64_t* x2f_ptr, const int* x2f_col, const double* x2f_val,
                   int ufull_rows, const int64_t* uf_ptr, const int* uf_col, const double* uf_val, const double* F2,
                   double length, const mk_solve_opts* opts, mk_igm** out);
+/* Same, with X2F (ptr / col / val) and F2 already resident on the device (device pointers; the HBM-resident timing path). UFull stays a
+ * host matrix: the rounding loop reads candidate rows from it on the host. X2F rows must have strictly increasing columns. */
+int mk_igm_create_dev(mk_ctx* ctx, int rows, int cols, const int64_t* x2f_ptr_dev, const int* x2f_col_dev, const double* x2f_val_dev,
+                      int ufull_rows, const int64_t* uf_ptr, const int* uf_col, const double* uf_val, const double* F2_dev,
+                      double length, const mk_solve_opts* opts, mk_igm** out);
 int mk_igm_destroy(mk_igm* g);
 /* NaiveIntegration Poisson solve (iter_rounding_init.h:173-212): min ||length X2F x - F2|| s.t. UFull[fixedIdcs] x = fixedVals.
  * x_small: cols, x0_full: ufull_rows (either may be NULL). */
@@ -140,11 +145,17 @@ int mk_dist_destroy(mk_dist* d);
 int mk_dfield_create(mk_dist* d, int n_local, int n_interior, int n_halo, const int* nbr_local, const double* val, const double* mass,
                      const int* send_counts, const int* recv_counts, const int* send_idx, mk_dfield** out);
 int mk_dfield_destroy(mk_dfield* f);
+/* Global multigrid hierarchy for the partitioned solves: every rank passes the SAME global stencil (nbr / val [3][nF], global face
+ * ids; the layout mk_field_get_operator reads back) and local_to_global[n_local], the global row of each local row. The hierarchy is
+ * built redundantly on every rank by the deterministic device set-up; level 0 runs distributed (halo exchange), the restricted
+ * residual is summed with one NCCL all-reduce and the coarse levels are replicated. Collective. */
+int mk_dfield_set_global(mk_dfield* f, int nF, const int* nbr, const double* val, const int* local_to_global);
 /* y = (L x) on the owned rows: pack -> NCCL send/recv (own stream) overlapped with the interior rows -> boundary rows. Collective. */
 int mk_dfield_spmv(mk_dfield* f, const double* x_local, double* y_local);
 int mk_dfield_spmv_bench(mk_dfield* f, int reps, int overlap, double* ms_per_launch);
-/* one distributed PCG solve L x = b, and the 50-step inverse iteration; preconditioner = multigrid V-cycle on each rank's diagonal
- * block (block-Jacobi across ranks). Collective: every rank calls with its rows. */
+/* one distributed PCG solve L x = b, and the 50-step inverse iteration. opts.precond: 0 none; 1 the global hierarchy of
+ * mk_dfield_set_global (falls back to 2 when it was not called); 2 a multigrid V-cycle on each rank's diagonal block (block-Jacobi
+ * across ranks). Collective: every rank calls with its rows. */
 int mk_dfield_pcg(mk_dfield* f, const double* b_local, const double* x0_local, const mk_solve_opts* opts, double* x_local, mk_stats* stats);
 int mk_dfield_solve(mk_dfield* f, const double* u0_local, int n_iter, const mk_solve_opts* opts, double* x_local, mk_stats* stats);
 

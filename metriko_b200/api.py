@@ -164,10 +164,24 @@ class CholeskyWrapper:
 class IgmProblem:
     """Device-resident IGM problem (mk_igm): A0 = length^2 X2F^T X2F assembled on the device, UFull, F2."""
 
-    def __init__(self, ctx: Context, X2F, UFull, F2, length: float, raw=None, **opts):
+    def __init__(self, ctx: Context, X2F, UFull, F2, length: float, raw=None, dev=None, **opts):
         """`raw` = (x2f_ptr i64, x2f_col i32, x2f_val f64, uf_ptr i64, uf_col i32, uf_val f64, F2 f64): the C-ABI arrays
-        themselves (e.g. pinned buffers), used as they are; X2F / UFull then only give the shapes."""
+        themselves (e.g. pinned buffers), used as they are; X2F / UFull then only give the shapes.
+        `dev` = (x2f_ptr, x2f_col, x2f_val, F2) raw DEVICE pointers (ints) of the same arrays already resident in HBM
+        (mk_igm_create_dev); `raw` must then be given too (its UFull arrays are read on the host)."""
         self.ctx = ctx
+        if dev is not None:
+            assert raw is not None
+            a = list(raw)
+            X, U = X2F, UFull
+            self.rows, self.cols = X.shape
+            self.ufull_rows = U.shape[0]
+            self.h = C.c_void_p()
+            o = default_opts(**opts)
+            ctx.check(ctx.L.mk_igm_create_dev(ctx.h, self.rows, self.cols, C.c_void_p(dev[0]), C.c_void_p(dev[1]), C.c_void_p(dev[2]), self.ufull_rows,
+                                              ptr(a[3]), ptr(a[4]), ptr(a[5]), C.c_void_p(dev[3]), float(length), C.byref(o), C.byref(self.h)))
+            self.stats = None
+            return
         if raw is None:
             X = sp.csr_matrix(X2F, dtype=np.float64)
             U = sp.csr_matrix(UFull, dtype=np.float64)

@@ -80,6 +80,7 @@ def lib() -> C.CDLL:
         L.mk_spd_destroy.argtypes = [vp]
         L.mk_spd_spmv_bench.argtypes = [vp, C.c_int, C.c_int, dp]
         L.mk_igm_create.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp, C.c_double, C.POINTER(SolveOpts), C.POINTER(vp)]
+        L.mk_igm_create_dev.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp, C.c_double, C.POINTER(SolveOpts), C.POINTER(vp)]
         L.mk_igm_destroy.argtypes = [vp]
         L.mk_igm_poisson.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.POINTER(Stats)]
         L.mk_igm_round.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp, ip, vp, vp, C.POINTER(Stats)]
@@ -90,6 +91,7 @@ def lib() -> C.CDLL:
         L.mk_dist_destroy.argtypes = [vp]
         L.mk_dfield_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]
         L.mk_dfield_destroy.argtypes = [vp]
+        L.mk_dfield_set_global.argtypes = [vp, C.c_int, vp, vp, vp]
         L.mk_dfield_spmv.argtypes = [vp, vp, vp]
         L.mk_dfield_spmv_bench.argtypes = [vp, C.c_int, C.c_int, dp]
         L.mk_dfield_pcg.argtypes = [vp, vp, vp, C.POINTER(SolveOpts), vp, C.POINTER(Stats)]

@@ -20,7 +20,8 @@ struct mk_dfield {
     int device = 0;
     DistFaceOp op;
     std::unique_ptr<FaceOp> blk_op;               // level 0 of the local hierarchy
-    std::unique_ptr<AmgPrecond<cdouble>> amg;     // multigrid on the diagonal block (block-Jacobi across ranks)
+    std::unique_ptr<AmgPrecond<cdouble>> amg;     // multigrid on the diagonal block (block-Jacobi across ranks; opts.precond = 2)
+    std::unique_ptr<DistAmgPrecond> gamg;         // global hierarchy, level 0 distributed, coarse levels replicated (opts.precond = 1)
     std::unique_ptr<DistPcg> pcg;
     DevBuf<cdouble> u, x_ext, b;
     std::vector<int> h_nbr;                       // host copies for the hierarchy set-up
@@ -121,6 +122,67 @@ int mk_dfield_create(mk_dist* d, int n_local, int n_interior, int n_halo, const 
     MK_API_END(d->ctx)
 }
 
+// Global multigrid hierarchy for the partitioned operator (DistAmgPrecond, dist.cuh): every rank passes the same global stencil
+// (nbr / val [3][nF], global face ids, as mk_field_get_operator lays it out) and the global row of each of its local rows.
+int mk_dfield_set_global(mk_dfield* f, int nF, const int* nbr, const double* val, const int* local_to_global) {
+    if (!f || nF <= 0 || !nbr || !val || !local_to_global) return MK_ERR_ARG;
+    MK_API_BEGIN(f->d->ctx)
+    MK_CUDA(cudaSetDevice(f->d->ctx->c.device));
+    cudaStream_t s = f->d->ctx->c.stream;
+    const int nloc = f->op.nloc;
+    for (int i = 0; i < nloc; i++)
+        if (local_to_global[i] < 0 || local_to_global[i] >= nF) throw std::invalid_argument("mk_dfield_set_global: row map out of range");
+    auto g = std::make_unique<DistAmgPrecond>();
+    g->A = &f->op;
+    g->dc = &f->d->c;
+    g->prm = amg_params_from_env();
+    g->nloc = nloc;
+    g->next = nloc + f->op.nhalo;
+    {
+        DevBuf<int> dn((size_t)3 * nF), dup(1);
+        DevBuf<cdouble> dv((size_t)3 * nF);
+        dn.upload(nbr, (size_t)3 * nF, s);
+        dv.upload((const cdouble*)val, (size_t)3 * nF, s);
+        dup.zero(s);
+        DeviceCsr<cdouble> A;
+        A.rows = A.cols = nF;
+        A.nnz = (int64_t)4 * nF;
+        A.ptr.alloc((size_t)nF + 1);
+        A.col.alloc((size_t)4 * nF);
+        A.val.alloc((size_t)4 * nF);
+        k_face_to_csr<<<(nF + kThreads) / kThreads, kThreads, 0, s>>>(nF, f->op.S.diag, dn.p, dv.p, A.ptr.p, A.col.p, A.val.p, dup.p);
+        MK_CHECK_LAUNCH();
+        if (dev_read_int(dup.p, s)) throw std::invalid_argument("mk_dfield_set_global: two faces share two edges (degenerate stencil)");
+        g->G = build_amg_device<cdouble>(s, std::move(A), &g->null_op, g->prm);
+    }
+    if (g->ready()) {
+        AmgLevelDev<cdouble>& L0 = g->G->lv[0];
+        DevBuf<int> l2g(nloc);
+        l2g.upload(local_to_global, nloc, s);
+        csr_gather_rows<cdouble>(L0.P, l2g.p, nloc, g->P0, s);
+        transpose_dev<cdouble>(g->P0, g->R0, true, s);
+        build_sell(g->P0, s);
+        build_sell(g->R0, s);
+        g->dinv.alloc(nloc);
+        k_gather_values<cdouble><<<(nloc + 255) / 256, 256, 0, s>>>(nloc, l2g.p, L0.dinv.p, g->dinv.p);
+        MK_CHECK_LAUNCH();
+        g->lmax = L0.lmax;
+        g->n1 = g->G->lv[1].n;
+        g->r.alloc(nloc); g->q.alloc(nloc); g->d_ext.alloc(g->next);
+        g->d_ext.zero(s);
+        MK_CUDA(cudaStreamSynchronize(s));
+        // the replicated level-0 pieces are no longer needed
+        L0.P = DeviceCsr<cdouble>();
+        L0.R = DeviceCsr<cdouble>();
+        L0.r.release(); L0.d.release(); L0.q.release(); L0.dinv.release();
+        f->gamg = std::move(g);
+    }
+    MK_CUDA(cudaStreamSynchronize(s));
+    MK_API_END(f->d->ctx)
+}
+
+static Precond<cdouble>* dfield_precond(mk_dfield* f, const mk_solve_opts& o);
+
 int mk_dfield_destroy(mk_dfield* f) {
     if (!f) return MK_OK;
     AllocStreamScope sc(f->stream);
@@ -195,6 +257,14 @@ static void dfield_setup_precond(mk_dfield* f) {
     f->amg = build_amg<cdouble>(f->d->ctx->c.stream, std::move(A), {}, false, f->blk_op.get(), amg_params_from_env());
 }
 
+// opts.precond: 0 none, 1 the global hierarchy when mk_dfield_set_global was called (else the local one), 2 local block-Jacobi hierarchy
+static Precond<cdouble>* dfield_precond(mk_dfield* f, const mk_solve_opts& o) {
+    if (o.precond == 0) return nullptr;
+    if (o.precond == 1 && f->gamg && f->gamg->ready()) return f->gamg.get();
+    dfield_setup_precond(f);
+    return f->amg.get();
+}
+
 // Inverse iteration (sls.h:44-51) on the partitioned operator: the same recurrence as the single-GPU driver, every scalar an
 // all-reduce of local partial sums. u0_local / x_local: this rank's rows in the plan's local order, host, complex interleaved.
 int mk_dfield_solve(mk_dfield* f, const double* u0_local, int n_iter, const mk_solve_opts* opts, double* x_local, mk_stats* stats) {
@@ -206,12 +276,11 @@ int mk_dfield_solve(mk_dfield* f, const double* u0_local, int n_iter, const mk_s
     mk_solve_opts o;
     if (opts) o = *opts; else mk_default_opts(&o);
     auto t0 = std::chrono::steady_clock::now();
-    if (o.precond == 1) dfield_setup_precond(f);
+    Precond<cdouble>* M = dfield_precond(f, o);
     MK_CUDA(cudaStreamSynchronize(s));
     auto t1 = std::chrono::steady_clock::now();
     DistPcg& pcg = *f->pcg;
     DistFaceOp& A = f->op;
-    Precond<cdouble>* M = o.precond == 1 ? f->amg.get() : nullptr;
     const int n = A.nloc, grid = pcg.grid;
     f->u.upload((const cdouble*)u0_local, n, s);
     MK_CUDA(cudaMemcpyAsync(f->x_ext.p, f->u.p, sizeof(cdouble) * n, cudaMemcpyDeviceToDevice, s));
@@ -277,14 +346,14 @@ int mk_dfield_pcg(mk_dfield* f, const double* b_local, const double* x0_local, c
     mk_solve_opts o;
     if (opts) o = *opts; else mk_default_opts(&o);
     auto t0 = std::chrono::steady_clock::now();
-    if (o.precond == 1) dfield_setup_precond(f);
+    Precond<cdouble>* M = dfield_precond(f, o);
     MK_CUDA(cudaStreamSynchronize(s));
     auto t1 = std::chrono::steady_clock::now();
     const int n = f->op.nloc;
     f->b.upload((const cdouble*)b_local, n, s);
     if (x0_local) f->x_ext.upload((const cdouble*)x0_local, n, s);
     else f->x_ext.zero(s);
-    SolveStats ss = f->pcg->solve(f->op, o.precond == 1 ? f->amg.get() : nullptr, f->b.p, f->x_ext.p, o.tol, o.max_iter, 8, 0);
+    SolveStats ss = f->pcg->solve(f->op, M, f->b.p, f->x_ext.p, o.tol, o.max_iter, 8, 0);
     f->x_ext.download((cdouble*)x_local, n, s);
     MK_CUDA(cudaStreamSynchronize(s));
     auto t2 = std::chrono::steady_clock::now();

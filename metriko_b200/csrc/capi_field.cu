@@ -154,32 +154,6 @@ int mk_field_get_operator(mk_field* f, int* rowptr, int* col, double* val, doubl
     MK_API_END(f->ctx)
 }
 
-// CSR copy of the face stencil for the set-up algebra: row f = {diagonal, three neighbours} with sorted columns, one thread
-// per face. Two faces sharing two edges would give a repeated column; that is flagged (degenerate input) rather than merged.
-static __global__ void __launch_bounds__(kThreads) k_face_to_csr(int nF, double diag, const int* __restrict__ nbr, const cdouble* __restrict__ val,
-                                                                 int* __restrict__ ptr, int* __restrict__ col, cdouble* __restrict__ cval, int* __restrict__ dup) {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f > nF) return;
-    ptr[f] = 4 * f;
-    if (f == nF) return;
-    int c[4] = {f, nbr[f], nbr[(size_t)nF + f], nbr[2 * (size_t)nF + f]};
-    cdouble v[4] = {make_c(diag, 0.0), ldc_nc(val + f), ldc_nc(val + (size_t)nF + f), ldc_nc(val + 2 * (size_t)nF + f)};
-#pragma unroll
-    for (int a = 1; a < 4; a++)  // insertion sort of 4 entries
-#pragma unroll
-        for (int b = a; b > 0; b--)
-            if (c[b] < c[b - 1]) {
-                const int tc = c[b]; c[b] = c[b - 1]; c[b - 1] = tc;
-                const cdouble tv = v[b]; v[b] = v[b - 1]; v[b - 1] = tv;
-            }
-    if (c[0] == c[1] || c[1] == c[2] || c[2] == c[3]) *dup = 1;
-#pragma unroll
-    for (int a = 0; a < 4; a++) {
-        col[(size_t)4 * f + a] = c[a];
-        stc(cval + (size_t)4 * f + a, v[a]);
-    }
-}
-
 // host set-up (the CPU mirror; also the fallback for degenerate stencils with repeated neighbours)
 static std::unique_ptr<AmgPrecond<cdouble>> build_face_amg_host(mk_field* f) {
     cudaStream_t s = f->ctx->c.stream;

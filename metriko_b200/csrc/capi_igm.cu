@@ -235,12 +235,36 @@ static HostCsr<double> csr_from_abi(int rows, int cols, const int64_t* ptr, cons
     return A;
 }
 
-extern "C" int mk_igm_create(mk_ctx* ctx, int rows, int cols, const int64_t* x2f_ptr, const int* x2f_col, const double* x2f_val,
-                             int ufull_rows, const int64_t* uf_ptr, const int* uf_col, const double* uf_val, const double* F2,
-                             double length, const mk_solve_opts* opts, mk_igm** out) {
+static int igm_create_impl(mk_ctx* ctx, int rows, int cols, const int64_t* x2f_ptr, const int* x2f_col, const double* x2f_val,
+                           int ufull_rows, const int64_t* uf_ptr, const int* uf_col, const double* uf_val, const double* F2,
+                           double length, const mk_solve_opts* opts, mk_igm** out, bool on_device) {
     if (!ctx || !out || rows <= 0 || cols <= 0 || !x2f_ptr || !x2f_col || !x2f_val || !uf_ptr || !uf_col || !uf_val || !F2) return MK_ERR_ARG;
-    if (x2f_ptr[rows] > 2000000000LL) return MK_ERR_ARG;
     MK_API_BEGIN(ctx)
+    // X2F (and F2) may already be resident in HBM (mk_igm_create_dev); the host mirror path then works on a downloaded copy
+    std::vector<int64_t> h_ptr;
+    std::vector<int> h_col;
+    std::vector<double> h_val, h_f2;
+    const int64_t* d_x2f_ptr = x2f_ptr;
+    const int* d_x2f_col = x2f_col;
+    const double* d_x2f_val = x2f_val;
+    const double* d_F2 = F2;
+    int64_t xnnz_in = 0;
+    if (on_device) {
+        MK_CUDA(cudaSetDevice(ctx->c.device));
+        MK_CUDA(cudaMemcpy(&xnnz_in, x2f_ptr + rows, sizeof(int64_t), cudaMemcpyDeviceToHost));
+        if (setup_on_host()) {
+            h_ptr.resize((size_t)rows + 1); h_col.resize((size_t)xnnz_in); h_val.resize((size_t)xnnz_in); h_f2.resize((size_t)rows);
+            MK_CUDA(cudaMemcpy(h_ptr.data(), x2f_ptr, sizeof(int64_t) * ((size_t)rows + 1), cudaMemcpyDeviceToHost));
+            MK_CUDA(cudaMemcpy(h_col.data(), x2f_col, sizeof(int) * (size_t)xnnz_in, cudaMemcpyDeviceToHost));
+            MK_CUDA(cudaMemcpy(h_val.data(), x2f_val, sizeof(double) * (size_t)xnnz_in, cudaMemcpyDeviceToHost));
+            MK_CUDA(cudaMemcpy(h_f2.data(), F2, sizeof(double) * (size_t)rows, cudaMemcpyDeviceToHost));
+            x2f_ptr = h_ptr.data(); x2f_col = h_col.data(); x2f_val = h_val.data(); F2 = h_f2.data();
+            on_device = false;
+        }
+    } else {
+        xnnz_in = x2f_ptr[rows];
+    }
+    if (xnnz_in > 2000000000LL) throw std::invalid_argument("mk_igm_create: X2F too large for int32 CSR");
     MK_CUDA(cudaSetDevice(ctx->c.device));
     cudaStream_t s = ctx->c.stream;
     auto t0 = hclock::now();
@@ -257,7 +281,7 @@ extern "C" int mk_igm_create(mk_ctx* ctx, int rows, int cols, const int64_t* x2f
     g->rhs0.alloc(cols);
     g->pcg = std::make_unique<Pcg<double>>(cols, s);
     g->x.alloc(cols); g->xprev.alloc(cols); g->b.alloc(cols); g->tmp.alloc(std::max(cols, ufull_rows));
-    const int64_t xnnz = x2f_ptr[rows];
+    const int64_t xnnz = xnnz_in;
     // ---- device set-up: X^T by transposition, A0 = length^2 X^T X by the atomic-free symbolic/numeric SpGEMM (the assembly of the
     // Poisson normal matrix E = X2F^T X2F, ir_init.h:174), rhs0 = length X^T F2, multigrid hierarchy of A0 + 1e-4 I.
     bool dev_setup = !setup_on_host();
@@ -267,7 +291,12 @@ extern "C" int mk_igm_create(mk_ctx* ctx, int rows, int cols, const int64_t* x2f
         X.ptr.alloc((size_t)rows + 1);
         X.col.alloc((size_t)std::max<int64_t>(xnnz, 1));
         X.val.alloc((size_t)std::max<int64_t>(xnnz, 1));
-        {
+        if (on_device) {
+            k_narrow_ptr<<<(rows + 256) / 256, 256, 0, s>>>(rows + 1, d_x2f_ptr, X.ptr.p);
+            MK_CHECK_LAUNCH();
+            MK_CUDA(cudaMemcpyAsync(X.col.p, d_x2f_col, sizeof(int) * (size_t)xnnz, cudaMemcpyDeviceToDevice, s));
+            MK_CUDA(cudaMemcpyAsync(X.val.p, d_x2f_val, sizeof(double) * (size_t)xnnz, cudaMemcpyDeviceToDevice, s));
+        } else {
             DevBuf<int64_t> p64((size_t)rows + 1);
             p64.upload(x2f_ptr, (size_t)rows + 1, s);
             k_narrow_ptr<<<(rows + 256) / 256, 256, 0, s>>>(rows + 1, p64.p, X.ptr.p);
@@ -277,6 +306,7 @@ extern "C" int mk_igm_create(mk_ctx* ctx, int rows, int cols, const int64_t* x2f
             MK_CUDA(cudaStreamSynchronize(s));
         }
         dev_setup = rows_sorted_strict(X, s);
+        if (!dev_setup && on_device) throw std::invalid_argument("mk_igm_create_dev: X2F rows must have strictly increasing columns");
         if (dev_setup) {
             tm.lap("upload X2F");
             DeviceCsr<double> Xt;
@@ -285,9 +315,12 @@ extern "C" int mk_igm_create(mk_ctx* ctx, int rows, int cols, const int64_t* x2f
             spgemm<double>(Xt, X, g->A0, s);
             k_scale_values<double><<<stream_grid(g->A0.nnz), kThreads, 0, s>>>(g->A0.nnz, g->A0.val.p, length * length);
             tm.lap("A0 = Xt X (device)");
-            DevBuf<double> f2((size_t)rows);
-            f2.upload(F2, (size_t)rows, s);
-            csr_matvec<double>(Xt, f2.p, g->rhs0.p, length, s);
+            DevBuf<double> f2;
+            if (!on_device) {
+                f2.alloc((size_t)rows);
+                f2.upload(F2, (size_t)rows, s);
+            }
+            csr_matvec<double>(Xt, on_device ? d_F2 : f2.p, g->rhs0.p, length, s);
             MK_CUDA(cudaStreamSynchronize(s));
             DeviceCsr<double> As;
             if (g->o.precond == 1) {
@@ -337,6 +370,18 @@ extern "C" int mk_igm_create(mk_ctx* ctx, int rows, int cols, const int64_t* x2f
     g->setup_ms = ms_since(t0);
     *out = g.release();
     MK_API_END(ctx)
+}
+
+extern "C" int mk_igm_create(mk_ctx* ctx, int rows, int cols, const int64_t* x2f_ptr, const int* x2f_col, const double* x2f_val,
+                             int ufull_rows, const int64_t* uf_ptr, const int* uf_col, const double* uf_val, const double* F2,
+                             double length, const mk_solve_opts* opts, mk_igm** out) {
+    return igm_create_impl(ctx, rows, cols, x2f_ptr, x2f_col, x2f_val, ufull_rows, uf_ptr, uf_col, uf_val, F2, length, opts, out, false);
+}
+
+extern "C" int mk_igm_create_dev(mk_ctx* ctx, int rows, int cols, const int64_t* x2f_ptr_dev, const int* x2f_col_dev, const double* x2f_val_dev,
+                                 int ufull_rows, const int64_t* uf_ptr, const int* uf_col, const double* uf_val, const double* F2_dev,
+                                 double length, const mk_solve_opts* opts, mk_igm** out) {
+    return igm_create_impl(ctx, rows, cols, x2f_ptr_dev, x2f_col_dev, x2f_val_dev, ufull_rows, uf_ptr, uf_col, uf_val, F2_dev, length, opts, out, true);
 }
 
 extern "C" int mk_igm_destroy(mk_igm* g) {

@@ -21,14 +21,17 @@ struct DeviceCsr {
     DevBuf<int> sl_ptr, sl_col;
     DevBuf<T> sl_val;
     double padding = 1.0;   // stored / true entries
-    // rows with more than kLongRow entries (dense dofs): empty in the SELL part, one CTA each, results parked in ylong[row]
+    // rows with more than kLongRow entries (dense dofs): empty in the SELL part, served by one extra CTA each in the same launch
     DevBuf<int> long_rows;
     DevBuf<unsigned int> long_bits;  // bit (row & 31) of word (row >> 5)
-    DevBuf<T> ylong;
     int n_long = 0;
+    // operators whose rows are long throughout (mean > kRowModeMean entries: the coarse IGM levels) skip the SELL copy and run the
+    // warp-per-row kernel on the CSR arrays
+    bool row_mode = false;
 };
 
 constexpr int kLongRow = 256;
+constexpr int kRowModeMean = 40;
 
 // ---- CSR -> SELL-32 conversion on the device (once per operator) ----
 // one warp per slice: width = longest non-long row, long rows flagged in a bit word and appended to the long-row list
@@ -102,6 +105,8 @@ static __global__ void k_sell_fill(int rows, int n_slices, const int* __restrict
 template <class T>
 inline void build_sell(DeviceCsr<T>& A, cudaStream_t s) {
     const int rows = A.rows;
+    A.row_mode = rows > 0 && A.nnz > (int64_t)kRowModeMean * rows;
+    if (A.row_mode) { A.n_slices = 0; A.n_long = 0; return; }
     const int ns = (rows + 31) / 32;
     A.n_slices = ns;
     DevBuf<int> width(std::max(ns, 1)), counter(1);
@@ -124,10 +129,6 @@ inline void build_sell(DeviceCsr<T>& A, cudaStream_t s) {
     k_sell_fill<T><<<wg, kThreads, 0, s>>>(rows, ns, A.ptr.p, A.col.p, A.val.p, A.sl_ptr.p, A.sl_col.p, A.sl_val.p);
     MK_CHECK_LAUNCH();
     A.padding = A.nnz ? (double)tot / (double)A.nnz : 1.0;
-    if (A.n_long) {
-        A.ylong.alloc(rows);
-        A.ylong.zero(s);
-    }
 }
 
 // plain CSR arrays only (operands of the device set-up algebra, devcsr.cuh)
@@ -151,28 +152,6 @@ inline void upload_csr(DeviceCsr<T>& A, int rows, int cols, const std::vector<in
     build_sell(A, s);  // synchronises the stream: the host vectors may die after return
 }
 
-// one CTA per long row: ylong[row] = sum_k val_k x[col_k]
-template <class T>
-__global__ void __launch_bounds__(kThreads) k_spmv_long(const int* __restrict__ rows, const int* __restrict__ ptr,
-                                                        const int* __restrict__ col, const T* __restrict__ val,
-                                                        const T* __restrict__ x, T* __restrict__ ylong, const PcgState* st) {
-    __shared__ double red[32];
-    if (st && st->done) return;
-    const int row = rows[blockIdx.x];
-    const int b = ptr[row], e = ptr[row + 1];
-    T acc = ST<T>::zero();
-    for (int k = b + threadIdx.x; k < e; k += blockDim.x) acc = ST<T>::fma_(ld_ro(val + k), ld_ro(x + col[k]), acc);
-    if constexpr (sizeof(T) == 16) {
-        const cdouble* a = reinterpret_cast<const cdouble*>(&acc);
-        double re = block_sum(a->x, red), im = block_sum(a->y, red);
-        if (threadIdx.x == 0) { cdouble o = make_c(re, im); st_rw(reinterpret_cast<cdouble*>(ylong) + row, o); }
-    } else {
-        const double* a = reinterpret_cast<const double*>(&acc);
-        double v = block_sum(*a, red);
-        if (threadIdx.x == 0) reinterpret_cast<double*>(ylong)[row] = v;
-    }
-}
-
 template <class T>
 __device__ __forceinline__ T group_sum(T v, int G);
 template <>
@@ -189,48 +168,66 @@ __device__ __forceinline__ cdouble group_sum<cdouble>(cdouble v, int G) {
     return v;
 }
 
-// y (+)= A x (+ shift x) on the SELL-32 layout, one thread per row, one warp per slice.
-// DOT: pq = <x, y>, alpha = rho / pq finished by the last CTA (the PCG step). ACC: y += (prolongation).
-template <class T, bool DOT, bool ACC>
-__global__ void __launch_bounds__(kThreads, 4) k_spmv_sell(int n, int n_slices, const int* __restrict__ sl_ptr, const int* __restrict__ sl_col,
-                                                        const T* __restrict__ sl_val, const unsigned int* __restrict__ long_bits,
-                                                        const T* __restrict__ ylong, const T* __restrict__ x, T* __restrict__ y, double shift,
-                                                        PcgState* st, ReduceWs ws) {
-    __shared__ double red[32];
-    if (st && st->done) return;
-    const int lane = threadIdx.x & 31;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+// sums a T over the CTA (result valid in thread 0)
+__device__ __forceinline__ double block_sum_t(double v, double* red) { return block_sum(v, red); }
+__device__ __forceinline__ cdouble block_sum_t(cdouble v, double* red) {
+    const double re = block_sum(v.x, red), im = block_sum(v.y, red);
+    return make_c(re, im);
+}
+
+// What happens to a finished row sum (A v)_row. One code path serves the three row shapes (SELL slice lane, long row, warp-per-row):
+//   kPlain : y = q                     kAcc  : y += q (prolongation)            kDot : y = q and <v, q> (the PCG step)
+//   kStep  : x (+)= v ; r -= q ; out = c1 v + c2 dinv .* r      (Chebyshev step fused into the SpMV; v = direction d, out = the next one)
+//   kResid : r = b - q ; out = c1 dinv .* r                     (residual + first direction; v = the iterate, c1 = 1 / theta)
+// `out` must not alias `v` (other rows still gather the old direction). Fusing the smoother saves a kernel and ~25% of the traffic per
+// smoothing step against SpMV + update.
+enum SpmvMode { kPlain = 0, kAcc = 1, kDot = 2, kStep = 3, kResid = 4 };
+
+template <class T>
+struct SpmvEpi {
+    const T* v;        // the vector A is applied to
+    double shift;      // (A + shift I)
+    T* y;              // kPlain / kAcc / kDot
+    const T* b;        // kResid
+    const T* dinv;     // kStep / kResid
+    T* r;              // kStep / kResid
+    T* x;              // kStep
+    T* out;            // kStep / kResid
+    double c1, c2;
+    int first;         // kStep: x = v instead of x += v
+};
+
+template <class T, int MODE>
+__device__ __forceinline__ double row_epilogue(const SpmvEpi<T>& e, int row, T acc) {
     double dot = 0.0;
-    for (int sl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; sl < n_slices; sl += nwarps) {
-        const int base = __ldg(sl_ptr + sl);
-        const int w = (__ldg(sl_ptr + sl + 1) - base) >> 5;
-        const int* cp = sl_col + base + lane;
-        const T* vp = sl_val + base + lane;
-        T acc = ST<T>::zero();
-        int k = 0;
-        for (; k + 4 <= w; k += 4) {
-            const int c0 = __ldg(cp + 32 * k), c1 = __ldg(cp + 32 * (k + 1)), c2 = __ldg(cp + 32 * (k + 2)), c3 = __ldg(cp + 32 * (k + 3));
-            const T v0 = ld_ro(vp + 32 * k), v1 = ld_ro(vp + 32 * (k + 1)), v2 = ld_ro(vp + 32 * (k + 2)), v3 = ld_ro(vp + 32 * (k + 3));
-            const T x0 = ld_ro(x + c0), x1 = ld_ro(x + c1), x2 = ld_ro(x + c2), x3 = ld_ro(x + c3);
-            acc = ST<T>::fma_(v0, x0, acc);
-            acc = ST<T>::fma_(v1, x1, acc);
-            acc = ST<T>::fma_(v2, x2, acc);
-            acc = ST<T>::fma_(v3, x3, acc);
+    if (MODE == kPlain || MODE == kAcc || MODE == kDot) {
+        if (MODE == kDot || e.shift != 0.0) {
+            const T vr = ld_ro(e.v + row);
+            if (e.shift != 0.0) acc = acc + ST<T>::scale(e.shift, vr);
+            if (MODE == kDot) dot = ST<T>::hdot(vr, acc);
         }
-        for (; k < w; k++) acc = ST<T>::fma_(ld_ro(vp + 32 * k), ld_ro(x + __ldg(cp + 32 * k)), acc);
-        const int row = sl * 32 + lane;
-        if (row < n) {
-            if (long_bits != nullptr && ((__ldg(long_bits + sl) >> lane) & 1u)) acc = acc + ld_rw(ylong + row);
-            if (DOT || shift != 0.0) {
-                const T xr = ld_ro(x + row);
-                if (shift != 0.0) acc = acc + ST<T>::scale(shift, xr);
-                if (DOT) dot += ST<T>::hdot(xr, acc);
-            }
-            if (ACC) acc = acc + ld_rw(y + row);
-            st_rw(y + row, acc);
-        }
+        if (MODE == kAcc) acc = acc + ld_rw(e.y + row);
+        st_rw(e.y + row, acc);
+    } else if (MODE == kStep) {
+        const T di = ld_ro(e.v + row);
+        if (e.shift != 0.0) acc = acc + ST<T>::scale(e.shift, di);
+        const T xi = e.first ? di : ld_rw(e.x + row) + di;
+        const T ri = ld_rw(e.r + row) - acc;
+        st_rw(e.x + row, xi);
+        st_rw(e.r + row, ri);
+        st_rw(e.out + row, ST<T>::scale(e.c1, di) + ST<T>::scale(e.c2, ld_ro(e.dinv + row) * ri));
+    } else {
+        if (e.shift != 0.0) acc = acc + ST<T>::scale(e.shift, ld_ro(e.v + row));
+        const T ri = ld_ro(e.b + row) - acc;
+        st_rw(e.r + row, ri);
+        st_rw(e.out + row, ST<T>::scale(e.c1, ld_ro(e.dinv + row) * ri));
     }
-    if (DOT) {
+    return dot;
+}
+
+template <int MODE>
+__device__ __forceinline__ void finish_dot(double dot, PcgState* st, ReduceWs ws, double* red) {
+    if (MODE == kDot) {
         double v[1] = {dot};
         grid_reduce<1>(v, ws.partials, ws.ticket, red, [&](const double* s) {
             st->pq = s[0];
@@ -240,19 +237,117 @@ __global__ void __launch_bounds__(kThreads, 4) k_spmv_sell(int n, int n_slices, 
     }
 }
 
+// SELL-32 SpMV, one thread per row, one warp per slice, in CTAs [0, sell_blocks); the long rows (dense dofs, empty in the SELL part) are
+// served by the CTAs [sell_blocks, sell_blocks + n_long) of the SAME launch, one CTA per row -- no second kernel, no dependency.
+template <class T, int MODE>
+__global__ void __launch_bounds__(kThreads, 6) k_spmv_sell(int n, int n_slices, const int* __restrict__ sl_ptr, const int* __restrict__ sl_col,
+                                                        const T* __restrict__ sl_val, const unsigned int* __restrict__ long_bits, int sell_blocks,
+                                                        const int* __restrict__ long_rows, const int* __restrict__ ptr, const int* __restrict__ col,
+                                                        const T* __restrict__ val, SpmvEpi<T> e, PcgState* st, ReduceWs ws) {
+    __shared__ double red[32];
+    if (st && st->done) return;
+    const T* __restrict__ x = e.v;
+    double dot = 0.0;
+    if ((int)blockIdx.x >= sell_blocks) {
+        const int row = long_rows[blockIdx.x - sell_blocks];
+        const int b = ptr[row], en = ptr[row + 1];
+        T acc = ST<T>::zero();
+        for (int k = b + threadIdx.x; k < en; k += blockDim.x) acc = ST<T>::fma_(ld_ro(val + k), ld_ro(x + __ldg(col + k)), acc);
+        acc = block_sum_t(acc, red);
+        if (threadIdx.x == 0) dot = row_epilogue<T, MODE>(e, row, acc);
+    } else {
+        const int lane = threadIdx.x & 31;
+        const int nwarps = (sell_blocks * blockDim.x) >> 5;
+        for (int sl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; sl < n_slices; sl += nwarps) {
+            const int base = __ldg(sl_ptr + sl);
+            const int w = (__ldg(sl_ptr + sl + 1) - base) >> 5;
+            const int* cp = sl_col + base + lane;
+            const T* vp = sl_val + base + lane;
+            T acc = ST<T>::zero();
+            int k = 0;
+            for (; k + 4 <= w; k += 4) {
+                const int c0 = __ldg(cp + 32 * k), c1 = __ldg(cp + 32 * (k + 1)), c2 = __ldg(cp + 32 * (k + 2)), c3 = __ldg(cp + 32 * (k + 3));
+                const T v0 = ld_ro(vp + 32 * k), v1 = ld_ro(vp + 32 * (k + 1)), v2 = ld_ro(vp + 32 * (k + 2)), v3 = ld_ro(vp + 32 * (k + 3));
+                const T x0 = ld_ro(x + c0), x1 = ld_ro(x + c1), x2 = ld_ro(x + c2), x3 = ld_ro(x + c3);
+                acc = ST<T>::fma_(v0, x0, acc);
+                acc = ST<T>::fma_(v1, x1, acc);
+                acc = ST<T>::fma_(v2, x2, acc);
+                acc = ST<T>::fma_(v3, x3, acc);
+            }
+            for (; k < w; k++) acc = ST<T>::fma_(ld_ro(vp + 32 * k), ld_ro(x + __ldg(cp + 32 * k)), acc);
+            const int row = sl * 32 + lane;
+            if (row < n && !(long_bits != nullptr && ((__ldg(long_bits + sl) >> lane) & 1u))) dot += row_epilogue<T, MODE>(e, row, acc);
+        }
+    }
+    finish_dot<MODE>(dot, st, ws, red);
+}
+
+// Warp-per-row SpMV on the plain CSR arrays for operators with long rows throughout (the coarse IGM levels reach > 100 entries per row):
+// lanes stride along the row (coalesced), no padding, any row length.
+template <class T, int MODE>
+__global__ void __launch_bounds__(kThreads) k_spmv_rows(int n, const int* __restrict__ ptr, const int* __restrict__ col, const T* __restrict__ val,
+                                                        SpmvEpi<T> e, PcgState* st, ReduceWs ws) {
+    __shared__ double red[32];
+    if (st && st->done) return;
+    const T* __restrict__ x = e.v;
+    const int lane = threadIdx.x & 31;
+    const int nw = (gridDim.x * blockDim.x) >> 5;
+    double dot = 0.0;
+    for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += nw) {
+        const int b = __ldg(ptr + row), en = __ldg(ptr + row + 1);
+        T acc = ST<T>::zero();
+        int k = b + lane;
+        for (; k + 32 < en; k += 64) {
+            const int c0 = __ldg(col + k), c1 = __ldg(col + k + 32);
+            const T v0 = ld_ro(val + k), v1 = ld_ro(val + k + 32);
+            acc = ST<T>::fma_(v0, ld_ro(x + c0), acc);
+            acc = ST<T>::fma_(v1, ld_ro(x + c1), acc);
+        }
+        if (k < en) acc = ST<T>::fma_(ld_ro(val + k), ld_ro(x + __ldg(col + k)), acc);
+        acc = group_sum<T>(acc, 32);
+        if (lane == 0) dot += row_epilogue<T, MODE>(e, row, acc);
+    }
+    finish_dot<MODE>(dot, st, ws, red);
+}
+
+template <class T, int MODE>
+inline void spmv_launch(const DeviceCsr<T>& A, const SpmvEpi<T>& e, PcgState* st, ReduceWs ws, cudaStream_t s) {
+    if (A.row_mode) {
+        k_spmv_rows<T, MODE><<<stream_grid((int64_t)A.rows * 32, kThreads, 16), kThreads, 0, s>>>(A.rows, A.ptr.p, A.col.p, A.val.p, e, st, ws);
+    } else {
+        int sell_blocks = stream_grid((int64_t)A.n_slices * 32, kThreads, 16);
+        if (sell_blocks + A.n_long > kMaxPartials) sell_blocks = std::max(1, kMaxPartials - A.n_long);
+        k_spmv_sell<T, MODE><<<sell_blocks + A.n_long, kThreads, 0, s>>>(A.rows, A.n_slices, A.sl_ptr.p, A.sl_col.p, A.sl_val.p,
+                                                                        A.n_long ? A.long_bits.p : nullptr, sell_blocks, A.long_rows.p, A.ptr.p,
+                                                                        A.col.p, A.val.p, e, st, ws);
+    }
+    MK_CHECK_LAUNCH();
+}
+
 // y (+)= A x (+ shift x); st != nullptr: skipped once st->done is set; dot: fused <x, y> reduction (needs st)
 template <class T>
 inline void spmv(const DeviceCsr<T>& A, const T* x, T* y, double shift, bool accumulate, bool dot, PcgState* st, ReduceWs ws, cudaStream_t s) {
-    if (A.n_long) k_spmv_long<T><<<A.n_long, kThreads, 0, s>>>(A.long_rows.p, A.ptr.p, A.col.p, A.val.p, x, A.ylong.p, st);
-    const int grid = stream_grid((int64_t)A.n_slices * 32, kThreads, 16);
-    const unsigned int* lb = A.n_long ? A.long_bits.p : nullptr;
-    if (dot && st)
-        k_spmv_sell<T, true, false><<<grid, kThreads, 0, s>>>(A.rows, A.n_slices, A.sl_ptr.p, A.sl_col.p, A.sl_val.p, lb, A.ylong.p, x, y, shift, st, ws);
-    else if (accumulate)
-        k_spmv_sell<T, false, true><<<grid, kThreads, 0, s>>>(A.rows, A.n_slices, A.sl_ptr.p, A.sl_col.p, A.sl_val.p, lb, A.ylong.p, x, y, shift, st, ws);
-    else
-        k_spmv_sell<T, false, false><<<grid, kThreads, 0, s>>>(A.rows, A.n_slices, A.sl_ptr.p, A.sl_col.p, A.sl_val.p, lb, A.ylong.p, x, y, shift, st, ws);
-    MK_CHECK_LAUNCH();
+    SpmvEpi<T> e{};
+    e.v = x; e.shift = shift; e.y = y;
+    if (dot && st) spmv_launch<T, kDot>(A, e, st, ws, s);
+    else if (accumulate) spmv_launch<T, kAcc>(A, e, st, ws, s);
+    else spmv_launch<T, kPlain>(A, e, st, ws, s);
+}
+
+template <class T>
+inline void spmv_cheb_step(const DeviceCsr<T>& A, double shift, const T* d_in, T* d_out, T* r, T* x, const T* dinv, double c1, double c2, int first,
+                           const PcgState* st, cudaStream_t s) {
+    SpmvEpi<T> e{};
+    e.v = d_in; e.shift = shift; e.dinv = dinv; e.r = r; e.x = x; e.out = d_out; e.c1 = c1; e.c2 = c2; e.first = first;
+    spmv_launch<T, kStep>(A, e, const_cast<PcgState*>(st), ReduceWs{nullptr, nullptr}, s);
+}
+
+template <class T>
+inline void spmv_cheb_resid(const DeviceCsr<T>& A, double shift, const T* x, const T* b, T* r, T* d_out, const T* dinv, double inv_theta,
+                            const PcgState* st, cudaStream_t s) {
+    SpmvEpi<T> e{};
+    e.v = x; e.shift = shift; e.b = b; e.dinv = dinv; e.r = r; e.out = d_out; e.c1 = inv_theta;
+    spmv_launch<T, kResid>(A, e, const_cast<PcgState*>(st), ReduceWs{nullptr, nullptr}, s);
 }
 
 template <class T>
@@ -260,9 +355,17 @@ struct CsrOp : LinOp<T> {
     const DeviceCsr<T>* A = nullptr;
     double shift = 0.0;
     explicit CsrOp(const DeviceCsr<T>* A_, double shift_ = 0.0) : A(A_), shift(shift_) { this->n = A_->rows; }
-    int launches_per_apply() const override { return A->n_long ? 2 : 1; }
+    int launches_per_apply() const override { return 1; }
     void apply(const T* x, T* y, PcgState* st, ReduceWs ws, cudaStream_t s, bool dot = true) override {
         spmv<T>(*A, x, y, shift, false, dot && st != nullptr, st, ws, s);
+    }
+    bool cheb_step(const T* d_in, T* d_out, T* r, T* x, const T* dinv, double c1, double c2, int first, const PcgState* st, cudaStream_t s) override {
+        spmv_cheb_step<T>(*A, shift, d_in, d_out, r, x, dinv, c1, c2, first, st, s);
+        return true;
+    }
+    bool cheb_resid(const T* x, const T* b, T* r, T* d_out, const T* dinv, double inv_theta, const PcgState* st, cudaStream_t s) override {
+        spmv_cheb_resid<T>(*A, shift, x, b, r, d_out, dinv, inv_theta, st, s);
+        return true;
     }
 };
 

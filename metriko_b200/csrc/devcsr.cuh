@@ -721,6 +721,43 @@ inline void copy_csr(const DeviceCsr<T>& A, DeviceCsr<T>& B, cudaStream_t s) {
     MK_CUDA(cudaMemcpyAsync(B.val.p, A.val.p, sizeof(T) * (size_t)A.nnz, cudaMemcpyDeviceToDevice, s));
 }
 
+// B = the listed rows of A, in list order (a rank's row block of a replicated operator, in the rank's local row order)
+static __global__ void k_gather_row_lengths(int m, const int* __restrict__ rows, const int* __restrict__ aptr, int* __restrict__ len) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) len[i] = aptr[rows[i] + 1] - aptr[rows[i]];
+}
+template <class T>
+static __global__ void k_gather_rows(int m, const int* __restrict__ rows, const int* __restrict__ aptr, const int* __restrict__ acol, const T* __restrict__ aval,
+                                     const int* __restrict__ bptr, int* __restrict__ bcol, T* __restrict__ bval) {
+    const int lane = threadIdx.x & 31;
+    const int nw = (gridDim.x * blockDim.x) >> 5;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < m; i += nw) {
+        const int a0 = aptr[rows[i]], len = aptr[rows[i] + 1] - a0, b0 = bptr[i];
+        for (int k = lane; k < len; k += 32) { bcol[b0 + k] = acol[a0 + k]; st_rw(bval + b0 + k, ld_ro(aval + a0 + k)); }
+    }
+}
+template <class T>
+inline void csr_gather_rows(const DeviceCsr<T>& A, const int* rows_dev, int m, DeviceCsr<T>& B, cudaStream_t s) {
+    DevBuf<int> len((size_t)m + 1);
+    len.zero(s);
+    k_gather_row_lengths<<<(m + 255) / 256, 256, 0, s>>>(m, rows_dev, A.ptr.p, len.p);
+    B.rows = m;
+    B.cols = A.cols;
+    B.ptr.alloc((size_t)m + 1);
+    dev_exclusive_scan(len.p, B.ptr.p, m, s);
+    B.nnz = dev_read_int(B.ptr.p + m, s);
+    B.col.alloc((size_t)std::max<int64_t>(B.nnz, 1));
+    B.val.alloc((size_t)std::max<int64_t>(B.nnz, 1));
+    k_gather_rows<T><<<stream_grid((int64_t)m * 32), kThreads, 0, s>>>(m, rows_dev, A.ptr.p, A.col.p, A.val.p, B.ptr.p, B.col.p, B.val.p);
+    MK_CHECK_LAUNCH();
+    MK_CUDA(cudaStreamSynchronize(s));
+}
+template <class T>
+static __global__ void k_gather_values(int m, const int* __restrict__ idx, const T* __restrict__ in, T* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) st_rw(out + i, ld_ro(in + idx[i]));
+}
+
 // device CSR -> host CSR (tests, coarsest-level inverse)
 template <class T, class S>
 inline HostCsr<S> download_csr(const DeviceCsr<T>& A, cudaStream_t s) {

@@ -11,7 +11,7 @@
 #include <memory>
 #include <vector>
 
-#include "amg.cuh"
+#include "amg_dev.cuh"
 #include "field.cuh"
 
 namespace mk {
@@ -243,7 +243,70 @@ struct DistFaceOp {
     int launches_per_apply() const { return 3; }
 };
 
-// Distributed PCG: A = DistFaceOp, M = local multigrid V-cycle on the diagonal block (block-Jacobi over ranks) or identity.
+// Multigrid preconditioner of the partitioned operator with the GLOBAL hierarchy (the same one the single-GPU path builds, so the
+// iteration counts are those of one GPU, not of block-Jacobi):
+//   level 0   : distributed -- Chebyshev smoothing with the partitioned operator (halo exchange per SpMV); this rank holds its rows
+//               of P_0 and their conjugate transpose;
+//   restrict  : every rank forms its partial sum R_0[:, mine] r_mine, one NCCL all-reduce of the level-1 vector adds them up;
+//   levels>=1 : replicated -- every rank runs the same coarse V-cycle on the full level-1 vector (bit-identical results, no traffic);
+//   prolong   : local, x_mine += P_0[mine, :] x_1.
+// The hierarchy is built redundantly on every rank from the global stencil by the deterministic device set-up. The replicated part is
+// ~20% of a V-cycle's work, which bounds the speed-up (Amdahl) -- distributing level 1 as well is the next step.
+struct NullOp : LinOp<cdouble> {
+    void apply(const cdouble*, cdouble*, PcgState*, ReduceWs, cudaStream_t, bool) override { throw std::logic_error("NullOp applied"); }
+};
+
+struct DistAmgPrecond : Precond<cdouble> {
+    DistFaceOp* A = nullptr;
+    DistComm* dc = nullptr;
+    NullOp null_op;
+    std::unique_ptr<AmgPrecond<cdouble>> G;  // global hierarchy; level 0 only contributes lmax / dinv / P_0
+    DeviceCsr<cdouble> P0, R0;               // this rank's rows of P_0 (local row order) and their conjugate transpose (n1 x n_local)
+    DevBuf<cdouble> dinv, r, d_ext, q;
+    double lmax = 2.0;
+    int nloc = 0, next = 0, n1 = 0;
+    AmgParams prm;
+
+    bool ready() const { return G && G->lv.size() >= 2; }
+
+    void smooth(const cdouble* b, cdouble* x_ext, bool zero_guess, const PcgState* st, cudaStream_t s) {
+        const int grid = stream_grid(nloc);
+        const double lmin = lmax / prm.cheb_ratio;
+        const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
+        double rho = 1.0 / sigma;
+        if (zero_guess) {
+            k_cheb_init<cdouble><<<grid, kThreads, 0, s>>>(nloc, b, (const cdouble*)nullptr, dinv.p, r.p, d_ext.p, 1.0 / theta, st);
+        } else {
+            A->apply(x_ext, q.p, st, s);
+            k_cheb_init<cdouble><<<grid, kThreads, 0, s>>>(nloc, b, q.p, dinv.p, r.p, d_ext.p, 1.0 / theta, st);
+        }
+        for (int k = 0; k < prm.cheb_degree; k++) {
+            A->apply(d_ext.p, q.p, st, s);
+            const double rho1 = 1.0 / (2.0 * sigma - rho);
+            k_cheb_step<cdouble><<<grid, kThreads, 0, s>>>(nloc, q.p, dinv.p, r.p, x_ext, d_ext.p, rho1 * rho, 2.0 * rho1 / delta,
+                                                          (zero_guess && k == 0) ? 1 : 0, st);
+            rho = rho1;
+        }
+        MK_CHECK_LAUNCH();
+    }
+
+    // z must have room for the halo slots ([owned | halo] layout): it is the level-0 iterate the partitioned operator is applied to
+    void apply(const cdouble* rin, cdouble* z, const PcgState* st, cudaStream_t s) override {
+        smooth(rin, z, true, st, s);
+        AmgLevelDev<cdouble>& C = G->lv[1];
+        spmv_plain(R0, r.p, C.b.p, false, st, s);
+        dc->allreduce_sum(reinterpret_cast<double*>(C.b.p), 2 * n1, s);
+        G->vcycle(1, C.b.p, C.x.p, st, s);
+        spmv_plain(P0, C.x.p, z, true, st, s);
+        smooth(rin, z, false, st, s);
+    }
+    int launches_per_apply() const override {
+        const int per_spmv = A->launches_per_apply();
+        return (2 * prm.cheb_degree + 1) * (per_spmv + 1) + 1 + 2 + (G ? G->launches_per_apply() - (4 + 2 * prm.cheb_degree) : 0);
+    }
+};
+
+// Distributed PCG: A = DistFaceOp, M = the global-hierarchy multigrid above (or the local V-cycle on the diagonal block, or identity).
 // Two all-reduces per iteration (<p,Ap>; {<r,r>, <r,z>}); the host looks at the state every `chunk` iterations.
 struct DistPcg {
     int n = 0, next = 0;
@@ -256,7 +319,7 @@ struct DistPcg {
     PcgState* h_st = nullptr;
     int grid = 1;
 
-    DistPcg(int n_, int next_, DistComm* dc_, cudaStream_t s_) : n(n_), next(next_), s(s_), dc(dc_), r(n_), z(n_), p_ext(next_), q(n_), st(1), part(8),
+    DistPcg(int n_, int next_, DistComm* dc_, cudaStream_t s_) : n(n_), next(next_), s(s_), dc(dc_), r(n_), z(next_), p_ext(next_), q(n_), st(1), part(8),
                                                                   partials(kMaxPartials * 4), ticket(1) {
         ticket.zero(s);
         st.zero(s);

@@ -51,6 +51,32 @@ static __global__ void __launch_bounds__(kThreads) k_field_assemble(int nF, int 
     }
 }
 
+// CSR copy of the face stencil for the set-up algebra: row f = {diagonal, three neighbours} with sorted columns, one thread
+// per face. Two faces sharing two edges would give a repeated column; that is flagged (degenerate input) rather than merged.
+static __global__ void __launch_bounds__(kThreads) k_face_to_csr(int nF, double diag, const int* __restrict__ nbr, const cdouble* __restrict__ val,
+                                                                 int* __restrict__ ptr, int* __restrict__ col, cdouble* __restrict__ cval, int* __restrict__ dup) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f > nF) return;
+    ptr[f] = 4 * f;
+    if (f == nF) return;
+    int c[4] = {f, nbr[f], nbr[(size_t)nF + f], nbr[2 * (size_t)nF + f]};
+    cdouble v[4] = {make_c(diag, 0.0), ldc_nc(val + f), ldc_nc(val + (size_t)nF + f), ldc_nc(val + 2 * (size_t)nF + f)};
+#pragma unroll
+    for (int a = 1; a < 4; a++)  // insertion sort of 4 entries
+#pragma unroll
+        for (int b = a; b > 0; b--)
+            if (c[b] < c[b - 1]) {
+                const int tc = c[b]; c[b] = c[b - 1]; c[b - 1] = tc;
+                const cdouble tv = v[b]; v[b] = v[b - 1]; v[b - 1] = tv;
+            }
+    if (c[0] == c[1] || c[1] == c[2] || c[2] == c[3]) *dup = 1;
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        col[(size_t)4 * f + a] = c[a];
+        stc(cval + (size_t)4 * f + a, v[a]);
+    }
+}
+
 // y = L x for the face stencil; DOT: pq = <x, y>, alpha = rho / pq.
 template <bool DOT>
 static __global__ void __launch_bounds__(kThreads) k_spmv_face(int nF, double diag, const int* __restrict__ nbr, const cdouble* __restrict__ val,
@@ -80,6 +106,36 @@ static __global__ void __launch_bounds__(kThreads) k_spmv_face(int nF, double di
     }
 }
 
+// Chebyshev smoothing step / residual fused into the face-stencil SpMV (see k_spmv_sell_cheb, csr.cuh, for the two modes)
+template <int MODE>
+static __global__ void __launch_bounds__(kThreads) k_spmv_face_cheb(int nF, double diag, const int* __restrict__ nbr, const cdouble* __restrict__ val,
+                                                             const cdouble* __restrict__ v, const cdouble* __restrict__ b, const cdouble* __restrict__ dinv,
+                                                             cdouble* __restrict__ r, cdouble* __restrict__ x, cdouble* __restrict__ out, double c1,
+                                                             double c2, int first, const PcgState* st) {
+    if (st && st->done) return;
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nF; f += gridDim.x * blockDim.x) {
+        const int n0 = __ldg(nbr + f), n1 = __ldg(nbr + (size_t)nF + f), n2 = __ldg(nbr + 2 * (size_t)nF + f);
+        const cdouble v0 = ldc_nc(val + f), v1 = ldc_nc(val + (size_t)nF + f), v2 = ldc_nc(val + 2 * (size_t)nF + f);
+        const cdouble vf = ldc_nc(v + f);
+        const cdouble x0 = ldc_nc(v + n0), x1 = ldc_nc(v + n1), x2 = ldc_nc(v + n2);
+        cdouble acc = make_c(diag * vf.x, diag * vf.y);
+        acc = ST<cdouble>::fma_(v0, x0, acc);
+        acc = ST<cdouble>::fma_(v1, x1, acc);
+        acc = ST<cdouble>::fma_(v2, x2, acc);
+        if (MODE == 1) {
+            const cdouble xi = first ? vf : ldc(x + f) + vf;
+            const cdouble ri = ldc(r + f) - acc;
+            stc(x + f, xi);
+            stc(r + f, ri);
+            stc(out + f, ST<cdouble>::scale(c1, vf) + ST<cdouble>::scale(c2, ldc_nc(dinv + f) * ri));
+        } else {
+            const cdouble ri = ldc_nc(b + f) - acc;
+            stc(r + f, ri);
+            stc(out + f, ST<cdouble>::scale(c1, ldc_nc(dinv + f) * ri));
+        }
+    }
+}
+
 struct FaceOp : LinOp<cdouble> {
     const FaceStencil* S;
     explicit FaceOp(const FaceStencil* S_) : S(S_) { n = S_->nF; }
@@ -88,6 +144,20 @@ struct FaceOp : LinOp<cdouble> {
         if (st && dot) k_spmv_face<true><<<grid, kThreads, 0, s>>>(S->nF, S->diag, S->nbr.p, S->val.p, x, y, st, ws);
         else k_spmv_face<false><<<grid, kThreads, 0, s>>>(S->nF, S->diag, S->nbr.p, S->val.p, x, y, st, ws);
         MK_CHECK_LAUNCH();
+    }
+    bool cheb_step(const cdouble* d_in, cdouble* d_out, cdouble* r, cdouble* x, const cdouble* dinv, double c1, double c2, int first,
+                   const PcgState* st, cudaStream_t s) override {
+        k_spmv_face_cheb<1><<<stream_grid(S->nF, kThreads, 8), kThreads, 0, s>>>(S->nF, S->diag, S->nbr.p, S->val.p, d_in, nullptr, dinv, r, x, d_out, c1, c2,
+                                                                                 first, st);
+        MK_CHECK_LAUNCH();
+        return true;
+    }
+    bool cheb_resid(const cdouble* x, const cdouble* b, cdouble* r, cdouble* d_out, const cdouble* dinv, double inv_theta, const PcgState* st,
+                    cudaStream_t s) override {
+        k_spmv_face_cheb<2><<<stream_grid(S->nF, kThreads, 8), kThreads, 0, s>>>(S->nF, S->diag, S->nbr.p, S->val.p, x, b, dinv, r, nullptr, d_out, inv_theta,
+                                                                                 0.0, 0, st);
+        MK_CHECK_LAUNCH();
+        return true;
     }
 };
 

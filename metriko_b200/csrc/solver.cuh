@@ -60,6 +60,21 @@ struct PcgState {
     int pad;
 };
 
+struct PcgState;
+// Pinned host copies of the solver state: cudaMallocHost / cudaFreeHost cost 3-5 ms each on this platform and a step creates several
+// solver objects, so the slots are recycled (per host thread; never returned to the driver).
+struct PinnedStatePool {
+    std::vector<void*> free_list;
+    void* get(size_t bytes) {
+        if (!free_list.empty()) { void* p = free_list.back(); free_list.pop_back(); return p; }
+        void* p = nullptr;
+        MK_CUDA(cudaMallocHost(&p, bytes < 256 ? 256 : bytes));
+        return p;
+    }
+    void put(void* p) { if (p) free_list.push_back(p); }
+    static PinnedStatePool& instance() { static thread_local PinnedStatePool pool; return pool; }
+};
+
 struct ReduceWs {
     double* partials;      // kMaxPartials * 4 doubles
     unsigned int* ticket;  // zero-initialised, reset by the last CTA
@@ -179,6 +194,11 @@ struct LinOp {
     // kernel finishes the fused reduction pq = <x, y>, alpha = rho / pq (the PCG step).
     virtual void apply(const T* x, T* y, PcgState* st, ReduceWs ws, cudaStream_t s, bool dot = true) = 0;
     virtual int launches_per_apply() const { return 1; }
+    // Chebyshev smoothing fused into the operator kernel (the multigrid V-cycle, amg.cuh). Return false when unsupported.
+    //   cheb_step : q = A d_in ; x (+)= d_in ; r -= q ; d_out = c1 d_in + c2 dinv .* r      (x = d_in when `first`)
+    //   cheb_resid: r = b - A x ; d_out = inv_theta dinv .* r
+    virtual bool cheb_step(const T*, T*, T*, T*, const T*, double, double, int, const PcgState*, cudaStream_t) { return false; }
+    virtual bool cheb_resid(const T*, const T*, T*, T*, const T*, double, const PcgState*, cudaStream_t) { return false; }
 };
 
 template <class T>
@@ -209,12 +229,12 @@ public:
     Pcg(int n, cudaStream_t stream) : n_(n), stream_(stream), r_(n), z_(n), p_(n), q_(n), st_(1), partials_(kMaxPartials * 4), ticket_(1) {
         ticket_.zero(stream_);
         st_.zero(stream_);
-        MK_CUDA(cudaMallocHost((void**)&h_st_, sizeof(PcgState)));
+        h_st_ = (PcgState*)PinnedStatePool::instance().get(sizeof(PcgState));
         grid_ = stream_grid(n);
     }
     ~Pcg() {
         if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
-        if (h_st_) cudaFreeHost(h_st_);
+        PinnedStatePool::instance().put(h_st_);
     }
     PcgState* state() { return st_.p; }
     ReduceWs ws() { return ReduceWs{partials_.p, ticket_.p}; }

@@ -73,8 +73,17 @@ class DistFaceField:
         ctx.check(ctx.L.mk_dfield_create(dctx.h, plan.n_local, plan.n_interior, plan.n_halo, *[ptr(v) for v in a], C.byref(self.h)))
         self.stats = None
 
+    def set_global(self, nbr_global, val_global):
+        """Hands every rank the global stencil (nbr / val [3, nF]) so that the solves use the GLOBAL multigrid hierarchy (level 0
+        distributed, restricted residual all-reduced, coarse levels replicated) instead of block-Jacobi. Collective."""
+        nbr, val = as_i32(nbr_global), as_c128(val_global)
+        assert nbr.shape == val.shape and nbr.shape[0] == 3
+        l2g = as_i32(self.plan.owned_global())
+        self.ctx.check(self.ctx.L.mk_dfield_set_global(self.h, nbr.shape[1], ptr(nbr), ptr(val), ptr(l2g)))
+
     @classmethod
-    def from_mesh(cls, dctx: DistContext, face2half, next_, twin, face, heArgOnFace, faceArea, N: int = 4, ranges=None):
+    def from_mesh(cls, dctx: DistContext, face2half, next_, twin, face, heArgOnFace, faceArea, N: int = 4, ranges=None,
+                  global_hierarchy: bool = True):
         """Partition + local assembly. The neighbour pattern is index bookkeeping on the host; the values
         -transport^N = -(-1)^N e^{iN(farg(h) - farg(twin h))} (frf.h:52-71) of the owned rows are evaluated with numpy here
         (set-up, O(rows/world)); the single-GPU path assembles them on the device (k_field_assemble)."""
@@ -83,13 +92,18 @@ class DistFaceField:
         rows = plan.owned_global()
         farg = np.asarray(heArgOnFace, np.float64)
         tw, nxt = np.asarray(twin), np.asarray(next_)
-        h = np.asarray(face2half, np.int64)[rows]
-        val = np.empty((3, plan.n_local), np.complex128)
+        h = np.asarray(face2half, np.int64)
+        if not global_hierarchy:
+            h = h[rows]
+        val = np.empty((3, len(h)), np.complex128)
         sign = -1.0 if (N & 1) else 1.0
         for j in range(3):
             val[j] = -sign * np.exp(1j * N * (farg[h] - farg[tw[h]]))
             h = nxt[h]
-        return cls(dctx, plan, val, np.asarray(faceArea, np.float64)[rows])
+        self = cls(dctx, plan, val[:, rows] if global_hierarchy else val, np.asarray(faceArea, np.float64)[rows])
+        if global_hierarchy:
+            self.set_global(nbr, val)
+        return self
 
     def spmv(self, x_local):
         x = as_c128(x_local)

@@ -46,14 +46,14 @@ def run(path, what):
     ctx = capi.Context(0)
     if "field" in what:
         F = api.FaceRosyField(ctx, *[d[k] for k in FIELD_KEYS], 4)
-        print("field spmv us", F.spmv_bench(5, False) * 1e3, F.spmv_bench(5, True) * 1e3)
+        print("field spmv us", F.spmv_bench(1, False) * 1e3, F.spmv_bench(1, True) * 1e3)
         F.solveSmallestEig(d["u0"], 3)
         print("field 3 outer:", F.stats)
     if "igm" in what:
         X = sp.csr_matrix((d["Xv"], d["Xc"], d["Xp"]), shape=tuple(d["Xs"]))
         U = sp.csr_matrix((d["Uv"], d["Uc"], d["Up"]), shape=tuple(d["Us"]))
         prob = api.IgmProblem(ctx, X, U, d["F2"], float(d["length"]))
-        print("igm spmv us", prob.spmv_bench(5, False) * 1e3)
+        print("igm spmv us", prob.spmv_bench(1, False) * 1e3)
         t = time.time()
         if "round" in what:
             out = prob.round(d["fixedIdcs"], d["fixedVals"], d["singularIdcs"], d["integerIdcs"], True, False)

@@ -179,3 +179,115 @@ def test_halo_plan_single_rank_and_morton():
     d_sorted = np.linalg.norm(np.diff(pts[order], axis=0), axis=1).mean()
     d_rand = np.linalg.norm(np.diff(pts, axis=0), axis=1).mean()
     assert d_sorted < 0.6 * d_rand
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The global-hierarchy preconditioner of the partitioned solves (csrc/dist.cuh DistAmgPrecond): level 0 distributed, restricted
+# residual all-reduced, coarse levels replicated. Emulated here with numpy + gloo on the hierarchy of the host mirror; it must
+# reproduce the single-process V-cycle exactly (same PCG iteration count), which is what makes the multi-GPU iteration counts
+# those of one GPU rather than of block-Jacobi.
+# ---------------------------------------------------------------------------------------------------------------------
+def _cheb(apply_A, dinv, lmax, b, x, zero, deg=2, ratio=8.0):
+    lmin = lmax / ratio
+    theta, delta = 0.5 * (lmax + lmin), 0.5 * (lmax - lmin)
+    sigma = theta / delta
+    rho = 1.0 / sigma
+    r = b.copy() if zero else b - apply_A(x)
+    d = dinv * r / theta
+    if zero:
+        x = np.zeros_like(b)
+    for _ in range(deg):
+        x = x + d
+        r = r - apply_A(d)
+        rho1 = 1.0 / (2 * sigma - rho)
+        d = rho1 * rho * d + 2 * rho1 / delta * dinv * r
+        rho = rho1
+    return x, r
+
+
+def _worker_global_amg(rank, world, port, name, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import scipy.sparse as sp
+        from amg_mirror import VCycle, pcg
+        from metriko_b200 import capi
+        g = load_golden(name)
+        nbr, val = ell3(g)
+        nF = nbr.shape[1]
+        plan = make_halo_plan(nbr, rank, world)
+        rows = plan.owned_global()
+        val_loc = val[:, rows]
+        nFr = np.arange(nF)
+        L = sp.csr_matrix((np.concatenate([np.full(nF, 3.0 + 1e-9, np.complex128), val.ravel()]),
+                           (np.concatenate([nFr, nFr, nFr, nFr]), np.concatenate([nFr, nbr.ravel()]))), shape=(nF, nF))
+        H = capi.amg_host_hierarchy(L)                 # every rank builds the same (deterministic) global hierarchy
+        assert len(H) >= 2
+        P0 = H[0][1].tocsr()[rows]                     # my rows of P_0, local order
+        R0 = P0.conj().T.tocsr()
+        dinv0, lmax0 = H[0][3][rows], H[0][2]
+        coarse = VCycle(H[1:])                         # replicated levels >= 1
+
+        def apply_A(v_loc):
+            x_ext = np.zeros(plan.n_local + plan.n_halo, np.complex128)
+            x_ext[:plan.n_local] = v_loc
+            return dist_spmv(plan, val_loc, x_ext)
+
+        def precond(r_loc):
+            x, r = _cheb(apply_A, dinv0, lmax0, r_loc, None, True)
+            part = R0 @ r                              # partial restriction over my fine rows
+            t = torch.from_numpy(np.ascontiguousarray(part).view(np.float64).copy())
+            dist.all_reduce(t)                         # the one data all-reduce of the V-cycle
+            x = x + P0 @ coarse(t.numpy().view(np.complex128))
+            x, _ = _cheb(apply_A, dinv0, lmax0, r_loc, x, False)
+            return x
+
+        b = (g["faceArea"] * g["u0"])[rows]
+        x = np.zeros(plan.n_local, np.complex128)
+        r = b.copy()
+        z = precond(r)
+        p = z.copy()
+        (rho, bb) = allreduce(np.vdot(r, z).real, np.vdot(b, b).real)
+        it = 0
+        while it < 200:
+            (rr,) = allreduce(np.vdot(r, r).real)
+            if rr <= 1e-20 * bb:
+                break
+            qv = apply_A(p)
+            (pq,) = allreduce(np.vdot(p, qv).real)
+            a = rho / pq
+            x += a * p
+            r -= a * qv
+            z = precond(r)
+            (rho1,) = allreduce(np.vdot(r, z).real)
+            p = z + (rho1 / rho) * p
+            rho = rho1
+            it += 1
+        # single-process reference with the same hierarchy
+        bg = g["faceArea"] * g["u0"]
+        x_ref, it_ref = pcg(L, bg, np.zeros_like(bg), VCycle(H))
+        assert abs(it - it_ref) <= 1, (it, it_ref)
+        assert np.abs(x - x_ref[rows]).max() < 1e-8 * np.abs(x_ref).max()
+        q.put((rank, "ok", it))
+    except Exception:  # noqa: BLE001
+        import traceback
+        q.put((rank, "fail", traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_global_hierarchy_preconditioner_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    world = 2
+    procs = [ctx.Process(target=_worker_global_amg, args=(r, world, port, "sphere_ico3", q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, status, info in res:
+        assert status == "ok", f"rank {rank}: {info}"
+    assert res[0][2] == res[1][2] and res[0][2] < 40
