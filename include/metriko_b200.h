@@ -81,6 +81,14 @@ int mk_field_get_operator(mk_field* f, int* rowptr, int* col, double* val, doubl
 int mk_field_solve(mk_field* f, const double* u0, int n_iter, const mk_solve_opts* opts, double* x, mk_stats* stats);
 /* Same, with u0 / x already resident on the device (HBM-resident timing path; pointers are device pointers). */
 int mk_field_solve_dev(mk_field* f, const double* u0_dev, int n_iter, const mk_solve_opts* opts, double* x_dev, mk_stats* stats);
+/* FieldType::CurvatureAligned (frf.h:25-33): rhs = M D / sqrt|D^H M D| with D = principalCurvatureDir() (frf.h:86-98, squared for
+ * N = 4) from the per-half lengths and dihedral angles (hmesh/hmesh.h:215, 508-519), then solveSquare(L - lambda M, rhs) with the
+ * reference's lambda = 0 (sls.h:16-27) as one multigrid-preconditioned CG solve. heLen, dihedralArg: host, nH; x (and rhs_out, may be
+ * NULL): host, complex interleaved, nF. The solution stays on the device for mk_field_decode. */
+int mk_field_solve_curvature_aligned(mk_field* f, const double* heLen, const double* dihedralArg, const mk_solve_opts* opts, double* rhs_out, double* x,
+                                     mk_stats* stats);
+/* solveSquare(lhs, rhs) (sls.h:16-27) for lhs = the assembled L (lambda = 0, frf.h:27): one Hermitian solve, host vectors. */
+int mk_field_solve_square(mk_field* f, const double* rhs, const mk_solve_opts* opts, double* x, mk_stats* stats);
 /* Field decode (frf.h:37-43): field[nF x N] complex interleaved from the last solution. Host output. */
 int mk_field_decode(mk_field* f, double* field);
 /* y = L x on host vectors (tests) and a timed device loop for the roofline (reps launches, returns ms per launch). */

@@ -56,6 +56,30 @@ class FaceRosyField:
         self.ctx.check(rc)
         return x
 
+    def solveCurvatureAligned(self, heLen, dihedralArg, return_rhs: bool = False, **opts):
+        """FieldType::CurvatureAligned (frf.h:25-33): principalCurvatureDir -> rhs -> solveSquare(L, rhs), all on the device."""
+        ln, da = as_f64(heLen), as_f64(dihedralArg)
+        assert len(ln) == self.nH and len(da) == self.nH
+        x = np.empty(self.nF, np.complex128)
+        rhs = np.empty(self.nF, np.complex128) if return_rhs else None
+        st = Stats()
+        o = default_opts(**opts)
+        rc = self.ctx.L.mk_field_solve_curvature_aligned(self.h, ptr(ln), ptr(da), C.byref(o), ptr(rhs), ptr(x), C.byref(st))
+        self.stats = st.as_dict()
+        self.ctx.check(rc)
+        return (x, rhs) if return_rhs else x
+
+    def solveSquare(self, rhs, **opts):
+        """solveSquare(L, rhs) (sls.h:16-27) on the assembled operator."""
+        b = as_c128(rhs)
+        x = np.empty(self.nF, np.complex128)
+        st = Stats()
+        o = default_opts(**opts)
+        rc = self.ctx.L.mk_field_solve_square(self.h, ptr(b), C.byref(o), ptr(x), C.byref(st))
+        self.stats = st.as_dict()
+        self.ctx.check(rc)
+        return x
+
     def solve_dev(self, u0_dev_ptr: int, nIter: int = 50, x_dev_ptr: int | None = None, **opts):
         st = Stats()
         o = default_opts(**opts)

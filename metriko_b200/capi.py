@@ -72,6 +72,8 @@ def lib() -> C.CDLL:
         L.mk_field_solve.argtypes = [vp, vp, C.c_int, C.POINTER(SolveOpts), vp, C.POINTER(Stats)]
         L.mk_field_solve_dev.argtypes = [vp, vp, C.c_int, C.POINTER(SolveOpts), vp, C.POINTER(Stats)]
         L.mk_field_decode.argtypes = [vp, vp]
+        L.mk_field_solve_curvature_aligned.argtypes = [vp, vp, vp, C.POINTER(SolveOpts), vp, vp, C.POINTER(Stats)]
+        L.mk_field_solve_square.argtypes = [vp, vp, C.POINTER(SolveOpts), vp, C.POINTER(Stats)]
         L.mk_field_spmv.argtypes = [vp, vp, vp]
         L.mk_field_spmv_bench.argtypes = [vp, C.c_int, C.c_int, dp]
         L.mk_solve_smallest_eig_csc.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.POINTER(SolveOpts), vp, C.POINTER(Stats)]

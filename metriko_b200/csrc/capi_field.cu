@@ -267,6 +267,73 @@ int mk_field_solve(mk_field* f, const double* u0, int n_iter, const mk_solve_opt
     MK_API_END_RC(f->ctx, rc)
 }
 
+// One Hermitian solve L x = b on the device operator (b in f->b, result in f->x): what solveSquare(L - 0 M, rhs) does (sls.h:16-27)
+static int field_square_impl(mk_field* f, const mk_solve_opts* opts, mk_stats* stats) {
+    mk_solve_opts o;
+    if (opts) o = *opts; else mk_default_opts(&o);
+    auto t0 = std::chrono::steady_clock::now();
+    field_setup_solver(f, o);
+    cudaStream_t s = f->ctx->c.stream;
+    MK_CUDA(cudaStreamSynchronize(s));
+    auto t1 = std::chrono::steady_clock::now();
+    f->x.zero(s);
+    f->pcg->bind(f->op.get(), o.precond == 1 ? f->amg.get() : nullptr, nullptr);
+    SolveStats ss = f->pcg->solve(f->b.p, f->x.p, o.tol, o.max_iter, false, 16, o.use_graph != 0);
+    MK_CUDA(cudaStreamSynchronize(s));
+    auto t2 = std::chrono::steady_clock::now();
+    f->has_solution = true;
+    const int rc = ss.status == 0 ? MK_OK : (ss.status == 2 ? MK_ERR_NOT_SPD : MK_ERR_NOT_CONVERGED);
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        stats->outer_iterations = 1;
+        stats->inner_iterations = ss.iterations;
+        stats->inner_max = ss.iterations;
+        stats->relres_max = ss.relres;
+        stats->kernel_launches = ss.launches;
+        stats->setup_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+        stats->solve_ms = std::chrono::duration<double, std::milli>(t2 - t1).count();
+        stats->status = rc;
+    }
+    return rc;
+}
+
+int mk_field_solve_square(mk_field* f, const double* rhs, const mk_solve_opts* opts, double* x, mk_stats* stats) {
+    if (!f || !f->assembled || !rhs || !x) return MK_ERR_ARG;
+    int rc = MK_OK;
+    MK_API_BEGIN(f->ctx)
+    MK_CUDA(cudaSetDevice(f->ctx->c.device));
+    cudaStream_t s = f->ctx->c.stream;
+    f->b.upload((const cdouble*)rhs, f->nF, s);
+    rc = field_square_impl(f, opts, stats);
+    f->x.download((cdouble*)x, f->nF, s);
+    MK_CUDA(cudaStreamSynchronize(s));
+    MK_API_END_RC(f->ctx, rc)
+}
+
+int mk_field_solve_curvature_aligned(mk_field* f, const double* heLen, const double* dihedralArg, const mk_solve_opts* opts, double* rhs_out, double* x,
+                                     mk_stats* stats) {
+    if (!f || !f->assembled || !heLen || !dihedralArg || !x || (f->N != 2 && f->N != 4)) return MK_ERR_ARG;  // assert(rosyN == 2 || rosyN == 4), frf.h:26
+    int rc = MK_OK;
+    MK_API_BEGIN(f->ctx)
+    MK_CUDA(cudaSetDevice(f->ctx->c.device));
+    cudaStream_t s = f->ctx->c.stream;
+    if (!f->pcg) f->pcg = std::make_unique<Pcg<cdouble>>(f->nF, s);
+    DevBuf<double> len(f->nH), darg(f->nH);
+    len.upload(heLen, f->nH, s);
+    darg.upload(dihedralArg, f->nH, s);
+    const int grid = stream_grid(f->nF);
+    k_curvature_rhs<<<grid, kThreads, 0, s>>>(f->nF, f->N, f->face2half.p, f->next.p, f->farg.p, len.p, darg.p, f->S.mass.p, f->b.p, f->pcg->state(),
+                                              f->pcg->ws());
+    k_scale_by_aux0<<<grid, kThreads, 0, s>>>(f->nF, f->b.p, f->pcg->state());
+    MK_CHECK_LAUNCH();
+    if (rhs_out) f->b.download((cdouble*)rhs_out, f->nF, s);
+    MK_CUDA(cudaStreamSynchronize(s));
+    rc = field_square_impl(f, opts, stats);
+    f->x.download((cdouble*)x, f->nF, s);
+    MK_CUDA(cudaStreamSynchronize(s));
+    MK_API_END_RC(f->ctx, rc)
+}
+
 int mk_field_decode(mk_field* f, double* field) {
     if (!f || !f->has_solution || !field) return MK_ERR_ARG;
     MK_API_BEGIN(f->ctx)

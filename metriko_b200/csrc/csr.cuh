@@ -28,22 +28,26 @@ struct DeviceCsr {
     // operators whose rows are long throughout (mean > kRowModeMean entries: the coarse IGM levels) skip the SELL copy and run the
     // warp-per-row kernel on the CSR arrays
     bool row_mode = false;
+    int row_lanes = 32;  // lanes per row in row mode (4, 8, 16 or 32, from the mean row length)
 };
 
 constexpr int kLongRow = 256;
-constexpr int kRowModeMean = 40;
+constexpr int kRowModeMean = 40;          // mean row length above which SELL is not attempted
+constexpr double kMaxSellPadding = 1.5;   // stored / true entries above which SELL is dropped for the lanes-per-row kernel ...
+constexpr double kRowModeMinMean = 8.0;   // ... unless the rows are this short (a thread per row then beats lanes per row even with padding)
+constexpr int kRowModeLong = 512;         // row mode: rows longer than this get a CTA of their own
 
 // ---- CSR -> SELL-32 conversion on the device (once per operator) ----
 // one warp per slice: width = longest non-long row, long rows flagged in a bit word and appended to the long-row list
-static __global__ void k_sell_width(int rows, int n_slices, const int* __restrict__ ptr, int* __restrict__ width32, unsigned int* __restrict__ long_bits,
-                                    int* __restrict__ long_rows, int* __restrict__ n_long) {
+static __global__ void k_sell_width(int rows, int n_slices, const int* __restrict__ ptr, int long_thresh, int* __restrict__ width32,
+                                    unsigned int* __restrict__ long_bits, int* __restrict__ long_rows, int* __restrict__ n_long) {
     const int lane = threadIdx.x & 31;
     const int sl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (sl >= n_slices) return;
     const int row = sl * 32 + lane;
     int len = 0;
     if (row < rows) len = ptr[row + 1] - ptr[row];
-    const bool is_long = len > kLongRow;
+    const bool is_long = len > long_thresh;
     const unsigned int bits = __ballot_sync(0xffffffffu, is_long);
     if (is_long) {
         long_rows[atomicAdd(n_long, 1)] = row;
@@ -101,34 +105,56 @@ static __global__ void k_sell_fill(int rows, int n_slices, const int* __restrict
     }
 }
 
-// SELL-32 layout (+ long-row list) from the plain CSR arrays already on the device (rows, cols, nnz, ptr, col, val set)
+// Chooses and builds the SpMV layout of an operator whose plain CSR arrays are on the device (rows, cols, nnz, ptr, col, val set):
+//   SELL-32 when the rows of a slice have similar lengths (stored / true entries <= kMaxSellPadding: the fine operators and the face
+//   hierarchy), otherwise "row mode": G lanes per row on the CSR arrays (the coarse IGM levels: mean 35-120 entries per row with a
+//   heavy tail, where SELL would store 4-5x the entries). Either way the very long rows (dense dofs) get one CTA each.
 template <class T>
 inline void build_sell(DeviceCsr<T>& A, cudaStream_t s) {
     const int rows = A.rows;
-    A.row_mode = rows > 0 && A.nnz > (int64_t)kRowModeMean * rows;
-    if (A.row_mode) { A.n_slices = 0; A.n_long = 0; return; }
     const int ns = (rows + 31) / 32;
     A.n_slices = ns;
+    A.row_mode = false;
+    A.n_long = 0;
+    if (rows <= 0) return;
     DevBuf<int> width(std::max(ns, 1)), counter(1);
     A.sl_ptr.alloc((size_t)ns + 1);
     A.long_bits.alloc(std::max(ns, 1));
     A.long_rows.alloc(std::max(1, std::min(rows, 1 << 16)));  // more than 65k dense rows would not be a sparse operator
-    counter.zero(s);
     const int wg = std::max(1, (ns * 32 + kThreads - 1) / kThreads);
-    k_sell_width<<<wg, kThreads, 0, s>>>(rows, ns, A.ptr.p, width.p, A.long_bits.p, A.long_rows.p, counter.p);
-    k_scan_exclusive<<<1, 1024, 0, s>>>(ns, width.p, A.sl_ptr.p);
-    MK_CHECK_LAUNCH();
+    auto scan_lengths = [&](int thresh, int& tot, int& nl) {
+        counter.zero(s);
+        k_sell_width<<<wg, kThreads, 0, s>>>(rows, ns, A.ptr.p, thresh, width.p, A.long_bits.p, A.long_rows.p, counter.p);
+        k_scan_exclusive<<<1, 1024, 0, s>>>(ns, width.p, A.sl_ptr.p);
+        MK_CHECK_LAUNCH();
+        MK_CUDA(cudaMemcpyAsync(&tot, A.sl_ptr.p + ns, sizeof(int), cudaMemcpyDeviceToHost, s));
+        MK_CUDA(cudaMemcpyAsync(&nl, counter.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+        MK_CUDA(cudaStreamSynchronize(s));
+        if (tot < 0 || nl > (1 << 16)) throw std::invalid_argument("build_sell: matrix too large / too many dense rows for this layout");
+    };
     int tot = 0, nl = 0;
-    MK_CUDA(cudaMemcpyAsync(&tot, A.sl_ptr.p + ns, sizeof(int), cudaMemcpyDeviceToHost, s));
-    MK_CUDA(cudaMemcpyAsync(&nl, counter.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-    MK_CUDA(cudaStreamSynchronize(s));
-    if (tot < 0 || nl > (1 << 16)) throw std::invalid_argument("build_sell: matrix too large / too many dense rows for the SELL layout");
+    scan_lengths(kLongRow, tot, nl);
+    A.padding = A.nnz ? (double)tot / (double)A.nnz : 1.0;  // long rows count as stored 0 / true len: only makes SELL look better
+    const double mean = (double)A.nnz / rows;
+    if (mean > kRowModeMean || (A.padding > kMaxSellPadding && mean >= kRowModeMinMean)) {
+        A.row_mode = true;
+        A.row_lanes = mean <= 6 ? 4 : (mean <= 12 ? 8 : (mean <= 24 ? 16 : 32));
+        const double pad = A.padding;
+        scan_lengths(kRowModeLong, tot, nl);  // only the really long rows leave the lanes-per-row kernel
+        A.n_long = nl;
+        if (getenv("MK_VERBOSE") && atoi(getenv("MK_VERBOSE")) >= 2)
+            fprintf(stderr, "[mk] layout: %d x %d nnz %lld mean %.1f SELL stored/true %.2f -> %d lanes per row, long rows %d\n", A.rows, A.cols,
+                    (long long)A.nnz, mean, pad, A.row_lanes, nl);
+        A.sl_ptr.release();
+        return;
+    }
     A.n_long = nl;
+    if (getenv("MK_VERBOSE") && atoi(getenv("MK_VERBOSE")) >= 2)
+        fprintf(stderr, "[mk] layout: %d x %d nnz %lld mean %.1f SELL stored/true %.2f long rows %d\n", A.rows, A.cols, (long long)A.nnz, mean, A.padding, nl);
     A.sl_col.alloc((size_t)std::max(tot, 1));
     A.sl_val.alloc((size_t)std::max(tot, 1));
     k_sell_fill<T><<<wg, kThreads, 0, s>>>(rows, ns, A.ptr.p, A.col.p, A.val.p, A.sl_ptr.p, A.sl_col.p, A.sl_val.p);
     MK_CHECK_LAUNCH();
-    A.padding = A.nnz ? (double)tot / (double)A.nnz : 1.0;
 }
 
 // plain CSR arrays only (operands of the device set-up algebra, devcsr.cuh)
@@ -237,6 +263,25 @@ __device__ __forceinline__ void finish_dot(double dot, PcgState* st, ReduceWs ws
     }
 }
 
+// one CTA sums a long row: four independent loads in flight per thread (a 15k-entry dense-dof row would otherwise serialise ~60 load
+// round trips and set the duration of the whole kernel)
+template <class T>
+__device__ __forceinline__ T long_row_sum(int b, int en, const int* __restrict__ col, const T* __restrict__ val, const T* __restrict__ x, double* red) {
+    T a0 = ST<T>::zero(), a1 = ST<T>::zero(), a2 = ST<T>::zero(), a3 = ST<T>::zero();
+    const int bs = blockDim.x;
+    int k = b + threadIdx.x;
+    for (; k + 3 * bs < en; k += 4 * bs) {
+        const int c0 = __ldg(col + k), c1 = __ldg(col + k + bs), c2 = __ldg(col + k + 2 * bs), c3 = __ldg(col + k + 3 * bs);
+        const T v0 = ld_ro(val + k), v1 = ld_ro(val + k + bs), v2 = ld_ro(val + k + 2 * bs), v3 = ld_ro(val + k + 3 * bs);
+        a0 = ST<T>::fma_(v0, ld_ro(x + c0), a0);
+        a1 = ST<T>::fma_(v1, ld_ro(x + c1), a1);
+        a2 = ST<T>::fma_(v2, ld_ro(x + c2), a2);
+        a3 = ST<T>::fma_(v3, ld_ro(x + c3), a3);
+    }
+    for (; k < en; k += bs) a0 = ST<T>::fma_(ld_ro(val + k), ld_ro(x + __ldg(col + k)), a0);
+    return block_sum_t((a0 + a1) + (a2 + a3), red);
+}
+
 // SELL-32 SpMV, one thread per row, one warp per slice, in CTAs [0, sell_blocks); the long rows (dense dofs, empty in the SELL part) are
 // served by the CTAs [sell_blocks, sell_blocks + n_long) of the SAME launch, one CTA per row -- no second kernel, no dependency.
 template <class T, int MODE>
@@ -250,10 +295,7 @@ __global__ void __launch_bounds__(kThreads, 6) k_spmv_sell(int n, int n_slices, 
     double dot = 0.0;
     if ((int)blockIdx.x >= sell_blocks) {
         const int row = long_rows[blockIdx.x - sell_blocks];
-        const int b = ptr[row], en = ptr[row + 1];
-        T acc = ST<T>::zero();
-        for (int k = b + threadIdx.x; k < en; k += blockDim.x) acc = ST<T>::fma_(ld_ro(val + k), ld_ro(x + __ldg(col + k)), acc);
-        acc = block_sum_t(acc, red);
+        const T acc = long_row_sum<T>(ptr[row], ptr[row + 1], col, val, x, red);
         if (threadIdx.x == 0) dot = row_epilogue<T, MODE>(e, row, acc);
     } else {
         const int lane = threadIdx.x & 31;
@@ -282,38 +324,67 @@ __global__ void __launch_bounds__(kThreads, 6) k_spmv_sell(int n, int n_slices, 
     finish_dot<MODE>(dot, st, ws, red);
 }
 
-// Warp-per-row SpMV on the plain CSR arrays for operators with long rows throughout (the coarse IGM levels reach > 100 entries per row):
-// lanes stride along the row (coalesced), no padding, any row length.
-template <class T, int MODE>
+// Lanes-per-row SpMV on the plain CSR arrays for operators with irregular row lengths (the coarse IGM levels): G lanes stride along
+// one row (no padding, coalesced within the row); rows longer than kRowModeLong are served by one CTA each, CTAs [row_blocks, ...).
+template <class T, int MODE, int G>
 __global__ void __launch_bounds__(kThreads) k_spmv_rows(int n, const int* __restrict__ ptr, const int* __restrict__ col, const T* __restrict__ val,
+                                                        const unsigned int* __restrict__ long_bits, int row_blocks, const int* __restrict__ long_rows,
                                                         SpmvEpi<T> e, PcgState* st, ReduceWs ws) {
     __shared__ double red[32];
     if (st && st->done) return;
     const T* __restrict__ x = e.v;
-    const int lane = threadIdx.x & 31;
-    const int nw = (gridDim.x * blockDim.x) >> 5;
     double dot = 0.0;
-    for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += nw) {
-        const int b = __ldg(ptr + row), en = __ldg(ptr + row + 1);
-        T acc = ST<T>::zero();
-        int k = b + lane;
-        for (; k + 32 < en; k += 64) {
-            const int c0 = __ldg(col + k), c1 = __ldg(col + k + 32);
-            const T v0 = ld_ro(val + k), v1 = ld_ro(val + k + 32);
-            acc = ST<T>::fma_(v0, ld_ro(x + c0), acc);
-            acc = ST<T>::fma_(v1, ld_ro(x + c1), acc);
+    if ((int)blockIdx.x >= row_blocks) {
+        const int row = long_rows[blockIdx.x - row_blocks];
+        const T acc = long_row_sum<T>(ptr[row], ptr[row + 1], col, val, x, red);
+        if (threadIdx.x == 0) dot = row_epilogue<T, MODE>(e, row, acc);
+    } else {
+        const int sub = threadIdx.x & (G - 1);
+        const int ngroups = (row_blocks * blockDim.x) / G;
+        const int nloop = (n + ngroups - 1) / ngroups;  // same trip count for every thread: the shuffles below need whole warps
+        int row = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+        for (int it = 0; it < nloop; it++, row += ngroups) {
+            const bool live = row < n && !(long_bits != nullptr && ((__ldg(long_bits + (row >> 5)) >> (row & 31)) & 1u));
+            T acc = ST<T>::zero();
+            if (live) {
+                const int b = __ldg(ptr + row), en = __ldg(ptr + row + 1);
+                int k = b + sub;
+                T acc1 = ST<T>::zero();
+                for (; k + 3 * G < en; k += 4 * G) {
+                    const int c0 = __ldg(col + k), c1 = __ldg(col + k + G), c2 = __ldg(col + k + 2 * G), c3 = __ldg(col + k + 3 * G);
+                    const T v0 = ld_ro(val + k), v1 = ld_ro(val + k + G), v2 = ld_ro(val + k + 2 * G), v3 = ld_ro(val + k + 3 * G);
+                    acc = ST<T>::fma_(v0, ld_ro(x + c0), acc);
+                    acc1 = ST<T>::fma_(v1, ld_ro(x + c1), acc1);
+                    acc = ST<T>::fma_(v2, ld_ro(x + c2), acc);
+                    acc1 = ST<T>::fma_(v3, ld_ro(x + c3), acc1);
+                }
+                for (; k < en; k += G) acc = ST<T>::fma_(ld_ro(val + k), ld_ro(x + __ldg(col + k)), acc);
+                acc = acc + acc1;
+            }
+            acc = group_sum<T>(acc, G);
+            if (live && sub == 0) dot += row_epilogue<T, MODE>(e, row, acc);
         }
-        if (k < en) acc = ST<T>::fma_(ld_ro(val + k), ld_ro(x + __ldg(col + k)), acc);
-        acc = group_sum<T>(acc, 32);
-        if (lane == 0) dot += row_epilogue<T, MODE>(e, row, acc);
     }
     finish_dot<MODE>(dot, st, ws, red);
+}
+
+template <class T, int MODE, int G>
+inline void spmv_rows_launch(const DeviceCsr<T>& A, const SpmvEpi<T>& e, PcgState* st, ReduceWs ws, cudaStream_t s) {
+    int row_blocks = stream_grid((int64_t)A.rows * G, kThreads, 16);
+    if (row_blocks + A.n_long > kMaxPartials) row_blocks = std::max(1, kMaxPartials - A.n_long);
+    k_spmv_rows<T, MODE, G><<<row_blocks + A.n_long, kThreads, 0, s>>>(A.rows, A.ptr.p, A.col.p, A.val.p, A.n_long ? A.long_bits.p : nullptr, row_blocks,
+                                                                       A.long_rows.p, e, st, ws);
 }
 
 template <class T, int MODE>
 inline void spmv_launch(const DeviceCsr<T>& A, const SpmvEpi<T>& e, PcgState* st, ReduceWs ws, cudaStream_t s) {
     if (A.row_mode) {
-        k_spmv_rows<T, MODE><<<stream_grid((int64_t)A.rows * 32, kThreads, 16), kThreads, 0, s>>>(A.rows, A.ptr.p, A.col.p, A.val.p, e, st, ws);
+        switch (A.row_lanes) {
+            case 4: spmv_rows_launch<T, MODE, 4>(A, e, st, ws, s); break;
+            case 8: spmv_rows_launch<T, MODE, 8>(A, e, st, ws, s); break;
+            case 16: spmv_rows_launch<T, MODE, 16>(A, e, st, ws, s); break;
+            default: spmv_rows_launch<T, MODE, 32>(A, e, st, ws, s); break;
+        }
     } else {
         int sell_blocks = stream_grid((int64_t)A.n_slices * 32, kThreads, 16);
         if (sell_blocks + A.n_long > kMaxPartials) sell_blocks = std::max(1, kMaxPartials - A.n_long);

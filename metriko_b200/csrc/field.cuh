@@ -254,6 +254,45 @@ static __global__ void __launch_bounds__(kThreads) k_decode(int nF, int N, const
     }
 }
 
+// ---- FieldType::CurvatureAligned (frf.h:25-33, 86-98) ----
+// principalCurvatureDir: D_f = 1/4 sum_{h in f} -c c / l * darg(h) with c = l e^{i farg(h)}, squared for N = 4; b = M D (the caller
+// divides by sqrt|D^H M D| = sqrt(aux0)). One thread per face, the three halves through face2half / next.
+static __global__ void __launch_bounds__(kThreads) k_curvature_rhs(int nF, int N, const int* __restrict__ face2half, const int* __restrict__ next,
+                                                            const double* __restrict__ farg, const double* __restrict__ len,
+                                                            const double* __restrict__ darg, const double* __restrict__ mass, cdouble* __restrict__ b,
+                                                            PcgState* st, ReduceWs ws) {
+    __shared__ double red[32];
+    double acc = 0.0;
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nF; f += gridDim.x * blockDim.x) {
+        int h = face2half[f];
+        cdouble dir = make_c(0.0, 0.0);
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            double s, c;
+            sincos(2.0 * farg[h], &s, &c);
+            const double w = -len[h] * darg[h];
+            dir = make_c(dir.x + w * c, dir.y + w * s);
+            h = next[h];
+        }
+        cdouble D = make_c(0.25 * dir.x, 0.25 * dir.y);
+        if (N == 4) D = D * D;
+        const double m = __ldg(mass + f);
+        stc(b + f, make_c(m * D.x, m * D.y));
+        acc += m * (D.x * D.x + D.y * D.y);
+    }
+    double v[1] = {acc};
+    grid_reduce<1>(v, ws.partials, ws.ticket, red, [&](const double* s) { st->aux0 = s[0]; });
+}
+
+// b /= sqrt|aux0| (frf.h:30)
+static __global__ void __launch_bounds__(kThreads) k_scale_by_aux0(int n, cdouble* __restrict__ b, const PcgState* st) {
+    const double s = 1.0 / sqrt(fabs(st->aux0));
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const cdouble v = ldc(b + i);
+        stc(b + i, make_c(v.x * s, v.y * s));
+    }
+}
+
 // ---- solution recycling across the outer iterations (Galerkin projection onto earlier solution increments) ----
 // The right-hand sides M u_k of successive inverse-iteration steps converge to the span of the few slowest eigenvectors,
 // which earlier solves already contain. E holds L-orthonormal increments e_j (e_i^H L e_j = delta_ij), so the

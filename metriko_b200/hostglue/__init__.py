@@ -111,6 +111,10 @@ class Session:
         return dict(twin=self.get("twin"), face=self.get("face"), face2half=self.get("face2half"), next=self.get("next"),
                     heArgOnFace=self.get("heArgOnFace"), faceArea=self.get("faceArea"))
 
+    def curvature_inputs(self):
+        """Per-half arrays principalCurvatureDir reads (frf.h:86-98): half lengths and dihedral angles (hmesh.h:215, 508-519)."""
+        return dict(heLen=self.get("heLen"), dihedralArg=self.get("dihedralArg"))
+
     def field_post(self, compressed, N: int = 4, matching: str = "curl") -> None:
         self.put("compressed", np.asarray(compressed, np.complex128))
         self._chk(self._L.hg_field_post(self._h, N, 1 if matching == "curl" else 0))

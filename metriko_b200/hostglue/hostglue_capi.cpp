@@ -39,6 +39,8 @@ static void export_mesh(Session& s) {
     b.put("faceArea", m.faceArea);
     b.put("heArgOnFace", m.heArgOnFace);
     b.put("angleDefect", m.angleDefect);
+    b.put("dihedralArg", m.dihedralArg);
+    b.put("heLen", m.heLen);
     auto put3 = [&](const char* name, const std::vector<V3>& v) {
         std::vector<double> o(v.size() * 3);
         for (size_t i = 0; i < v.size(); i++) { o[3 * i] = v[i].x; o[3 * i + 1] = v[i].y; o[3 * i + 2] = v[i].z; }

@@ -150,6 +150,7 @@ struct Hmesh {
     std::vector<int> next, prev, twin, tail, head, edge, face, crnr;
     std::vector<V3> faceBasisX, faceBasisY, faceNormal;
     std::vector<double> faceArea, heArgOnFace, angleDefect;
+    std::vector<double> dihedralArg, heLen;  // per half: dihedral angle (hmesh.h:508-519), |vec(h)| (hmesh.h:215)
 
     V3 vec(int h) const { return pos[head[h]] - pos[tail[h]]; }
     bool canonical(int h) const { return edge2half[edge[h]] == h; }
@@ -275,6 +276,17 @@ inline Hmesh build_hmesh(const RawMesh& rm) {
             h = m.vnext_ccw(h);
         } while (h != h0);
         m.angleDefect[v] = 2 * M_PI - sum;
+    }
+    // dihedral angle per half (hmesh.h:508-519; closed meshes: no boundary edges) and half length (hmesh.h:215)
+    m.dihedralArg.resize(nH);
+    m.heLen.resize(nH);
+    for (int h = 0; h < nH; h++) {
+        const V3 n1 = m.faceNormal[m.face[h]], n2 = m.faceNormal[m.face[m.twin[h]]];
+        const V3 e = m.vec(h);
+        const double len = e.norm();
+        const V3 v = e * (1.0 / len);
+        m.heLen[h] = len;
+        m.dihedralArg[h] = std::atan2(v.dot(n1.cross(n2)), n1.dot(n2));
     }
     return m;
 }

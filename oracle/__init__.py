@@ -12,5 +12,6 @@ pinned only by the reference's own runtime invariants. The
 scipy's SuperLU (`splu`), the closest available relative of `Eigen::SparseLU` (sparse_linear_solver.h:42).
 """
 from .field import connection_laplacian, galerkin_mass_matrix, solve_smallest_eig, decode_field, random_u0  # noqa: F401
+from .field import principal_curvature_dir, curvature_aligned  # noqa: F401
 from . import igm  # noqa: F401
 from .igm import iterative_rounding, iterative_rounding_x2f, naive_poisson  # noqa: F401

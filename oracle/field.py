@@ -56,6 +56,31 @@ def solve_smallest_eig(L, M, u0, n_iter: int = 50):
     return x
 
 
+def principal_curvature_dir(face2half, next_, heArgOnFace, heLen, dihedralArg) -> np.ndarray:
+    """frf.h:86-98: D_f = 1/4 sum over the halves h of f of -c c / l * darg(h), c = polar(1, farg(h)) * l, l = len(h)."""
+    h = np.asarray(face2half, np.int64).copy()
+    nxt = np.asarray(next_)
+    farg, ln, da = (np.asarray(a, np.float64) for a in (heArgOnFace, heLen, dihedralArg))
+    d = np.zeros(len(h), np.complex128)
+    for _ in range(3):
+        c = np.exp(1j * farg[h]) * ln[h]
+        d += -c * c / ln[h] * da[h]
+        h = nxt[h]
+    return 0.25 * d
+
+
+def curvature_aligned(L, M, D, N: int):
+    """frf.h:25-33 with the reference's lambda = 0: D squared for N = 4, rhs = M D / sqrt|D^H M D|, x = solveSquare(L - 0 M, rhs)
+    (sls.h:16-27: a sparse LU solve). Returns (x, rhs)."""
+    assert N in (2, 4)
+    D = np.asarray(D, np.complex128)
+    if N == 4:
+        D = D * D
+    rhs = (M @ D) / np.sqrt(abs(np.vdot(D, M @ D)))
+    x = spla.splu(sp.csc_matrix(L)).solve(rhs)
+    return x, rhs
+
+
 def decode_field(z, N: int) -> np.ndarray:
     """frf.h:37-43: field(f,i) = (e^{i arg z_f})^{1/N} * (e^{2 pi i / N})^i."""
     z = np.asarray(z, np.complex128)

@@ -123,3 +123,26 @@ def test_full_size_properties(ctx):
     st3 = dict(F.stats)
     assert field_angle_error(z, z3, 4).max() < ANGLE_TOL
     assert st["inner_iterations"] < 0.6 * st3["inner_iterations"]
+
+
+def test_curvature_aligned_field_matches_oracle(ctx):
+    """FieldType::CurvatureAligned (frf.h:25-33, 86-98): device rhs = M D / sqrt|D^H M D| and solveSquare(L, rhs) against the oracle's
+    sparse-LU solve; decoded directions within 1e-5 rad (no global phase here: the solve is a linear system, not an eigenproblem)."""
+    s = Session().make_sphere(20, 4, bump=0.15)
+    fi, cu = s.field_inputs(), s.curvature_inputs()
+    nF = s.dims["nF"]
+    L = oracle.connection_laplacian(fi["twin"], fi["face"], fi["heArgOnFace"], nF, 4)
+    M = oracle.galerkin_mass_matrix(fi["faceArea"])
+    D = oracle.principal_curvature_dir(fi["face2half"], fi["next"], fi["heArgOnFace"], cu["heLen"], cu["dihedralArg"])
+    x_ref, rhs_ref = oracle.curvature_aligned(L, M, D, 4)
+    F = api.FaceRosyField(ctx, fi["face2half"], fi["next"], fi["twin"], fi["face"], fi["heArgOnFace"], fi["faceArea"], 4)
+    x, rhs = F.solveCurvatureAligned(cu["heLen"], cu["dihedralArg"], return_rhs=True)
+    assert np.abs(rhs - rhs_ref).max() <= 1e-12 * np.abs(rhs_ref).max()
+    assert F.stats["relres_max"] <= 1.001e-10 and F.stats["status"] == 0
+    assert np.abs(x - x_ref).max() <= 1e-8 * np.abs(x_ref).max()
+    big = np.abs(x_ref) > 1e-6 * np.abs(x_ref).max()      # the direction of a (numerically) zero vector is undefined
+    assert (np.abs(np.angle(x[big] * np.conj(x_ref[big]))) / 4).max() < 1e-5
+    assert np.abs(F.decode() - oracle.decode_field(x, 4)).max() < 1e-9
+    y = F.solveSquare(rhs_ref)
+    assert np.abs(y - x_ref).max() <= 1e-8 * np.abs(x_ref).max()
+    F.close()
