@@ -40,7 +40,9 @@ typedef struct mk_solve_opts {
     int precond;       /* 0 = none, 1 = smoothed-aggregation multigrid (default) */
     int use_graph;     /* replay the PCG iteration as a CUDA graph (default 1) */
     int recycle;       /* eigen-solve: how many earlier solution increments are kept as a Galerkin start space for the next
-                          inverse-iteration solve (default 32, 0 = plain warm start); n * 16 B each on the device */
+                          inverse-iteration solve (default 64, capped by the number of outer iterations; 0 = plain warm start); n * 16 B each on
+                          the device. Measured at 1M vertices, 50 outer steps: 4018 inner iterations without, 1559 with 32 slots (the space
+                          freezes when full and the counts climb again), 1187 with 50 */
 } mk_solve_opts;
 
 typedef struct mk_stats {

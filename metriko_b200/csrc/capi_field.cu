@@ -34,7 +34,7 @@ void mk_default_opts(mk_solve_opts* o) {
     o->max_iter = 100000;
     o->precond = 1;
     o->use_graph = 1;
-    o->recycle = 32;
+    o->recycle = 64;
 }
 
 int mk_device_count(void) {

@@ -368,6 +368,8 @@ struct DistPcg {
         A.apply(x_ext, q.p, nullptr, s);
         k_dist_residual<<<grid, kThreads, 0, s>>>(n, b, q.p, r.p);
         int keep = 0;
+        bool breakdown = false;
+        double prev_relres = 1e300;
         for (int attempt = 0; attempt < 4; attempt++) {
             start(A, M, b, tol, maxit, keep);
             keep = 1;
@@ -379,6 +381,7 @@ struct DistPcg {
                 if (h_st->done) break;
                 batch = chunk;
             }
+            breakdown = h_st->done == 2;
             // true residual
             A.apply(x_ext, q.p, nullptr, s);
             k_dist_residual<<<grid, kThreads, 0, s>>>(n, b, q.p, r.p);
@@ -391,9 +394,11 @@ struct DistPcg {
             out.relres = h_st->bnorm2 > 0 ? std::sqrt(rr / h_st->bnorm2) : 0.0;
             out.restarts = attempt;
             launches += 6;
-            if (out.relres <= tol * 1.0000001 || h_st->iter >= maxit || h_st->done == 2) break;
+            if (out.relres <= tol * 1.0000001 || h_st->iter >= maxit || breakdown) break;
+            if (attempt > 0 && out.relres > 0.5 * prev_relres) break;  // fp64 floor reached (see Pcg::solve)
+            prev_relres = out.relres;
         }
-        out.status = (out.relres <= tol * 1.0000001 || h_st->bnorm2 == 0) ? 0 : (h_st->iter >= maxit ? 1 : 2);
+        out.status = (out.relres <= tol * 1.0000001 || h_st->bnorm2 == 0) ? 0 : (breakdown ? 2 : 1);
         out.launches = launches;
         return out;
     }

@@ -426,6 +426,7 @@ inline EigStats inverse_iteration(Ctx& ctx, OpT& A, Precond<cdouble>* M, const d
         MK_CHECK_LAUNCH();
         SolveStats ss = pcg.solve(b, x, tol, maxit, true, 16, use_graph, hint);
         hint = ss.iterations + 1;
+        if (getenv("MK_VERBOSE")) fprintf(stderr, "[mk] inverse iteration %d: %d inner iterations (restarts %d), relres %.2e\n", it, ss.iterations, ss.restarts, ss.relres);
         if (add) {
             // new basis vector: e = x - x0, L-orthogonalised against the others (it already is, up to the solve tolerance),
             // normalised in the energy norm with an explicit L e so that the Galerkin relation stays exact to round-off

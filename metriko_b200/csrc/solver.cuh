@@ -267,6 +267,8 @@ public:
             launch_residual(b, tol2, maxit, 0);
             launches += 1 + A_->launches_per_apply();
         }
+        bool breakdown = false;
+        double prev_relres = 1e300;
         for (int attempt = 0; attempt < 4; attempt++) {
             start_direction();
             launches += 1 + (M_ ? M_->launches_per_apply() : 0);
@@ -278,6 +280,7 @@ public:
                 if (h_st_->done) break;
                 batch = hint > 0 ? std::max(2, chunk / 4) : chunk;
             }
+            breakdown = h_st_->done == 2;
             // true residual check (recurrence residuals drift at the 1e-10 level)
             A_->apply(x, q_.p, nullptr, ws(), stream_);
             if (P_) P_->apply(q_.p, nullptr, stream_);
@@ -288,8 +291,15 @@ public:
             out.relres = h_st_->bnorm2 > 0 ? std::sqrt(h_st_->rr / h_st_->bnorm2) : 0.0;
             out.restarts = attempt;
             if (h_st_->done == 1 || h_st_->iter >= maxit) break;
+            if (breakdown) break;
+            // The recurrence residual met the threshold but the true one did not: restart from the true residual -- unless the
+            // last restart gained less than 2x, i.e. fp64 is exhausted (attainable ||b - A x|| / ||b|| ~ eps * cond(A): ~5e-11 at 1M
+            // vertices, ~4e-10 at 8M for right-hand sides along the smallest eigenvector, which inverse iteration produces)
+            if (attempt > 0 && out.relres > 0.5 * prev_relres) break;
+            prev_relres = out.relres;
         }
-        out.status = (out.relres <= tol * 1.0000001 || h_st_->bnorm2 == 0) ? 0 : (h_st_->iter >= maxit ? 1 : 2);
+        // 0 ok; 1 tolerance not reached (iteration cap or fp64 floor; the result is still the best iterate); 2 breakdown (<p, A p> <= 0 or NaN)
+        out.status = (out.relres <= tol * 1.0000001 || h_st_->bnorm2 == 0) ? 0 : (breakdown ? 2 : 1);
         out.launches = launches;
         return out;
     }

@@ -50,7 +50,8 @@ def one(ctx, s, name, igm=True):
         F.assemble()
         F.solveSmallestEig(u0, 50)
         st = dict(F.stats)
-        r = {"field_setup_ms": st["setup_ms"], "field_solve_ms": st["solve_ms"], "field_inner": st["inner_iterations"]}
+        r = {"field_setup_ms": st["setup_ms"], "field_solve_ms": st["solve_ms"], "field_inner": st["inner_iterations"],
+             "field_relres_max": st["relres_max"], "field_status": st["status"]}
         if igm:
             prob = api.IgmProblem(ctx, X2F, UFull, inp["F2"], inp["length"])
             o = prob.round(inp["fixedIdcs"], inp["fixedVals"], inp["singularIdcs"], inp["integerIdcs"], True, False)
