@@ -37,6 +37,10 @@ sys.path.insert(0, ROOT)
 METRIC = "field+IGM solve throughput at 1M verts (ms_per_step = solve ms)"
 UNIT = "verts/s"
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only when MEASURED_PEAKS.json is absent
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of k_spmv_face<false> from the committed `ncu --set full` capture
+# (profiles/ncu_full_spmv_kernels_r01b.csv: 159.5 MB read + 19.8 MB written), keyed by the face count it was taken at
+NCU_TRAFFIC_BYTES = {2097152: 179.3e6}
+NCU_TRAFFIC_SOURCE = "profiles/ncu_full_spmv_kernels_r01b.csv (ncu --set full, per launch)"
 
 
 def log(*a):
@@ -214,6 +218,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     h2d = sum(host[k].nbytes for k in host)
     d2h = nF * 16 + UFull.shape[0] * 8
     stage = {}
+    e2e_stage = []
 
     def step_resident():
         """inputs in HBM: field arrays uploaded once (F), u0 / x device tensors, X2F and F2 device tensors (mk_igm_create_dev);
@@ -236,14 +241,23 @@ def run_b200(args, rank: int, world: int, local_rank: int):
 
     def step_e2e():
         """reference-facing API with host buffers: create -> assemble -> solveSmallestEig -> iterative_rounding"""
+        t = [time.perf_counter()]
         Fe = api.FaceRosyField(ctx, host["face2half"], host["next"], host["twin"], host["face"], host["heArgOnFace"], host["faceArea"], 4)
+        t.append(time.perf_counter())
         ze = Fe.solveSmallestEig(host["u0"], 50)
+        t.append(time.perf_counter())
         Fe.close()
+        t.append(time.perf_counter())
         prob = api.IgmProblem(ctx, X2F, UFull, inp["F2"], inp["length"], raw=(host["x2f_ptr"], host["x2f_col"], host["x2f_val"],
                                                                              host["uf_ptr"], host["uf_col"], host["uf_val"], host["F2"]))
+        t.append(time.perf_counter())
         out = prob.round(inp["fixedIdcs"], inp["fixedVals"], inp["singularIdcs"], inp["integerIdcs"], True, False)
+        t.append(time.perf_counter())
         prob.close()
+        t.append(time.perf_counter())
         assert out["success"] and ze.shape[0] == nF
+        e2e_stage.append(dict(zip(("field_create", "field_solve", "field_close", "igm_create", "igm_round", "igm_close"),
+                                  [round((b - a) * 1e3, 1) for a, b in zip(t[:-1], t[1:])])))
         return out
 
     def timed(fn, warm, steps, profile=False):
@@ -296,7 +310,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     peak, peak_src = hbm_peak()
     achieved = alg_bytes / (spmv_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "k_spmv_face<false> (y = L x, complex fp64 face stencil)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "us_per_launch": spmv_ms * 1e3,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES.get(nF), "traffic_source": NCU_TRAFFIC_SOURCE if nF in NCU_TRAFFIC_BYTES else None,
+                "peak_source": peak_src, "us_per_launch": spmv_ms * 1e3,
                 "algorithmic_bytes_per_launch": alg_bytes, "stored_format_bytes_per_launch": stored_bytes,
                 "achieved_stored_format_gbs": stored_bytes / (spmv_ms * 1e-3) / 1e9, "fused_dot_us_per_launch": spmv_dot_ms * 1e3}
     try:
@@ -304,7 +319,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         a_ms = prob.spmv_bench(reps, False)
         A = prob.matrix()
         a_bytes = A.nnz * 12 + (A.shape[0] + 1) * 4 + A.shape[0] * 16
-        roofline["igm_spmv"] = {"kernel": "k_spmv_csr<double> (y = (A0 + 1e-4 I) x)", "rows": A.shape[0], "nnz": int(A.nnz),
+        roofline["igm_spmv"] = {"kernel": "k_spmv_sell<double, kPlain> (y = (A0 + 1e-4 I) x, SELL-32 + long-row CTAs in one launch)", "rows": A.shape[0], "nnz": int(A.nnz),
                                 "us_per_launch": a_ms * 1e3, "achieved": a_bytes / (a_ms * 1e-3) / 1e9, "frac": a_bytes / (a_ms * 1e-3) / 1e9 / peak}
         prob.close()
     except Exception as e:  # noqa: BLE001
@@ -322,7 +337,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                        "parallelism": f"batch x{world} (one mesh per GPU, no data-path collective)",
                        "l2": "inputs larger than L2 (field stencil working set 92 B/face = %.0f MB)" % (92 * nF / 1e6)},
             "e2e": {"value": world * nV / (per_e2e * 1e-3), "unit": UNIT, "ms_per_step": per_e2e, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stages": stage}
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stages": stage, "e2e_stages_ms": e2e_stage[-args.steps:]}
     if world == 1 and not args.no_cpu:
         t, cv, det = cpu_reference_step(args.cpu_levels)
         line["cpu_baseline"] = {"value": cv / t, "unit": UNIT, "cores": 1, "kind": "port", "ms": t * 1e3,

@@ -15,6 +15,7 @@ struct mk_dist {
 };
 
 struct mk_dfield {
+    std::shared_ptr<Arena> arena;   // first member: destroyed last
     mk_dist* d = nullptr;
     cudaStream_t stream = nullptr;
     int device = 0;
@@ -75,6 +76,7 @@ int mk_dfield_create(mk_dist* d, int n_local, int n_interior, int n_halo, const 
     MK_CUDA(cudaSetDevice(d->ctx->c.device));
     cudaStream_t s = d->ctx->c.stream;
     auto f = std::make_unique<mk_dfield>();
+    f->arena = d->ctx->c.arena;
     f->d = d;
     f->stream = s;
     f->device = d->ctx->c.device;

@@ -11,6 +11,7 @@
 using namespace mk;
 
 struct mk_field {
+    std::shared_ptr<Arena> arena;   // first member: destroyed last, after every buffer below went back to it
     mk_ctx* ctx = nullptr;
     cudaStream_t stream = nullptr;  // copies, so that destruction does not depend on the context object
     int device = 0;
@@ -60,6 +61,7 @@ int mk_ctx_create(int device, void* stream, mk_ctx** out) {
     }
     mk_ctx* c = new mk_ctx();
     c->c.device = device;
+    c->c.arena = std::make_shared<Arena>();
     if (stream) {
         c->c.stream = (cudaStream_t)stream;
     } else {
@@ -92,6 +94,7 @@ int mk_field_create(mk_ctx* ctx, int nF, int nH, int N, const int* face2half, co
     MK_CUDA(cudaSetDevice(ctx->c.device));
     cudaStream_t s = ctx->c.stream;
     auto f = std::make_unique<mk_field>();
+    f->arena = ctx->c.arena;
     f->ctx = ctx;
     f->stream = s;
     f->device = ctx->c.device;

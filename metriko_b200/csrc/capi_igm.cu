@@ -97,6 +97,7 @@ extern "C" int mk_solve_smallest_eig_csc(mk_ctx* ctx, int n, const int* L_outer,
 // real SPD solver handle (CholeskyWrapper, ir.h:14-20)
 // ------------------------------------------------------------------------------------------------
 struct mk_spd {
+    std::shared_ptr<Arena> arena;   // first member: destroyed last
     mk_ctx* ctx = nullptr;
     cudaStream_t stream = nullptr;
     int device = 0;
@@ -118,6 +119,7 @@ extern "C" int mk_spd_factorize(mk_ctx* ctx, int n, const int* outer, const int*
     cudaStream_t s = ctx->c.stream;
     auto t0 = hclock::now();
     auto h = std::make_unique<mk_spd>();
+    h->arena = ctx->c.arena;
     h->ctx = ctx;
     h->stream = s;
     h->device = ctx->c.device;
@@ -208,6 +210,7 @@ extern "C" int mk_spd_spmv_bench(mk_spd* h, int reps, int fused_dot, double* ms_
 // IGM
 // ------------------------------------------------------------------------------------------------
 struct mk_igm {
+    std::shared_ptr<Arena> arena;   // first member: destroyed last
     mk_ctx* ctx = nullptr;
     cudaStream_t stream = nullptr;
     int device = 0;
@@ -269,6 +272,7 @@ static int igm_create_impl(mk_ctx* ctx, int rows, int cols, const int64_t* x2f_p
     cudaStream_t s = ctx->c.stream;
     auto t0 = hclock::now();
     auto g = std::make_unique<mk_igm>();
+    g->arena = ctx->c.arena;
     g->ctx = ctx;
     g->stream = s;
     g->device = ctx->c.device;

@@ -8,7 +8,7 @@ struct mk_ctx {
     mk::Ctx c;
 };
 
-#define MK_API_BEGIN(ctxp) try { mk::AllocStreamScope _alloc_scope((ctxp)->c.stream);
+#define MK_API_BEGIN(ctxp) try { mk::AllocStreamScope _alloc_scope((ctxp)->c.stream, (ctxp)->c.arena.get());
 #define MK_API_END_RC(ctxp, rc)                                                     \
     return (rc);                                                                    \
     } catch (const mk::CudaError& e) { (ctxp)->c.err = e.what(); return MK_ERR_CUDA; } \

@@ -14,6 +14,7 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     bool owns_stream = false;
     std::string err;
+    std::shared_ptr<Arena> arena;  // device memory of everything created under this context (handles share ownership)
 };
 
 // Face stencil storage ("ELL-3", SoA): every face row of L has the constant diagonal 3 + 1e-9 (frf.h:65-75, closed

@@ -3,42 +3,135 @@
 // Replaces the direct factorisations of the reference (Eigen::SparseLU sls.h:42-47, CHOLMOD LDL^T
 // ss/suitesparse_pdefinite.h:26-41, Eigen::SimplicialLLT ir.h:14-20) with an HBM-bound iterative path.
 #pragma once
+#include <map>
 #include <memory>
+#include <unordered_map>
 #include <vector>
 
 #include "common.cuh"
 
 namespace mk {
 
-// Device allocations go through the stream-ordered pool (cudaMallocAsync) on the calling context's stream: a solve step
-// allocates and frees gigabytes of operators / hierarchies, and cudaMalloc / cudaFree round trips to the driver cost
-// hundreds of ms per step. Every C-ABI entry point sets the stream (AllocStreamScope) before touching a DevBuf.
+// Device memory comes from a per-context arena: a few large slabs obtained from the driver once and sub-allocated on the host
+// (best fit, coalescing free list). A solve step allocates and frees gigabytes of operators, hierarchies and work vectors; driver
+// allocations -- cudaMalloc / cudaFree as well as growth or trimming of the stream-ordered pool -- cost 0.06-0.5 s per GB on this
+// platform (profiles/alloc_probe_r01.txt) and showed up as sporadic 0.3-0.9 s outliers inside timed steps. With the arena a step makes
+// no driver allocation call at all once the slabs exist. Every context issues all its work on ONE stream, so handing a freed block to
+// the next request is ordered correctly without events; one host thread per context (include/metriko_b200.h).
+// Buffers created outside any context scope fall back to cudaMallocAsync on the scope's stream.
+struct Arena {
+    static constexpr size_t kAlign = 512;
+    static constexpr size_t kSlabMin = (size_t)2 << 30;
+    std::vector<void*> slabs;
+    std::map<char*, size_t> free_by_addr;
+    std::multimap<size_t, char*> free_by_size;
+    std::unordered_map<void*, size_t> live;
+    size_t reserved = 0, in_use = 0, peak = 0;
+    Arena() = default;
+    Arena(const Arena&) = delete;
+    Arena& operator=(const Arena&) = delete;
+    ~Arena() {
+        for (void* p : slabs) cudaFree(p);
+    }
+    bool is_slab_base(const char* p) const {
+        for (void* b : slabs)
+            if ((const char*)b == p) return true;
+        return false;
+    }
+    void erase_free(char* p, size_t sz) {
+        free_by_addr.erase(p);
+        auto r = free_by_size.equal_range(sz);
+        for (auto it = r.first; it != r.second; ++it)
+            if (it->second == p) { free_by_size.erase(it); break; }
+    }
+    void insert_free(char* p, size_t sz) {
+        // coalesce with the neighbours -- never across a slab boundary: a block must lie inside ONE driver allocation
+        // (cudaMemcpy / cudaMemset reject ranges that span two, even when they are adjacent in the address space)
+        auto nx = free_by_addr.find(p + sz);
+        if (nx != free_by_addr.end() && !is_slab_base(p + sz)) { const size_t s2 = nx->second; erase_free(nx->first, s2); sz += s2; }
+        auto it = free_by_addr.lower_bound(p);
+        if (it != free_by_addr.begin() && !is_slab_base(p)) {
+            --it;
+            if (it->first + it->second == p) { char* q = it->first; const size_t s0 = it->second; erase_free(q, s0); p = q; sz += s0; }
+        }
+        free_by_addr[p] = sz;
+        free_by_size.emplace(sz, p);
+    }
+    void* alloc(size_t bytes) {
+        bytes = (bytes + kAlign - 1) / kAlign * kAlign;
+        auto it = free_by_size.lower_bound(bytes);
+        if (it == free_by_size.end()) {
+            const size_t slab = bytes > kSlabMin ? bytes : kSlabMin;
+            void* base = nullptr;
+            MK_CUDA(cudaMalloc(&base, slab));
+            slabs.push_back(base);
+            reserved += slab;
+            insert_free((char*)base, slab);
+            it = free_by_size.lower_bound(bytes);
+        }
+        char* p = it->second;
+        const size_t sz = it->first;
+        erase_free(p, sz);
+        if (sz > bytes) insert_free(p + bytes, sz - bytes);
+        live[p] = bytes;
+        in_use += bytes;
+        if (in_use > peak) peak = in_use;
+        return p;
+    }
+    void release(void* p) {
+        auto it = live.find(p);
+        if (it == live.end()) return;
+        const size_t sz = it->second;
+        live.erase(it);
+        in_use -= sz;
+        insert_free((char*)p, sz);
+    }
+};
+
 inline cudaStream_t& alloc_stream() {
     static thread_local cudaStream_t s = nullptr;
     return s;
 }
+inline Arena*& alloc_arena() {
+    static thread_local Arena* a = nullptr;
+    return a;
+}
 struct AllocStreamScope {
     cudaStream_t prev;
-    explicit AllocStreamScope(cudaStream_t s) : prev(alloc_stream()) { alloc_stream() = s; }
-    ~AllocStreamScope() { alloc_stream() = prev; }
+    Arena* prev_arena;
+    explicit AllocStreamScope(cudaStream_t s, Arena* a = nullptr) : prev(alloc_stream()), prev_arena(alloc_arena()) { alloc_stream() = s; alloc_arena() = a; }
+    ~AllocStreamScope() { alloc_stream() = prev; alloc_arena() = prev_arena; }
 };
 
 template <class T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
+    Arena* owner = nullptr;  // the arena the block came from (null: cudaMallocAsync); handles keep their arena alive
     DevBuf() = default;
     explicit DevBuf(size_t n_) { alloc(n_); }
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
-    DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), owner(o.owner) { o.p = nullptr; o.n = 0; o.owner = nullptr; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; owner = o.owner; o.p = nullptr; o.n = 0; o.owner = nullptr; }
+        return *this;
+    }
     ~DevBuf() { release(); }
-    void release() { if (p) cudaFreeAsync(p, alloc_stream()); p = nullptr; n = 0; }
+    void release() {
+        if (p) {
+            if (owner) owner->release(p);
+            else cudaFreeAsync(p, alloc_stream());
+        }
+        p = nullptr; n = 0; owner = nullptr;
+    }
     void alloc(size_t n_) {
         release();
         n = n_;
-        if (n) MK_CUDA(cudaMallocAsync((void**)&p, n * sizeof(T), alloc_stream()));
+        if (!n) return;
+        owner = alloc_arena();
+        if (owner) p = (T*)owner->alloc(n * sizeof(T));
+        else MK_CUDA(cudaMallocAsync((void**)&p, n * sizeof(T), alloc_stream()));
     }
     void zero(cudaStream_t s) { if (n) MK_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
     void upload(const T* h, size_t cnt, cudaStream_t s) { if (cnt) MK_CUDA(cudaMemcpyAsync(p, h, cnt * sizeof(T), cudaMemcpyHostToDevice, s)); }
