@@ -22,16 +22,18 @@ struct DeviceCsr {
     DevBuf<T> sl_val;
     double padding = 1.0;   // stored / true entries
     // rows with more than kLongRow entries (dense dofs): empty in the SELL part, served by one extra CTA each in the same launch
-    DevBuf<int> long_rows;
-    DevBuf<unsigned int> long_bits;  // bit (row & 31) of word (row >> 5)
-    int n_long = 0;
+    DevBuf<int> long_rows;           // "medium" rows (long_thresh < length <= kHugeRow): one WARP each, 8 per extra CTA
+    DevBuf<int> huge_rows;           // longer rows (dense dofs): one CTA each
+    DevBuf<unsigned int> long_bits;  // bit (row & 31) of word (row >> 5): row is served by the extra CTAs, not by the bulk part
+    int n_long = 0, n_huge = 0;
     // operators whose rows are long throughout (mean > kRowModeMean entries: the coarse IGM levels) skip the SELL copy and run the
     // warp-per-row kernel on the CSR arrays
     bool row_mode = false;
     int row_lanes = 32;  // lanes per row in row mode (4, 8, 16 or 32, from the mean row length)
 };
 
-constexpr int kLongRow = 256;
+constexpr int kLongRow = 64;               // SELL: rows longer than this leave the slices (one wide row would serialise its whole slice)
+constexpr int kHugeRow = 2048;            // rows longer than this get a whole CTA, the ones in between a warp
 constexpr int kRowModeMean = 40;          // mean row length above which SELL is not attempted
 constexpr double kMaxSellPadding = 1.5;   // stored / true entries above which SELL is dropped for the lanes-per-row kernel ...
 constexpr double kRowModeMinMean = 8.0;   // ... unless the rows are this short (a thread per row then beats lanes per row even with padding)
@@ -40,7 +42,8 @@ constexpr int kRowModeLong = 512;         // row mode: rows longer than this get
 // ---- CSR -> SELL-32 conversion on the device (once per operator) ----
 // one warp per slice: width = longest non-long row, long rows flagged in a bit word and appended to the long-row list
 static __global__ void k_sell_width(int rows, int n_slices, const int* __restrict__ ptr, int long_thresh, int* __restrict__ width32,
-                                    unsigned int* __restrict__ long_bits, int* __restrict__ long_rows, int* __restrict__ n_long) {
+                                    unsigned int* __restrict__ long_bits, int* __restrict__ long_rows, int* __restrict__ huge_rows,
+                                    int* __restrict__ n_long) {
     const int lane = threadIdx.x & 31;
     const int sl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (sl >= n_slices) return;
@@ -50,7 +53,8 @@ static __global__ void k_sell_width(int rows, int n_slices, const int* __restric
     const bool is_long = len > long_thresh;
     const unsigned int bits = __ballot_sync(0xffffffffu, is_long);
     if (is_long) {
-        long_rows[atomicAdd(n_long, 1)] = row;
+        if (len > kHugeRow) huge_rows[atomicAdd(n_long + 1, 1)] = row;
+        else long_rows[atomicAdd(n_long, 1)] = row;
         len = 0;
     }
     for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
@@ -116,21 +120,27 @@ inline void build_sell(DeviceCsr<T>& A, cudaStream_t s) {
     A.n_slices = ns;
     A.row_mode = false;
     A.n_long = 0;
+    A.n_huge = 0;
     if (rows <= 0) return;
-    DevBuf<int> width(std::max(ns, 1)), counter(1);
+    DevBuf<int> width(std::max(ns, 1)), counter(2);
     A.sl_ptr.alloc((size_t)ns + 1);
     A.long_bits.alloc(std::max(ns, 1));
-    A.long_rows.alloc(std::max(1, std::min(rows, 1 << 16)));  // more than 65k dense rows would not be a sparse operator
+    A.long_rows.alloc(std::max(1, rows));
+    A.huge_rows.alloc(std::max(1, std::min(rows, 1 << 16)));  // more than 65k dense rows would not be a sparse operator
     const int wg = std::max(1, (ns * 32 + kThreads - 1) / kThreads);
+    int nh = 0;
     auto scan_lengths = [&](int thresh, int& tot, int& nl) {
         counter.zero(s);
-        k_sell_width<<<wg, kThreads, 0, s>>>(rows, ns, A.ptr.p, thresh, width.p, A.long_bits.p, A.long_rows.p, counter.p);
+        k_sell_width<<<wg, kThreads, 0, s>>>(rows, ns, A.ptr.p, thresh, width.p, A.long_bits.p, A.long_rows.p, A.huge_rows.p, counter.p);
         k_scan_exclusive<<<1, 1024, 0, s>>>(ns, width.p, A.sl_ptr.p);
         MK_CHECK_LAUNCH();
+        int c[2] = {0, 0};
         MK_CUDA(cudaMemcpyAsync(&tot, A.sl_ptr.p + ns, sizeof(int), cudaMemcpyDeviceToHost, s));
-        MK_CUDA(cudaMemcpyAsync(&nl, counter.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+        MK_CUDA(cudaMemcpyAsync(c, counter.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
         MK_CUDA(cudaStreamSynchronize(s));
-        if (tot < 0 || nl > (1 << 16)) throw std::invalid_argument("build_sell: matrix too large / too many dense rows for this layout");
+        nl = c[0];
+        nh = c[1];
+        if (tot < 0 || nh > (1 << 16)) throw std::invalid_argument("build_sell: matrix too large / too many dense rows for this layout");
     };
     int tot = 0, nl = 0;
     scan_lengths(kLongRow, tot, nl);
@@ -142,15 +152,18 @@ inline void build_sell(DeviceCsr<T>& A, cudaStream_t s) {
         const double pad = A.padding;
         scan_lengths(kRowModeLong, tot, nl);  // only the really long rows leave the lanes-per-row kernel
         A.n_long = nl;
+        A.n_huge = nh;
         if (getenv("MK_VERBOSE") && atoi(getenv("MK_VERBOSE")) >= 2)
             fprintf(stderr, "[mk] layout: %d x %d nnz %lld mean %.1f SELL stored/true %.2f -> %d lanes per row, long rows %d\n", A.rows, A.cols,
-                    (long long)A.nnz, mean, pad, A.row_lanes, nl);
+                    (long long)A.nnz, mean, pad, A.row_lanes, nl + nh);
         A.sl_ptr.release();
         return;
     }
     A.n_long = nl;
+    A.n_huge = nh;
     if (getenv("MK_VERBOSE") && atoi(getenv("MK_VERBOSE")) >= 2)
-        fprintf(stderr, "[mk] layout: %d x %d nnz %lld mean %.1f SELL stored/true %.2f long rows %d\n", A.rows, A.cols, (long long)A.nnz, mean, A.padding, nl);
+        fprintf(stderr, "[mk] layout: %d x %d nnz %lld mean %.1f SELL stored/true %.2f long rows %d + %d\n", A.rows, A.cols, (long long)A.nnz, mean,
+                A.padding, nl, nh);
     A.sl_col.alloc((size_t)std::max(tot, 1));
     A.sl_val.alloc((size_t)std::max(tot, 1));
     k_sell_fill<T><<<wg, kThreads, 0, s>>>(rows, ns, A.ptr.p, A.col.p, A.val.p, A.sl_ptr.p, A.sl_col.p, A.sl_val.p);
@@ -282,25 +295,68 @@ __device__ __forceinline__ T long_row_sum(int b, int en, const int* __restrict__
     return block_sum_t((a0 + a1) + (a2 + a3), red);
 }
 
-// SELL-32 SpMV, one thread per row, one warp per slice, in CTAs [0, sell_blocks); the long rows (dense dofs, empty in the SELL part) are
-// served by the CTAs [sell_blocks, sell_blocks + n_long) of the SAME launch, one CTA per row -- no second kernel, no dependency.
+// one warp sums a medium row (lanes stride along it, four loads in flight)
+template <class T>
+__device__ __forceinline__ T warp_row_sum(int b, int en, const int* __restrict__ col, const T* __restrict__ val, const T* __restrict__ x, int lane) {
+    T a0 = ST<T>::zero(), a1 = ST<T>::zero(), a2 = ST<T>::zero(), a3 = ST<T>::zero();
+    int k = b + lane;
+    for (; k + 96 < en; k += 128) {
+        const int c0 = __ldg(col + k), c1 = __ldg(col + k + 32), c2 = __ldg(col + k + 64), c3 = __ldg(col + k + 96);
+        const T v0 = ld_ro(val + k), v1 = ld_ro(val + k + 32), v2 = ld_ro(val + k + 64), v3 = ld_ro(val + k + 96);
+        a0 = ST<T>::fma_(v0, ld_ro(x + c0), a0);
+        a1 = ST<T>::fma_(v1, ld_ro(x + c1), a1);
+        a2 = ST<T>::fma_(v2, ld_ro(x + c2), a2);
+        a3 = ST<T>::fma_(v3, ld_ro(x + c3), a3);
+    }
+    for (; k < en; k += 32) a0 = ST<T>::fma_(ld_ro(val + k), ld_ro(x + __ldg(col + k)), a0);
+    return group_sum<T>((a0 + a1) + (a2 + a3), 32);
+}
+
+// The rows that are not served by the bulk part of an SpMV launch, in the FIRST CTAs of the grid (they are the longest-running ones):
+// CTAs [0, n_huge): one huge row each; CTAs [n_huge, n_huge + ceil(n_long / 8)): one medium row per warp. Returns the dot contribution
+// of the calling thread; `extra` = number of such CTAs.
+template <class T, int MODE>
+__device__ __forceinline__ double extra_rows(int n_huge, const int* __restrict__ huge_rows, int n_long, const int* __restrict__ long_rows,
+                                             const int* __restrict__ ptr, const int* __restrict__ col, const T* __restrict__ val,
+                                             const SpmvEpi<T>& e, double* red) {
+    const T* __restrict__ x = e.v;
+    double dot = 0.0;
+    if ((int)blockIdx.x < n_huge) {
+        const int row = huge_rows[blockIdx.x];
+        const T acc = long_row_sum<T>(ptr[row], ptr[row + 1], col, val, x, red);
+        if (threadIdx.x == 0) dot = row_epilogue<T, MODE>(e, row, acc);
+    } else {
+        const int idx = ((int)blockIdx.x - n_huge) * (kThreads / 32) + (threadIdx.x >> 5);
+        if (idx < n_long) {
+            const int row = long_rows[idx];
+            const T acc = warp_row_sum<T>(ptr[row], ptr[row + 1], col, val, x, threadIdx.x & 31);
+            if ((threadIdx.x & 31) == 0) dot = row_epilogue<T, MODE>(e, row, acc);
+        }
+    }
+    return dot;
+}
+inline int extra_blocks(int n_huge, int n_long) { return n_huge + (n_long + kThreads / 32 - 1) / (kThreads / 32); }
+
+// SELL-32 SpMV: the CTAs after the `extra` ones run one thread per row, one warp per slice; rows longer than kLongRow are empty in the
+// slices and served by the extra CTAs of the SAME launch (extra_rows) -- no second kernel, no dependency, and no slice is serialised by
+// one wide row.
 template <class T, int MODE>
 __global__ void __launch_bounds__(kThreads, 6) k_spmv_sell(int n, int n_slices, const int* __restrict__ sl_ptr, const int* __restrict__ sl_col,
-                                                        const T* __restrict__ sl_val, const unsigned int* __restrict__ long_bits, int sell_blocks,
-                                                        const int* __restrict__ long_rows, const int* __restrict__ ptr, const int* __restrict__ col,
-                                                        const T* __restrict__ val, SpmvEpi<T> e, PcgState* st, ReduceWs ws) {
+                                                        const T* __restrict__ sl_val, const unsigned int* __restrict__ long_bits, int extra,
+                                                        int n_huge, const int* __restrict__ huge_rows, int n_long, const int* __restrict__ long_rows,
+                                                        const int* __restrict__ ptr, const int* __restrict__ col, const T* __restrict__ val,
+                                                        SpmvEpi<T> e, PcgState* st, ReduceWs ws) {
     __shared__ double red[32];
     if (st && st->done) return;
     const T* __restrict__ x = e.v;
     double dot = 0.0;
-    if ((int)blockIdx.x >= sell_blocks) {
-        const int row = long_rows[blockIdx.x - sell_blocks];
-        const T acc = long_row_sum<T>(ptr[row], ptr[row + 1], col, val, x, red);
-        if (threadIdx.x == 0) dot = row_epilogue<T, MODE>(e, row, acc);
+    if ((int)blockIdx.x < extra) {
+        dot = extra_rows<T, MODE>(n_huge, huge_rows, n_long, long_rows, ptr, col, val, e, red);
     } else {
         const int lane = threadIdx.x & 31;
+        const int sell_blocks = gridDim.x - extra;
         const int nwarps = (sell_blocks * blockDim.x) >> 5;
-        for (int sl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; sl < n_slices; sl += nwarps) {
+        for (int sl = (((int)blockIdx.x - extra) * blockDim.x + threadIdx.x) >> 5; sl < n_slices; sl += nwarps) {
             const int base = __ldg(sl_ptr + sl);
             const int w = (__ldg(sl_ptr + sl + 1) - base) >> 5;
             const int* cp = sl_col + base + lane;
@@ -325,24 +381,24 @@ __global__ void __launch_bounds__(kThreads, 6) k_spmv_sell(int n, int n_slices, 
 }
 
 // Lanes-per-row SpMV on the plain CSR arrays for operators with irregular row lengths (the coarse IGM levels): G lanes stride along
-// one row (no padding, coalesced within the row); rows longer than kRowModeLong are served by one CTA each, CTAs [row_blocks, ...).
+// one row (no padding, coalesced within the row); rows longer than kRowModeLong are served by the extra CTAs (extra_rows).
 template <class T, int MODE, int G>
 __global__ void __launch_bounds__(kThreads) k_spmv_rows(int n, const int* __restrict__ ptr, const int* __restrict__ col, const T* __restrict__ val,
-                                                        const unsigned int* __restrict__ long_bits, int row_blocks, const int* __restrict__ long_rows,
+                                                        const unsigned int* __restrict__ long_bits, int extra, int n_huge,
+                                                        const int* __restrict__ huge_rows, int n_long, const int* __restrict__ long_rows,
                                                         SpmvEpi<T> e, PcgState* st, ReduceWs ws) {
     __shared__ double red[32];
     if (st && st->done) return;
     const T* __restrict__ x = e.v;
     double dot = 0.0;
-    if ((int)blockIdx.x >= row_blocks) {
-        const int row = long_rows[blockIdx.x - row_blocks];
-        const T acc = long_row_sum<T>(ptr[row], ptr[row + 1], col, val, x, red);
-        if (threadIdx.x == 0) dot = row_epilogue<T, MODE>(e, row, acc);
+    if ((int)blockIdx.x < extra) {
+        dot = extra_rows<T, MODE>(n_huge, huge_rows, n_long, long_rows, ptr, col, val, e, red);
     } else {
         const int sub = threadIdx.x & (G - 1);
+        const int row_blocks = gridDim.x - extra;
         const int ngroups = (row_blocks * blockDim.x) / G;
         const int nloop = (n + ngroups - 1) / ngroups;  // same trip count for every thread: the shuffles below need whole warps
-        int row = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+        int row = (((int)blockIdx.x - extra) * blockDim.x + threadIdx.x) / G;
         for (int it = 0; it < nloop; it++, row += ngroups) {
             const bool live = row < n && !(long_bits != nullptr && ((__ldg(long_bits + (row >> 5)) >> (row & 31)) & 1u));
             T acc = ST<T>::zero();
@@ -370,10 +426,11 @@ __global__ void __launch_bounds__(kThreads) k_spmv_rows(int n, const int* __rest
 
 template <class T, int MODE, int G>
 inline void spmv_rows_launch(const DeviceCsr<T>& A, const SpmvEpi<T>& e, PcgState* st, ReduceWs ws, cudaStream_t s) {
+    const int extra = extra_blocks(A.n_huge, A.n_long);
     int row_blocks = stream_grid((int64_t)A.rows * G, kThreads, 16);
-    if (row_blocks + A.n_long > kMaxPartials) row_blocks = std::max(1, kMaxPartials - A.n_long);
-    k_spmv_rows<T, MODE, G><<<row_blocks + A.n_long, kThreads, 0, s>>>(A.rows, A.ptr.p, A.col.p, A.val.p, A.n_long ? A.long_bits.p : nullptr, row_blocks,
-                                                                       A.long_rows.p, e, st, ws);
+    if (MODE == kDot && row_blocks + extra > kMaxPartials) row_blocks = std::max(1, kMaxPartials - extra);
+    k_spmv_rows<T, MODE, G><<<row_blocks + extra, kThreads, 0, s>>>(A.rows, A.ptr.p, A.col.p, A.val.p, extra ? A.long_bits.p : nullptr, extra, A.n_huge,
+                                                                    A.huge_rows.p, A.n_long, A.long_rows.p, e, st, ws);
 }
 
 template <class T, int MODE>
@@ -386,13 +443,25 @@ inline void spmv_launch(const DeviceCsr<T>& A, const SpmvEpi<T>& e, PcgState* st
             default: spmv_rows_launch<T, MODE, 32>(A, e, st, ws, s); break;
         }
     } else {
+        const int extra = extra_blocks(A.n_huge, A.n_long);
         int sell_blocks = stream_grid((int64_t)A.n_slices * 32, kThreads, 16);
-        if (sell_blocks + A.n_long > kMaxPartials) sell_blocks = std::max(1, kMaxPartials - A.n_long);
-        k_spmv_sell<T, MODE><<<sell_blocks + A.n_long, kThreads, 0, s>>>(A.rows, A.n_slices, A.sl_ptr.p, A.sl_col.p, A.sl_val.p,
-                                                                        A.n_long ? A.long_bits.p : nullptr, sell_blocks, A.long_rows.p, A.ptr.p,
-                                                                        A.col.p, A.val.p, e, st, ws);
+        if (MODE == kDot && sell_blocks + extra > kMaxPartials) sell_blocks = std::max(1, kMaxPartials - extra);
+        k_spmv_sell<T, MODE><<<sell_blocks + extra, kThreads, 0, s>>>(A.rows, A.n_slices, A.sl_ptr.p, A.sl_col.p, A.sl_val.p,
+                                                                     extra ? A.long_bits.p : nullptr, extra, A.n_huge, A.huge_rows.p, A.n_long,
+                                                                     A.long_rows.p, A.ptr.p, A.col.p, A.val.p, e, st, ws);
     }
     MK_CHECK_LAUNCH();
+}
+
+// pq = <x, y>, alpha = rho / pq as a kernel of its own: only for operators with so many long rows that the fused-dot launch would
+// need more CTAs than the reduction workspace holds partials for
+template <class T>
+__global__ void __launch_bounds__(kThreads) k_dot_alpha(int n, const T* __restrict__ x, const T* __restrict__ y, PcgState* st, ReduceWs ws) {
+    __shared__ double red[32];
+    if (st->done) return;
+    double acc = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) acc += ST<T>::hdot(ld_ro(x + i), ld_ro(y + i));
+    finish_dot<kDot>(acc, st, ws, red);
 }
 
 // y (+)= A x (+ shift x); st != nullptr: skipped once st->done is set; dot: fused <x, y> reduction (needs st)
@@ -400,6 +469,12 @@ template <class T>
 inline void spmv(const DeviceCsr<T>& A, const T* x, T* y, double shift, bool accumulate, bool dot, PcgState* st, ReduceWs ws, cudaStream_t s) {
     SpmvEpi<T> e{};
     e.v = x; e.shift = shift; e.y = y;
+    if (dot && st && extra_blocks(A.n_huge, A.n_long) > kMaxPartials / 2) {
+        spmv_launch<T, kPlain>(A, e, st, ws, s);
+        k_dot_alpha<T><<<stream_grid(A.rows), kThreads, 0, s>>>(A.rows, x, y, st, ws);
+        MK_CHECK_LAUNCH();
+        return;
+    }
     if (dot && st) spmv_launch<T, kDot>(A, e, st, ws, s);
     else if (accumulate) spmv_launch<T, kAcc>(A, e, st, ws, s);
     else spmv_launch<T, kPlain>(A, e, st, ws, s);
