@@ -28,6 +28,8 @@ namespace mk {
 template <class T> struct HostScalar;
 template <> struct HostScalar<double> { using type = double; };
 template <> struct HostScalar<cdouble> { using type = std::complex<double>; };
+template <> struct HostScalar<float> { using type = float; };
+template <> struct HostScalar<cfloat> { using type = std::complex<float>; };
 
 struct AmgParams {
     double theta = 0.0;        // strength threshold (0: every off-diagonal is strong)
@@ -477,6 +479,14 @@ struct AmgLevelDev {
     double lmax = 2.0;
 };
 
+// Hands the coarse part of a V-cycle to another solver (the fp64 tail of the mixed-precision cycle)
+template <class T>
+struct CoarseHandoff {
+    virtual ~CoarseHandoff() = default;
+    virtual void solve(const T* b, T* x, const PcgState* st, cudaStream_t s) = 0;  // x = V(b) on level `handoff_level`
+    virtual int launches() const = 0;
+};
+
 template <class T>
 struct AmgPrecond : Precond<T> {
     using S = typename HostScalar<T>::type;
@@ -488,6 +498,8 @@ struct AmgPrecond : Precond<T> {
     bool coarse_dense = false;
     double op_complexity = 0, grid_complexity = 0;
     ReduceWs dummy_ws{nullptr, nullptr};
+    CoarseHandoff<T>* handoff = nullptr;  // levels >= handoff_level are solved by it (lv[handoff_level] only holds x and b)
+    int handoff_level = -1;
 
     void apply_A(int l, const T* x, T* y, const PcgState* st, cudaStream_t s) {
         if (l == 0 && fine_op) fine_op->apply(x, y, const_cast<PcgState*>(st), dummy_ws, s, false);
@@ -551,7 +563,8 @@ struct AmgPrecond : Precond<T> {
         smooth(l, b, x, true, st, s);  // leaves r = b - A x in L.r
         AmgLevelDev<T>& C = lv[l + 1];
         spmv_plain(L.R, L.r.p, C.b.p, false, st, s);
-        vcycle(l + 1, C.b.p, C.x.p, st, s);
+        if (handoff && l + 1 == handoff_level) handoff->solve(C.b.p, C.x.p, st, s);
+        else vcycle(l + 1, C.b.p, C.x.p, st, s);
         spmv_plain(L.P, C.x.p, x, true, st, s);
         smooth(l, b, x, false, st, s);
     }
@@ -561,9 +574,162 @@ struct AmgPrecond : Precond<T> {
     int launches_per_apply() const override {
         const int nl = (int)lv.size();
         const int per = 4 + 2 * prm.cheb_degree;  // fused smoothing: init, degree, restrict, prolong, resid, degree
+        if (handoff) return handoff_level * per + handoff->launches();
         return (nl - 1) * per + (coarse_dense ? 1 : 17);
     }
+    int launches_from_level(int l0) const {
+        const int per = 4 + 2 * prm.cheb_degree;
+        return ((int)lv.size() - 1 - l0) * per + (coarse_dense ? 1 : 17);
+    }
 };
+
+// ---- mixed precision: the V-cycle in fp32 storage and arithmetic, wrapped as a preconditioner of the fp64 PCG ----
+// The V-cycle is the bandwidth of an iteration (its operators and work vectors are ~80 % of the bytes moved), while PCG only needs
+// z ~ M^{-1} r to a few digits: halving its bytes costs nothing in the final accuracy (residuals, dots and updates stay fp64; the true
+// residual is re-checked at exit as before). r is scaled to unit 2-norm on the way down (its norm falls by 1e-10 over a solve).
+template <class T, class Tlo>
+static __global__ void __launch_bounds__(kThreads) k_precond_in(int n, const T* __restrict__ r, Tlo* __restrict__ b, const PcgState* st) {
+    if (st->done) return;
+    const double s = st->rr > 0.0 ? rsqrt(st->rr) : 1.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) st_rw(b + i, to_low<Tlo, T>(ld_ro(r + i), s));
+}
+template <class T, class Tlo>
+static __global__ void __launch_bounds__(kThreads) k_precond_out(int n, const Tlo* __restrict__ x, T* __restrict__ z, const PcgState* st) {
+    if (st->done) return;
+    const double s = st->rr > 0.0 ? sqrt(st->rr) : 1.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) st_rw(z + i, to_high<T, Tlo>(ld_ro(x + i), s));
+}
+
+template <class T, class Tlo>
+static __global__ void k_widen_vector(int n, const Tlo* __restrict__ in, T* __restrict__ out, const PcgState* st) {
+    if (st && st->done) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) st_rw(out + i, to_high<T, Tlo>(ld_ro(in + i), 1.0));
+}
+template <class T, class Tlo>
+static __global__ void k_narrow_vector_st(int n, const T* __restrict__ in, Tlo* __restrict__ out, const PcgState* st) {
+    if (st && st->done) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) st_rw(out + i, to_low<Tlo, T>(ld_ro(in + i), 1.0));
+}
+
+// Optional fp64 tail: levels >= kMixedHandoffLevel of the mixed cycle run in fp64 (they are a few percent of the bytes and carry the low
+// modes). Measured at 1M vertices it does NOT pay: the IGM operator needs 1,378 inner iterations with an fp64 cycle and 1,559 with an
+// all-fp32 one, and still 1,555 with the tail from level 2 -- the loss comes from the fine levels (the 1e-4 shift against row sums that
+// cancel to ~1e-6 of the diagonal in fp32), not from the coarse solve -- while the conversions cost 4 % of the step. Hence disabled
+// (hand-off level beyond any hierarchy depth); the fp32 cycle is still the faster one overall (field solve -23 %, IGM solve -3 %).
+constexpr int kMixedHandoffLevel = 99;
+template <class T>
+struct Fp64Tail : CoarseHandoff<typename LowOf<T>::type> {
+    using Tlo = typename LowOf<T>::type;
+    AmgPrecond<T>* hi = nullptr;
+    int level = 0, n = 0;
+    DevBuf<T> b, x;
+    void solve(const Tlo* b_lo, Tlo* x_lo, const PcgState* st, cudaStream_t s) override {
+        const int grid = stream_grid(n);
+        k_widen_vector<T, Tlo><<<grid, kThreads, 0, s>>>(n, b_lo, b.p, st);
+        hi->vcycle(level, b.p, x.p, st, s);
+        k_narrow_vector_st<T, Tlo><<<grid, kThreads, 0, s>>>(n, x.p, x_lo, st);
+        MK_CHECK_LAUNCH();
+    }
+    int launches() const override { return 2 + hi->launches_from_level(level); }
+};
+
+template <class T>
+struct MixedPrecond : Precond<T> {
+    using Tlo = typename LowOf<T>::type;
+    std::unique_ptr<AmgPrecond<T>> hi;    // fp64 hierarchy: only its levels >= the hand-off level are kept
+    Fp64Tail<T> tail;
+    std::unique_ptr<AmgPrecond<Tlo>> lo;
+    std::unique_ptr<LinOp<Tlo>> fine_lo;  // level-0 operator in fp32 storage (owned here)
+    DevBuf<Tlo> b_lo, z_lo;
+    int n = 0;
+    void apply(const T* r, T* z, const PcgState* st, cudaStream_t s) override {
+        const int grid = stream_grid(n);
+        k_precond_in<T, Tlo><<<grid, kThreads, 0, s>>>(n, r, b_lo.p, st);
+        lo->apply(b_lo.p, z_lo.p, st, s);
+        k_precond_out<T, Tlo><<<grid, kThreads, 0, s>>>(n, z_lo.p, z, st);
+        MK_CHECK_LAUNCH();
+    }
+    int launches_per_apply() const override { return lo->launches_per_apply() + 2; }
+};
+
+template <class T, class Tlo>
+static __global__ void k_narrow_vector(int n, const T* __restrict__ in, Tlo* __restrict__ out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) st_rw(out + i, to_low<Tlo, T>(ld_ro(in + i), 1.0));
+}
+
+// fp32 copy of the fine levels of a device hierarchy (operators converted, work vectors allocated in fp32); the coarse levels stay in
+// `hi`, which the result owns. fine_lo: the level-0 operator in fp32 (or null when level 0 of `hi` holds its own CSR operator).
+template <class T>
+inline std::unique_ptr<MixedPrecond<T>> lower_precision(cudaStream_t s, std::unique_ptr<AmgPrecond<T>> hi_in,
+                                                        std::unique_ptr<LinOp<typename LowOf<T>::type>> fine_lo) {
+    using Tlo = typename LowOf<T>::type;
+    auto mp = std::make_unique<MixedPrecond<T>>();
+    mp->hi = std::move(hi_in);
+    AmgPrecond<T>& hi = *mp->hi;
+    mp->lo = std::make_unique<AmgPrecond<Tlo>>();
+    AmgPrecond<Tlo>& lo = *mp->lo;
+    lo.prm = hi.prm;
+    mp->fine_lo = std::move(fine_lo);
+    lo.fine_op = mp->fine_lo.get();
+    lo.op_complexity = hi.op_complexity;
+    lo.grid_complexity = hi.grid_complexity;
+    const int nl = (int)hi.lv.size();
+    const int K = nl > kMixedHandoffLevel ? kMixedHandoffLevel : -1;  // -1: hierarchy too shallow, everything in fp32
+    const int n_lo = K > 0 ? K + 1 : nl;
+    lo.lv.resize(n_lo);
+    for (int l = 0; l < n_lo; l++) {
+        AmgLevelDev<T>& H = hi.lv[l];
+        AmgLevelDev<Tlo>& L = lo.lv[l];
+        const int n = H.n;
+        L.n = n;
+        L.lmax = H.lmax;
+        L.x.alloc(n); L.b.alloc(n);
+        if (K > 0 && l == K) break;  // the hand-off level only exchanges x and b
+        if (!(l == 0 && lo.fine_op)) lower_csr<T, Tlo>(H.A, L.A, s);
+        if (l + 1 < nl) {
+            lower_csr<T, Tlo>(H.P, L.P, s);
+            lower_csr<T, Tlo>(H.R, L.R, s);
+        }
+        L.dinv.alloc(n);
+        k_narrow_vector<T, Tlo><<<stream_grid(n), kThreads, 0, s>>>(n, H.dinv.p, L.dinv.p);
+        L.r.alloc(n); L.d.alloc(n); L.q.alloc(n);
+        MK_CHECK_LAUNCH();
+    }
+    if (K > 0) {
+        mp->tail.hi = mp->hi.get();
+        mp->tail.level = K;
+        mp->tail.n = hi.lv[K].n;
+        mp->tail.b.alloc(mp->tail.n);
+        mp->tail.x.alloc(mp->tail.n);
+        lo.handoff = &mp->tail;
+        lo.handoff_level = K;
+        MK_CUDA(cudaStreamSynchronize(s));
+        for (int l = 0; l < K; l++) hi.lv[l] = AmgLevelDev<T>();  // the fine fp64 levels are no longer needed
+        hi.lv[0].n = lo.lv[0].n;
+    } else {
+        lo.coarse_n = hi.coarse_n;
+        lo.coarse_dense = hi.coarse_dense;
+        if (hi.coarse_dense) {
+            const size_t m = hi.coarse_inv.n;
+            lo.coarse_inv.alloc(m);
+            k_narrow_vector<T, Tlo><<<stream_grid((int64_t)m), kThreads, 0, s>>>((int)m, hi.coarse_inv.p, lo.coarse_inv.p);
+            MK_CHECK_LAUNCH();
+        }
+        MK_CUDA(cudaStreamSynchronize(s));
+        mp->hi.reset();
+    }
+    mp->n = lo.lv[0].n;
+    mp->b_lo.alloc(mp->n);
+    mp->z_lo.alloc(mp->n);
+    MK_CUDA(cudaStreamSynchronize(s));
+    return mp;
+}
+
+// MK_PRECOND_FP32=0 keeps the V-cycle in fp64
+inline bool precond_fp32() {
+    const char* e = getenv("MK_PRECOND_FP32");
+    return !(e && std::strcmp(e, "0") == 0);
+}
 
 template <class T>
 inline void upload_host_csr(DeviceCsr<T>& D, const HostCsr<typename HostScalar<T>::type>& H, cudaStream_t s) {

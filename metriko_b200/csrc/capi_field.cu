@@ -22,7 +22,9 @@ struct mk_field {
     bool assembled = false;
     std::unique_ptr<FaceOp> op;
     std::unique_ptr<Pcg<cdouble>> pcg;
-    std::unique_ptr<AmgPrecond<cdouble>> amg;
+    std::unique_ptr<AmgPrecond<cdouble>> amg;       // fp64 hierarchy (MK_PRECOND_FP32=0, or the host mirror path)
+    std::unique_ptr<MixedPrecond<cdouble>> amg_lo;  // fp32 V-cycle (default)
+    Precond<cdouble>* precond() { return amg_lo ? (Precond<cdouble>*)amg_lo.get() : (Precond<cdouble>*)amg.get(); }
     DevBuf<cdouble> u, x, b;
     RecycleSpace rec;
     bool has_solution = false;
@@ -127,6 +129,7 @@ int mk_field_assemble(mk_field* f) {
     MK_CHECK_LAUNCH();
     f->assembled = true;
     f->amg.reset();
+    f->amg_lo.reset();
     f->op = std::make_unique<FaceOp>(&f->S);
     MK_API_END(f->ctx)
 }
@@ -210,7 +213,13 @@ static std::unique_ptr<AmgPrecond<cdouble>> build_face_amg(mk_field* f) {
 
 static void field_setup_solver(mk_field* f, const mk_solve_opts& o) {
     if (!f->pcg) f->pcg = std::make_unique<Pcg<cdouble>>(f->nF, f->ctx->c.stream);
-    if (o.precond == 1 && !f->amg) f->amg = build_face_amg(f);
+    if (o.precond == 1 && !f->amg && !f->amg_lo) {
+        f->amg = build_face_amg(f);
+        if (precond_fp32()) {
+            cudaStream_t s = f->ctx->c.stream;
+            f->amg_lo = lower_precision<cdouble>(s, std::move(f->amg), std::make_unique<FaceOpLo>(&f->S, s));
+        }
+    }
 }
 
 static int field_solve_impl(mk_field* f, const cdouble* u0_dev, int n_iter, const mk_solve_opts* opts, mk_stats* stats) {
@@ -224,7 +233,7 @@ static int field_solve_impl(mk_field* f, const cdouble* u0_dev, int n_iter, cons
     MK_CUDA(cudaMemcpyAsync(f->u.p, u0_dev, sizeof(cdouble) * f->nF, cudaMemcpyDeviceToDevice, s));
     MK_CUDA(cudaMemcpyAsync(f->x.p, u0_dev, sizeof(cdouble) * f->nF, cudaMemcpyDeviceToDevice, s));
     f->rec.init(f->nF, std::min(o.recycle, n_iter), s);
-    EigStats es = inverse_iteration(f->ctx->c, *f->op, o.precond == 1 ? f->amg.get() : nullptr, f->S.mass.p, f->nF, f->u.p, f->x.p,
+    EigStats es = inverse_iteration(f->ctx->c, *f->op, o.precond == 1 ? f->precond() : nullptr, f->S.mass.p, f->nF, f->u.p, f->x.p,
                                     f->b.p, *f->pcg, n_iter, o.tol, o.max_iter, o.use_graph != 0, &f->rec);
     MK_CUDA(cudaStreamSynchronize(s));
     auto t2 = std::chrono::steady_clock::now();
@@ -280,7 +289,7 @@ static int field_square_impl(mk_field* f, const mk_solve_opts* opts, mk_stats* s
     MK_CUDA(cudaStreamSynchronize(s));
     auto t1 = std::chrono::steady_clock::now();
     f->x.zero(s);
-    f->pcg->bind(f->op.get(), o.precond == 1 ? f->amg.get() : nullptr, nullptr);
+    f->pcg->bind(f->op.get(), o.precond == 1 ? f->precond() : nullptr, nullptr);
     SolveStats ss = f->pcg->solve(f->b.p, f->x.p, o.tol, o.max_iter, false, 16, o.use_graph != 0);
     MK_CUDA(cudaStreamSynchronize(s));
     auto t2 = std::chrono::steady_clock::now();

@@ -221,7 +221,10 @@ struct mk_igm {
     DeviceCsr<double> A0, dUFull;    // A0 = length^2 X2F^T X2F
     DevBuf<double> rhs0;             // length X2F^T F2
     std::unique_ptr<CsrOp<double>> opA0, opA;  // A0 and A0 + 1e-4 I
-    std::unique_ptr<AmgPrecond<double>> amg;   // hierarchy of A0 + 1e-4 I, used for both stages
+    std::unique_ptr<AmgPrecond<double>> amg;   // hierarchy of A0 + 1e-4 I, used for both stages (fp64: MK_PRECOND_FP32=0 / host mirror)
+    std::unique_ptr<MixedPrecond<double>> amg_lo;  // the same hierarchy as an fp32 V-cycle (default)
+    DeviceCsr<float> A0_lo;                        // A0 in fp32 storage: level 0 of that V-cycle (applied with the 1e-4 shift)
+    Precond<double>* precond() { return amg_lo ? (Precond<double>*)amg_lo.get() : (Precond<double>*)amg.get(); }
     std::unique_ptr<Pcg<double>> pcg;
     DevBuf<double> x, xprev, b, tmp;
     double setup_ms = 0;
@@ -339,6 +342,11 @@ static int igm_create_impl(mk_ctx* ctx, int rows, int cols, const int64_t* x2f_p
             if (g->o.precond == 1) {
                 g->amg = build_amg_device<double>(s, std::move(As), g->opA.get(), amg_params_from_env(true));
                 tm.lap("build_amg_device");
+                if (precond_fp32()) {
+                    lower_csr<double, float>(g->A0, g->A0_lo, s);
+                    g->amg_lo = lower_precision<double>(s, std::move(g->amg), std::make_unique<CsrOp<float>>(&g->A0_lo, 1e-4));
+                    tm.lap("fp32 copy of the hierarchy");
+                }
             }
         }
     }
@@ -520,7 +528,7 @@ struct IgmRun {
         }
     }
     SolveStats solve(CsrOp<double>* op) {
-        g->pcg->bind(op, g->amg.get(), &proj);
+        g->pcg->bind(op, g->precond(), &proj);
         SolveStats ss = g->pcg->solve(g->b.p, g->x.p, g->o.tol, g->o.max_iter, false, 16, g->o.use_graph != 0);
         st.outer_iterations++;
         st.inner_iterations += ss.iterations;

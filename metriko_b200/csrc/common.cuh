@@ -71,6 +71,41 @@ template <> struct ST<cdouble> {
     __host__ __device__ static cdouble cj(cdouble a) { return make_c(a.x, -a.y); }
 };
 
+// ---- fp32 storage types of the multigrid V-cycle (the preconditioner only: PCG, residuals and every result stay fp64) ----
+struct cfloat {
+    float x, y;
+};
+__host__ __device__ inline cfloat make_cf(float a, float b) { cfloat r; r.x = a; r.y = b; return r; }
+__host__ __device__ inline cfloat operator+(cfloat a, cfloat b) { return make_cf(a.x + b.x, a.y + b.y); }
+__host__ __device__ inline cfloat operator-(cfloat a, cfloat b) { return make_cf(a.x - b.x, a.y - b.y); }
+__host__ __device__ inline cfloat operator*(cfloat a, cfloat b) { return make_cf(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+template <> struct ST<float> {
+    __host__ __device__ static float zero() { return 0.0f; }
+    __host__ __device__ static double hdot(float a, float b) { return (double)a * (double)b; }
+    __host__ __device__ static double abs2(float a) { return (double)a * (double)a; }
+    __host__ __device__ static float fma_(float a, float b, float c) { return a * b + c; }
+    __host__ __device__ static float scale(double s, float a) { return (float)s * a; }
+    __host__ __device__ static float cj(float a) { return a; }
+};
+template <> struct ST<cfloat> {
+    __host__ __device__ static cfloat zero() { return make_cf(0.0f, 0.0f); }
+    __host__ __device__ static double hdot(cfloat a, cfloat b) { return (double)a.x * b.x + (double)a.y * b.y; }
+    __host__ __device__ static double abs2(cfloat a) { return (double)a.x * a.x + (double)a.y * a.y; }
+    __host__ __device__ static cfloat fma_(cfloat a, cfloat b, cfloat c) { return make_cf(c.x + a.x * b.x - a.y * b.y, c.y + a.x * b.y + a.y * b.x); }
+    __host__ __device__ static cfloat scale(double s, cfloat a) { return make_cf((float)s * a.x, (float)s * a.y); }
+    __host__ __device__ static cfloat cj(cfloat a) { return make_cf(a.x, -a.y); }
+};
+// narrowing / widening between the fp64 solver types and their fp32 storage types, with a real scale factor
+template <class Tlo, class T> __device__ __forceinline__ Tlo to_low(T v, double s);
+template <> __device__ __forceinline__ float to_low<float, double>(double v, double s) { return (float)(v * s); }
+template <> __device__ __forceinline__ cfloat to_low<cfloat, cdouble>(cdouble v, double s) { return make_cf((float)(v.x * s), (float)(v.y * s)); }
+template <class T, class Tlo> __device__ __forceinline__ T to_high(Tlo v, double s);
+template <> __device__ __forceinline__ double to_high<double, float>(float v, double s) { return (double)v * s; }
+template <> __device__ __forceinline__ cdouble to_high<cdouble, cfloat>(cfloat v, double s) { return make_c((double)v.x * s, (double)v.y * s); }
+template <class T> struct LowOf;
+template <> struct LowOf<double> { using type = float; };
+template <> struct LowOf<cdouble> { using type = cfloat; };
+
 // 16-byte vector load/store of a cdouble (LDG.E.128 / STG.E.128)
 __device__ __forceinline__ cdouble ldc(const cdouble* p) {
     double2 v = *reinterpret_cast<const double2*>(p);
@@ -91,6 +126,12 @@ template <> __device__ __forceinline__ cdouble ld_rw<cdouble>(const cdouble* p) 
 template <class T> __device__ __forceinline__ void st_rw(T* p, T v);
 template <> __device__ __forceinline__ void st_rw<double>(double* p, double v) { *p = v; }
 template <> __device__ __forceinline__ void st_rw<cdouble>(cdouble* p, cdouble v) { stc(p, v); }
+template <> __device__ __forceinline__ float ld_ro<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ cfloat ld_ro<cfloat>(const cfloat* p) { const float2 v = __ldg(reinterpret_cast<const float2*>(p)); return make_cf(v.x, v.y); }
+template <> __device__ __forceinline__ float ld_rw<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ cfloat ld_rw<cfloat>(const cfloat* p) { const float2 v = *reinterpret_cast<const float2*>(p); return make_cf(v.x, v.y); }
+template <> __device__ __forceinline__ void st_rw<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void st_rw<cfloat>(cfloat* p, cfloat v) { *reinterpret_cast<float2*>(p) = make_float2(v.x, v.y); }
 
 // ---- deterministic block reduction: warp shuffles, then one smem pass ----
 __device__ __forceinline__ double warp_sum(double v) {

@@ -170,6 +170,27 @@ inline void build_sell(DeviceCsr<T>& A, cudaStream_t s) {
     MK_CHECK_LAUNCH();
 }
 
+// fp32-valued copy of an operator (same pattern) with its own SpMV layout: the V-cycle's storage format
+template <class T, class Tlo>
+static __global__ void k_narrow_values(int64_t n, const T* __restrict__ in, Tlo* __restrict__ out) {
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) st_rw(out + k, to_low<Tlo, T>(ld_ro(in + k), 1.0));
+}
+template <class T, class Tlo>
+inline void lower_csr(const DeviceCsr<T>& A, DeviceCsr<Tlo>& B, cudaStream_t s) {
+    B.rows = A.rows;
+    B.cols = A.cols;
+    B.nnz = A.nnz;
+    if (!A.ptr.p) return;  // operator not materialised (level 0 behind an external fine operator)
+    B.ptr.alloc((size_t)A.rows + 1);
+    B.col.alloc((size_t)std::max<int64_t>(A.nnz, 1));
+    B.val.alloc((size_t)std::max<int64_t>(A.nnz, 1));
+    MK_CUDA(cudaMemcpyAsync(B.ptr.p, A.ptr.p, sizeof(int) * ((size_t)A.rows + 1), cudaMemcpyDeviceToDevice, s));
+    MK_CUDA(cudaMemcpyAsync(B.col.p, A.col.p, sizeof(int) * (size_t)A.nnz, cudaMemcpyDeviceToDevice, s));
+    if (A.nnz) k_narrow_values<T, Tlo><<<stream_grid(A.nnz), kThreads, 0, s>>>(A.nnz, A.val.p, B.val.p);
+    MK_CHECK_LAUNCH();
+    build_sell(B, s);
+}
+
 // plain CSR arrays only (operands of the device set-up algebra, devcsr.cuh)
 template <class T>
 inline void upload_csr_plain(DeviceCsr<T>& A, int rows, int cols, const int* ptr, const int* col, const T* val, int64_t nnz, cudaStream_t s) {
@@ -207,11 +228,30 @@ __device__ __forceinline__ cdouble group_sum<cdouble>(cdouble v, int G) {
     return v;
 }
 
+template <>
+__device__ __forceinline__ float group_sum<float>(float v, int G) {
+    for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <>
+__device__ __forceinline__ cfloat group_sum<cfloat>(cfloat v, int G) {
+    for (int o = G >> 1; o > 0; o >>= 1) {
+        v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+        v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+    }
+    return v;
+}
+
 // sums a T over the CTA (result valid in thread 0)
 __device__ __forceinline__ double block_sum_t(double v, double* red) { return block_sum(v, red); }
 __device__ __forceinline__ cdouble block_sum_t(cdouble v, double* red) {
     const double re = block_sum(v.x, red), im = block_sum(v.y, red);
     return make_c(re, im);
+}
+__device__ __forceinline__ float block_sum_t(float v, double* red) { return (float)block_sum((double)v, red); }
+__device__ __forceinline__ cfloat block_sum_t(cfloat v, double* red) {
+    const double re = block_sum((double)v.x, red), im = block_sum((double)v.y, red);
+    return make_cf((float)re, (float)im);
 }
 
 // What happens to a finished row sum (A v)_row. One code path serves the three row shapes (SELL slice lane, long row, warp-per-row):

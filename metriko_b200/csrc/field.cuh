@@ -162,6 +162,77 @@ struct FaceOp : LinOp<cdouble> {
     }
 };
 
+// ---- the face stencil in fp32 storage: level 0 of the mixed-precision V-cycle (amg.cuh MixedPrecond). 36 B/face of operator
+// (24 values + 12 indices) against 60 B/face in fp64; the vectors are complex fp32 too. MODE 0: y = L v; 1 / 2: fused Chebyshev step /
+// residual exactly as k_spmv_face_cheb. ----
+template <int MODE>
+static __global__ void __launch_bounds__(kThreads) k_spmv_face_lo(int nF, float diag, const int* __restrict__ nbr, const cfloat* __restrict__ val,
+                                                           const cfloat* __restrict__ v, const cfloat* __restrict__ b, const cfloat* __restrict__ dinv,
+                                                           cfloat* __restrict__ r, cfloat* __restrict__ x, cfloat* __restrict__ out, float c1, float c2,
+                                                           int first, const PcgState* st) {
+    if (st && st->done) return;
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nF; f += gridDim.x * blockDim.x) {
+        const int n0 = __ldg(nbr + f), n1 = __ldg(nbr + (size_t)nF + f), n2 = __ldg(nbr + 2 * (size_t)nF + f);
+        const cfloat v0 = ld_ro(val + f), v1 = ld_ro(val + (size_t)nF + f), v2 = ld_ro(val + 2 * (size_t)nF + f);
+        const cfloat vf = ld_ro(v + f);
+        const cfloat x0 = ld_ro(v + n0), x1 = ld_ro(v + n1), x2 = ld_ro(v + n2);
+        cfloat acc = make_cf(diag * vf.x, diag * vf.y);
+        acc = ST<cfloat>::fma_(v0, x0, acc);
+        acc = ST<cfloat>::fma_(v1, x1, acc);
+        acc = ST<cfloat>::fma_(v2, x2, acc);
+        if (MODE == 0) {
+            st_rw(out + f, acc);
+        } else if (MODE == 1) {
+            const cfloat xi = first ? vf : ld_rw(x + f) + vf;
+            const cfloat ri = ld_rw(r + f) - acc;
+            const cfloat t = ld_ro(dinv + f) * ri;
+            st_rw(x + f, xi);
+            st_rw(r + f, ri);
+            st_rw(out + f, make_cf(c1 * vf.x + c2 * t.x, c1 * vf.y + c2 * t.y));
+        } else {
+            const cfloat ri = ld_ro(b + f) - acc;
+            const cfloat t = ld_ro(dinv + f) * ri;
+            st_rw(r + f, ri);
+            st_rw(out + f, make_cf(c1 * t.x, c1 * t.y));
+        }
+    }
+}
+
+static __global__ void __launch_bounds__(kThreads) k_narrow_stencil(size_t n, const cdouble* __restrict__ in, cfloat* __restrict__ out) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const cdouble v = ldc_nc(in + i);
+        st_rw(out + i, make_cf((float)v.x, (float)v.y));
+    }
+}
+
+struct FaceOpLo : LinOp<cfloat> {
+    const FaceStencil* S;  // shares the neighbour indices
+    DevBuf<cfloat> val;
+    FaceOpLo(const FaceStencil* S_, cudaStream_t s) : S(S_) {
+        n = S_->nF;
+        val.alloc((size_t)3 * n);
+        k_narrow_stencil<<<stream_grid((int64_t)3 * n), kThreads, 0, s>>>((size_t)3 * n, S->val.p, val.p);
+        MK_CHECK_LAUNCH();
+    }
+    int grid() const { return stream_grid(S->nF, kThreads, 8); }
+    void apply(const cfloat* x, cfloat* y, PcgState* st, ReduceWs, cudaStream_t s, bool = true) override {
+        k_spmv_face_lo<0><<<grid(), kThreads, 0, s>>>(S->nF, (float)S->diag, S->nbr.p, val.p, x, nullptr, nullptr, nullptr, nullptr, y, 0.f, 0.f, 0, st);
+        MK_CHECK_LAUNCH();
+    }
+    bool cheb_step(const cfloat* d_in, cfloat* d_out, cfloat* r, cfloat* x, const cfloat* dinv, double c1, double c2, int first, const PcgState* st,
+                   cudaStream_t s) override {
+        k_spmv_face_lo<1><<<grid(), kThreads, 0, s>>>(S->nF, (float)S->diag, S->nbr.p, val.p, d_in, nullptr, dinv, r, x, d_out, (float)c1, (float)c2, first, st);
+        MK_CHECK_LAUNCH();
+        return true;
+    }
+    bool cheb_resid(const cfloat* x, const cfloat* b, cfloat* r, cfloat* d_out, const cfloat* dinv, double inv_theta, const PcgState* st,
+                    cudaStream_t s) override {
+        k_spmv_face_lo<2><<<grid(), kThreads, 0, s>>>(S->nF, (float)S->diag, S->nbr.p, val.p, x, b, dinv, r, nullptr, d_out, (float)inv_theta, 0.f, 0, st);
+        MK_CHECK_LAUNCH();
+        return true;
+    }
+};
+
 // ---- inverse iteration helper kernels (sls.h:44-51) ----
 
 // b = m .* u ; aux0 = <u, b> = u^H M u
