@@ -41,6 +41,7 @@ struct AmgParams {
     int dense_row = 64;        // fine-level rows longer than this are "dense dofs": never aggregated with others, carried
                                // as singletons to the coarsest level (solved exactly there), l1-scaled in the smoother
     int agg = 1;               // 0 = sequential greedy (Vanek), 1 = MIS(2) roots (parallel; what the device set-up runs)
+    int inject_dense = 1;      // prolongator rows of dense dofs are not smoothed (injection from their singleton aggregate)
 };
 
 // real_op: the real symmetric IGM / LM operators use a strength threshold (drops weak and wrong-signed cotan couplings
@@ -55,6 +56,7 @@ inline AmgParams amg_params_from_env(bool real_op = false) {
     if (const char* e = getenv("MK_AMG_OMEGA")) p.omega_scale = atof(e);
     if (const char* e = getenv("MK_AMG_DENSE")) p.dense_row = atoi(e);
     if (const char* e = getenv("MK_AMG_AGG")) p.agg = atoi(e);
+    if (const char* e = getenv("MK_AMG_INJECT")) p.inject_dense = atoi(e);
     return p;
 }
 
@@ -361,6 +363,14 @@ inline std::vector<AmgHostLevel<S>> build_hierarchy(HostCsr<S> A, std::vector<S>
             P.val.reserve(AT.col.size() + n);
             for (int i = 0; i < n; i++) {
                 bool placed = false;
+                if (n_dense && dense[i] && prm.inject_dense) {
+                    // dense dofs are interpolated by injection from their own singleton aggregate: smoothing their row would spread
+                    // them over every neighbouring aggregate and couple all of those pairwise in the Galerkin product (a clique per seam)
+                    P.col.push_back(T.col[i]);
+                    P.val.push_back(T.val[i]);
+                    P.ptr[i + 1] = (int)P.col.size();
+                    continue;
+                }
                 for (int k = AT.ptr[i]; k < AT.ptr[i + 1]; k++) {
                     int c = AT.col[k];
                     S v = S(-omega) * L.dinv[i] * AT.val[k];

@@ -199,18 +199,34 @@ static __global__ void k_build_tentative(int n, const int* __restrict__ agg, con
     st_rw(tval + i, ST<T>::scale(1.0 / nrm, t));
 }
 
-// S = I - omega D^{-1} A on the pattern of A
+// S = I - omega D^{-1} A on the pattern of A -- except the rows of dense dofs, which are the identity (one entry): dense dofs are
+// interpolated by injection from their own singleton aggregate. Smoothing their row would spread them over every neighbouring aggregate
+// and couple all of those pairwise in the Galerkin product (a clique per seam: 35 instead of 13 entries per row on level 1 of the IGM
+// operator, 89 instead of 23 on level 2, at unchanged iteration counts).
+static __global__ void k_smoother_lengths(int n, const int* __restrict__ ptr, const char* __restrict__ dense, int* __restrict__ len) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) len[i] = (dense && dense[i]) ? 1 : ptr[i + 1] - ptr[i];
+}
 template <class T>
 static __global__ void k_smoother_matrix(int n, const int* __restrict__ ptr, const int* __restrict__ col, const T* __restrict__ val, const T* __restrict__ dinv,
-                                         double omega, T* __restrict__ sval) {
+                                         double omega, const char* __restrict__ dense, const int* __restrict__ sptr, int* __restrict__ scol,
+                                         T* __restrict__ sval) {
     const int lane = threadIdx.x & 31;
     const int nw = (gridDim.x * blockDim.x) >> 5;
     for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += nw) {
+        const int s0 = sptr[i];
+        if (dense && dense[i]) {
+            if (lane == 0) { scol[s0] = i; st_rw(sval + s0, dev_one<T>()); }
+            continue;
+        }
         const T d = ST<T>::scale(-omega, ld_ro(dinv + i));
-        for (int k = ptr[i] + lane; k < ptr[i + 1]; k += 32) {
+        const int b = ptr[i];
+        for (int k = b + lane; k < ptr[i + 1]; k += 32) {
+            const int c = col[k];
             T v = d * ld_ro(val + k);
-            if (col[k] == i) v = v + dev_one<T>();
-            st_rw(sval + k, v);
+            if (c == i) v = v + dev_one<T>();
+            scol[s0 + k - b] = c;
+            st_rw(sval + s0 + k - b, v);
         }
     }
 }
@@ -388,8 +404,20 @@ inline std::unique_ptr<AmgPrecond<T>> build_amg_device(cudaStream_t s, DeviceCsr
         const double omega = prm.omega_scale / rho;
         {
             DeviceCsr<T> Sm;
-            copy_csr(A, Sm, s);
-            k_smoother_matrix<T><<<stream_grid((int64_t)n * 32), kThreads, 0, s>>>(n, A.ptr.p, A.col.p, A.val.p, L.dinv.p, omega, Sm.val.p);
+            const char* inj = (n_dense && prm.inject_dense) ? dense.p : nullptr;
+            Sm.rows = Sm.cols = n;
+            Sm.ptr.alloc((size_t)n + 1);
+            {
+                DevBuf<int> len((size_t)n + 1);
+                len.zero(s);
+                k_smoother_lengths<<<(n + 255) / 256, 256, 0, s>>>(n, A.ptr.p, inj, len.p);
+                dev_exclusive_scan(len.p, Sm.ptr.p, n, s);
+                Sm.nnz = dev_read_int(Sm.ptr.p + n, s);
+            }
+            Sm.col.alloc((size_t)std::max<int64_t>(Sm.nnz, 1));
+            Sm.val.alloc((size_t)std::max<int64_t>(Sm.nnz, 1));
+            k_smoother_matrix<T><<<stream_grid((int64_t)n * 32), kThreads, 0, s>>>(n, A.ptr.p, A.col.p, A.val.p, L.dinv.p, omega, inj, Sm.ptr.p, Sm.col.p,
+                                                                                  Sm.val.p);
             MK_CHECK_LAUNCH();
             spgemm<T>(Sm, Tm, L.P, s);
         }
