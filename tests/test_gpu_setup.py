@@ -144,3 +144,51 @@ def test_host_and_device_setup_give_the_same_rounding(ctx):
     # same integers; the ORDER may differ among dofs that are already integral to round-off (selection ties, flagged by the API)
     assert dict(zip(map(int, a["fixedIdcs"]), map(int, a["fixedVals"]))) == dict(zip(map(int, b["fixedIdcs"]), map(int, b["fixedVals"])))
     assert np.abs(a["fullx"] - b["fullx"]).max() < 1e-7
+
+
+def test_device_resident_inputs_and_precisions_give_the_same_rounding(ctx):
+    """mk_igm_create_dev (X2F / F2 already in HBM: the `value` path of bench.py) against the host-buffer entry point, and the fp32
+    V-cycle (default) against the fp64 one (MK_PRECOND_FP32=0): identical integers, fullx within the post_checking tolerance."""
+    import torch
+    g = load_golden("sphere_octa4_roundseams")
+    X = sp.csr_matrix(g["X2F"], dtype=np.float64)
+    X.sort_indices()
+    U = sp.csr_matrix(g["UFull"], dtype=np.float64)
+    U.sort_indices()
+    raw = (X.indptr.astype(np.int64), X.indices.astype(np.int32), X.data.astype(np.float64),
+           U.indptr.astype(np.int64), U.indices.astype(np.int32), U.data.astype(np.float64), np.ascontiguousarray(g["F2"], np.float64))
+    dev_t = [torch.from_numpy(a).cuda() for a in (raw[0], raw[1], raw[2], raw[6])]
+    outs = {}
+    for name, kw, env in (("host", {}, None), ("dev", {"dev": tuple(int(t.data_ptr()) for t in dev_t)}, None), ("fp64", {}, "0")):
+        if env is not None:
+            os.environ["MK_PRECOND_FP32"] = env
+        try:
+            prob = api.IgmProblem(ctx, X, U, g["F2"], float(g["length"]), raw=raw, **kw)
+            outs[name] = prob.round(g["fixedIdcs"], g["fixedVals"], g["singularIdcs"], g["integerIdcs"], True, bool(g["round_seams"]))
+            assert prob.stats["relres_max"] <= 1.001e-10
+            prob.close()
+        finally:
+            os.environ.pop("MK_PRECOND_FP32", None)
+    ref = dict(zip(g["out_fixedIdcs"].tolist(), g["out_fixedVals"].tolist()))
+    for name, o in outs.items():
+        assert o["success"], name
+        assert dict(zip(map(int, o["fixedIdcs"]), map(int, o["fixedVals"]))) == ref, name
+        assert np.abs(o["fullx"] - g["fullx"]).max() < 1e-6, name
+
+
+def test_field_fp32_and_fp64_cycles_agree(ctx, ico4):
+    fi = ico4.field_inputs()
+    nF = ico4.dims["nF"]
+    u0 = oracle.random_u0(nF, 0)
+    z = {}
+    for mode in ("1", "0"):
+        os.environ["MK_PRECOND_FP32"] = mode
+        try:
+            F = api.FaceRosyField(ctx, fi["face2half"], fi["next"], fi["twin"], fi["face"], fi["heArgOnFace"], fi["faceArea"], 4)
+            z[mode] = F.solveSmallestEig(u0, 50)
+            assert F.stats["relres_max"] <= 1.001e-10 and F.stats["status"] == 0
+            F.close()
+        finally:
+            os.environ.pop("MK_PRECOND_FP32", None)
+    from oracle.field import field_angle_error
+    assert field_angle_error(z["1"], z["0"], 4).max() < 1e-7
