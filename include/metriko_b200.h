@@ -91,6 +91,14 @@ int mk_field_solve_curvature_aligned(mk_field* f, const double* heLen, const dou
                                      mk_stats* stats);
 /* solveSquare(lhs, rhs) (sls.h:16-27) for lhs = the assembled L (lambda = 0, frf.h:27): one Hermitian solve, host vectors. */
 int mk_field_solve_square(mk_field* f, const double* rhs, const mk_solve_opts* opts, double* x, mk_stats* stats);
+/* computeMatching + computeSingular (frf.h:100-202) on the last solution, which stays on the device: per edge the connection
+ * (frf.h:109-117), the matching (matching_type 1 = Curl frf.h:169-202, 0 = Principal frf.h:138-167) and the effort; per vertex the
+ * singularity index (frf.h:100-107). Inputs are the Hmesh flat arrays (hmesh/hmesh.h:98-146): pos[3 nV], tail / head / edge / prev [nH],
+ * edge2face[2 nE], faceBasisX / faceBasisY [3 nF], vert2half[nV], angleDefect[nV]; closed meshes (half 2e is the canonical half of edge e,
+ * hmesh.h:378). Outputs (host): matching[nE], effort[nE], singular[nV]. */
+int mk_field_matching(mk_field* f, int nV, int nE, int matching_type, const double* pos, const int* tail, const int* head, const int* edge2face,
+                      const double* faceBasisX, const double* faceBasisY, const int* edge, const int* prev, const int* vert2half,
+                      const double* angleDefect, int* matching, double* effort, int* singular);
 /* Field decode (frf.h:37-43): field[nF x N] complex interleaved from the last solution. Host output. */
 int mk_field_decode(mk_field* f, double* field);
 /* y = L x on host vectors (tests) and a timed device loop for the roofline (reps launches, returns ms per launch). */

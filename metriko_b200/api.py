@@ -69,6 +69,18 @@ class FaceRosyField:
         self.ctx.check(rc)
         return (x, rhs) if return_rhs else x
 
+    def computeMatching(self, mesh: dict, matching: str = "curl"):
+        """computeMatching(Curl | Principal) + computeSingular (frf.h:100-202) on the device, from the last solution. `mesh`: the Hmesh
+        flat arrays pos, tail, head, edge2face, faceBasisX, faceBasisY, edge, prev, vert2half, angleDefect. Returns (matching, effort, singular)."""
+        pos, bx, by = as_f64(mesh["pos"]).reshape(-1), as_f64(mesh["faceBasisX"]).reshape(-1), as_f64(mesh["faceBasisY"]).reshape(-1)
+        tail, head, edge, prev = (as_i32(mesh[k]) for k in ("tail", "head", "edge", "prev"))
+        e2f, v2h, dfc = as_i32(mesh["edge2face"]).reshape(-1), as_i32(mesh["vert2half"]), as_f64(mesh["angleDefect"])
+        nV, nE = len(v2h), len(e2f) // 2
+        m, eff, sing = np.empty(nE, np.int32), np.empty(nE, np.float64), np.empty(nV, np.int32)
+        self.ctx.check(self.ctx.L.mk_field_matching(self.h, nV, nE, 1 if matching == "curl" else 0, ptr(pos), ptr(tail), ptr(head), ptr(e2f), ptr(bx),
+                                                    ptr(by), ptr(edge), ptr(prev), ptr(v2h), ptr(dfc), ptr(m), ptr(eff), ptr(sing)))
+        return m, eff, sing
+
     def solveSquare(self, rhs, **opts):
         """solveSquare(L, rhs) (sls.h:16-27) on the assembled operator."""
         b = as_c128(rhs)

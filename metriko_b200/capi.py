@@ -72,6 +72,7 @@ def lib() -> C.CDLL:
         L.mk_field_solve.argtypes = [vp, vp, C.c_int, C.POINTER(SolveOpts), vp, C.POINTER(Stats)]
         L.mk_field_solve_dev.argtypes = [vp, vp, C.c_int, C.POINTER(SolveOpts), vp, C.POINTER(Stats)]
         L.mk_field_decode.argtypes = [vp, vp]
+        L.mk_field_matching.argtypes = [vp, C.c_int, C.c_int, C.c_int] + [vp] * 13
         L.mk_field_solve_curvature_aligned.argtypes = [vp, vp, vp, C.POINTER(SolveOpts), vp, vp, C.POINTER(Stats)]
         L.mk_field_solve_square.argtypes = [vp, vp, C.POINTER(SolveOpts), vp, C.POINTER(Stats)]
         L.mk_field_spmv.argtypes = [vp, vp, vp]

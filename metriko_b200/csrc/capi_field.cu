@@ -346,6 +346,32 @@ int mk_field_solve_curvature_aligned(mk_field* f, const double* heLen, const dou
     MK_API_END_RC(f->ctx, rc)
 }
 
+int mk_field_matching(mk_field* f, int nV, int nE, int matching_type, const double* pos, const int* tail, const int* head, const int* edge2face,
+                      const double* faceBasisX, const double* faceBasisY, const int* edge, const int* prev, const int* vert2half,
+                      const double* angleDefect, int* matching, double* effort, int* singular) {
+    if (!f || !f->has_solution || nV <= 0 || nE <= 0 || 2 * nE != f->nH || (matching_type != 0 && matching_type != 1) || !pos || !tail || !head ||
+        !edge2face || !faceBasisX || !faceBasisY || !edge || !prev || !vert2half || !angleDefect || !matching || !effort || !singular)
+        return MK_ERR_ARG;
+    MK_API_BEGIN(f->ctx)
+    MK_CUDA(cudaSetDevice(f->ctx->c.device));
+    cudaStream_t s = f->ctx->c.stream;
+    const int nH = f->nH, nF = f->nF;
+    DevBuf<double> d_pos((size_t)3 * nV), d_bx((size_t)3 * nF), d_by((size_t)3 * nF), d_def(nV), d_eff(nE);
+    DevBuf<int> d_tail(nH), d_head(nH), d_e2f((size_t)2 * nE), d_edge(nH), d_prev(nH), d_v2h(nV), d_match(nE), d_sing(nV);
+    d_pos.upload(pos, (size_t)3 * nV, s); d_bx.upload(faceBasisX, (size_t)3 * nF, s); d_by.upload(faceBasisY, (size_t)3 * nF, s);
+    d_def.upload(angleDefect, nV, s); d_tail.upload(tail, nH, s); d_head.upload(head, nH, s); d_e2f.upload(edge2face, (size_t)2 * nE, s);
+    d_edge.upload(edge, nH, s); d_prev.upload(prev, nH, s); d_v2h.upload(vert2half, nV, s);
+    k_edge_matching<<<stream_grid(nE), kThreads, 0, s>>>(nE, f->N, matching_type, f->x.p, d_pos.p, d_tail.p, d_head.p, d_e2f.p, d_bx.p, d_by.p, d_match.p,
+                                                         d_eff.p);
+    k_vertex_singular<<<stream_grid(nV), kThreads, 0, s>>>(nV, f->N, d_v2h.p, f->twin.p, d_prev.p, d_edge.p, d_def.p, d_eff.p, d_sing.p);
+    MK_CHECK_LAUNCH();
+    d_match.download(matching, nE, s);
+    d_eff.download(effort, nE, s);
+    d_sing.download(singular, nV, s);
+    MK_CUDA(cudaStreamSynchronize(s));
+    MK_API_END(f->ctx)
+}
+
 int mk_field_decode(mk_field* f, double* field) {
     if (!f || !f->has_solution || !field) return MK_ERR_ARG;
     MK_API_BEGIN(f->ctx)

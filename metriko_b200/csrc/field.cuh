@@ -365,6 +365,96 @@ static __global__ void __launch_bounds__(kThreads) k_scale_by_aux0(int n, cdoubl
     }
 }
 
+// ---- per-edge matching and per-vertex singularity index (frf.h:100-202): the elementwise steps between the eigen-solve and the
+// seam / cut bookkeeping, on the device so that the field does not have to leave it for them ----
+__device__ __forceinline__ cdouble field_dir(cdouble z, int N, int i) {  // frf.h:37-43
+    double s, c;
+    sincos(atan2(z.y, z.x) / (double)N + 2.0 * M_PI * (double)i / (double)N, &s, &c);
+    return make_c(c, s);
+}
+__device__ __forceinline__ cdouble cdiv(cdouble a, cdouble b) {
+    const double d = b.x * b.x + b.y * b.y;
+    return make_c((a.x * b.x + a.y * b.y) / d, (a.y * b.x - a.x * b.y) / d);
+}
+
+// One thread per edge: connection (frf.h:109-117), then curl matching (type 1, frf.h:169-202) or principal matching (type 0,
+// frf.h:138-167) and the effort. v = normalised vector of the canonical half 2e (hmesh.h:378).
+static __global__ void __launch_bounds__(kThreads) k_edge_matching(int nE, int N, int type, const cdouble* __restrict__ z, const double* __restrict__ pos,
+                                                            const int* __restrict__ tail, const int* __restrict__ head,
+                                                            const int* __restrict__ edge2face, const double* __restrict__ bx,
+                                                            const double* __restrict__ by, int* __restrict__ matching, double* __restrict__ effort) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nE; e += gridDim.x * blockDim.x) {
+        const int h = 2 * e, t = tail[h], hd = head[h];
+        double vx = pos[3 * hd] - pos[3 * t], vy = pos[3 * hd + 1] - pos[3 * t + 1], vz = pos[3 * hd + 2] - pos[3 * t + 2];
+        const double vn = sqrt(vx * vx + vy * vy + vz * vz);
+        vx /= vn; vy /= vn; vz /= vn;
+        const int f0 = edge2face[2 * e], f1 = edge2face[2 * e + 1];
+        const double x0[3] = {bx[3 * f0], bx[3 * f0 + 1], bx[3 * f0 + 2]}, y0[3] = {by[3 * f0], by[3 * f0 + 1], by[3 * f0 + 2]};
+        const double x1[3] = {bx[3 * f1], bx[3 * f1 + 1], bx[3 * f1 + 2]}, y1[3] = {by[3 * f1], by[3 * f1 + 1], by[3 * f1 + 2]};
+        const cdouble ef = make_c(vx * x0[0] + vy * x0[1] + vz * x0[2], vx * y0[0] + vy * y0[1] + vz * y0[2]);
+        const cdouble eg = make_c(vx * x1[0] + vy * x1[1] + vz * x1[2], vx * y1[0] + vy * y1[1] + vz * y1[2]);
+        const cdouble conn = cdiv(eg, ef);
+        const cdouble z0 = ldc_nc(z + f0), z1 = ldc_nc(z + f1);
+        if (type == 1) {
+            int iM = 0;
+            double mn = 32767000.;
+            for (int i = 0; i < N; i++) {
+                double curl = 0;
+                for (int j = 0; j < N; j++) {
+                    const cdouble c0 = field_dir(z0, N, j), c1 = field_dir(z1, N, (i + j) % N);
+                    // v . (X1 c1.re + Y1 c1.im - X0 c0.re - Y0 c0.im) = eg . c1 - ef . c0 as planar dot products
+                    const double d = (eg.x * c1.x + eg.y * c1.y) - (ef.x * c0.x + ef.y * c0.y);
+                    curl += d * d;
+                }
+                if (curl < mn) { iM = i; mn = curl; }
+            }
+            cdouble coef = make_c(1.0, 0.0);
+            for (int i = 0; i < N; i++) coef = coef * cdiv(field_dir(z1, N, (i + iM) % N), field_dir(z0, N, i) * conn);
+            matching[e] = iM;
+            effort[e] = atan2(coef.y, coef.x);
+        } else {
+            double minRot = 1000.;
+            int offset = 0;
+            cdouble coef = make_c(1.0, 0.0);
+            const cdouble transport0 = conn * field_dir(z0, N, 0);
+            for (int i = 0; i < N; i++) {
+                const cdouble jf = field_dir(z0, N, i), jg = field_dir(z1, N, i);
+                coef = coef * cdiv(jg, conn * jf);
+                const cdouble q = cdiv(jg, transport0);
+                const double r = atan2(q.y, q.x);
+                if (fabs(r) < fabs(minRot)) { offset = i; minRot = r; }
+            }
+            const double eff = atan2(coef.y, coef.x);
+            double residuals = 0;
+            for (int i = 0; i < N; i++) {
+                const cdouble q = cdiv(field_dir(z1, N, (i + offset) % N), conn * field_dir(z0, N, i));
+                residuals += atan2(q.y, q.x);
+            }
+            effort[e] = eff;
+            matching[e] = offset - (int)round((residuals - eff) / (2.0 * M_PI));
+        }
+    }
+}
+
+// One thread per vertex: singular[v] = round((N angleDefect[v] + sum over outgoing halfs of -/+ effort[edge]) / 2 pi) (frf.h:100-107);
+// the halfs are walked ccw through twin(prev(h)) (hmesh.h:158-161); a half is canonical iff h == 2 edge[h] (hmesh.h:378).
+static __global__ void __launch_bounds__(kThreads) k_vertex_singular(int nV, int N, const int* __restrict__ vert2half, const int* __restrict__ twin,
+                                                              const int* __restrict__ prev, const int* __restrict__ edge,
+                                                              const double* __restrict__ angleDefect, const double* __restrict__ effort,
+                                                              int* __restrict__ singular) {
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nV; v += gridDim.x * blockDim.x) {
+        double sum = angleDefect[v] * (double)N;
+        const int h0 = vert2half[v];
+        int h = h0, guard = 0;
+        do {
+            const int e = edge[h];
+            sum += (h == 2 * e ? -1.0 : 1.0) * effort[e];
+            h = twin[prev[h]];
+        } while (h != h0 && ++guard < 4096);
+        singular[v] = (int)round(sum / (2.0 * M_PI));
+    }
+}
+
 // ---- solution recycling across the outer iterations (Galerkin projection onto earlier solution increments) ----
 // The right-hand sides M u_k of successive inverse-iteration steps converge to the span of the few slowest eigenvectors,
 // which earlier solves already contain. E holds L-orthonormal increments e_j (e_i^H L e_j = delta_ij), so the

@@ -146,3 +146,22 @@ def test_curvature_aligned_field_matches_oracle(ctx):
     y = F.solveSquare(rhs_ref)
     assert np.abs(y - x_ref).max() <= 1e-8 * np.abs(x_ref).max()
     F.close()
+
+
+@pytest.mark.parametrize("matching", ["curl", "principal"])
+def test_matching_and_singularities_on_device(ctx, ico4, matching):
+    """computeMatching + computeSingular (frf.h:100-202) on the device against the host restatement of the same lines (hostglue, which
+    also generates every IGM fixture): identical matchings and singularity indices, efforts to round-off; sum of indices = N * chi."""
+    s = ico4
+    fi = s.field_inputs()
+    nF = s.dims["nF"]
+    F = api.FaceRosyField(ctx, fi["face2half"], fi["next"], fi["twin"], fi["face"], fi["heArgOnFace"], fi["faceArea"], 4)
+    z = F.solveSmallestEig(oracle.random_u0(nF, 0), 50)
+    mesh = {k: s.get(k) for k in ("pos", "tail", "head", "edge2face", "faceBasisX", "faceBasisY", "edge", "prev", "vert2half", "angleDefect")}
+    m, eff, sing = F.computeMatching(mesh, matching)
+    s.field_post(z, 4, matching)
+    assert np.array_equal(m, s.get("matching"))
+    assert np.array_equal(sing, s.get("singular"))
+    assert np.abs(eff - s.get("effort")).max() < 1e-9
+    assert sing.sum() == 4 * s.dims["euler"]
+    F.close()
