@@ -323,7 +323,15 @@ __device__ __forceinline__ T long_row_sum(int b, int en, const int* __restrict__
     T a0 = ST<T>::zero(), a1 = ST<T>::zero(), a2 = ST<T>::zero(), a3 = ST<T>::zero();
     const int bs = blockDim.x;
     int k = b + threadIdx.x;
-    for (; k + 3 * bs < en; k += 4 * bs) {
+    if constexpr (sizeof(T) > 8) {  // complex fp64: two streams (register budget of the kernels this is inlined into)
+        for (; k + bs < en; k += 2 * bs) {
+            const int c0 = __ldg(col + k), c1 = __ldg(col + k + bs);
+            const T v0 = ld_ro(val + k), v1 = ld_ro(val + k + bs);
+            a0 = ST<T>::fma_(v0, ld_ro(x + c0), a0);
+            a1 = ST<T>::fma_(v1, ld_ro(x + c1), a1);
+        }
+    }
+    for (; sizeof(T) <= 8 && k + 3 * bs < en; k += 4 * bs) {
         const int c0 = __ldg(col + k), c1 = __ldg(col + k + bs), c2 = __ldg(col + k + 2 * bs), c3 = __ldg(col + k + 3 * bs);
         const T v0 = ld_ro(val + k), v1 = ld_ro(val + k + bs), v2 = ld_ro(val + k + 2 * bs), v3 = ld_ro(val + k + 3 * bs);
         a0 = ST<T>::fma_(v0, ld_ro(x + c0), a0);
@@ -340,7 +348,15 @@ template <class T>
 __device__ __forceinline__ T warp_row_sum(int b, int en, const int* __restrict__ col, const T* __restrict__ val, const T* __restrict__ x, int lane) {
     T a0 = ST<T>::zero(), a1 = ST<T>::zero(), a2 = ST<T>::zero(), a3 = ST<T>::zero();
     int k = b + lane;
-    for (; k + 96 < en; k += 128) {
+    if constexpr (sizeof(T) > 8) {
+        for (; k + 32 < en; k += 64) {
+            const int c0 = __ldg(col + k), c1 = __ldg(col + k + 32);
+            const T v0 = ld_ro(val + k), v1 = ld_ro(val + k + 32);
+            a0 = ST<T>::fma_(v0, ld_ro(x + c0), a0);
+            a1 = ST<T>::fma_(v1, ld_ro(x + c1), a1);
+        }
+    }
+    for (; sizeof(T) <= 8 && k + 96 < en; k += 128) {
         const int c0 = __ldg(col + k), c1 = __ldg(col + k + 32), c2 = __ldg(col + k + 64), c3 = __ldg(col + k + 96);
         const T v0 = ld_ro(val + k), v1 = ld_ro(val + k + 32), v2 = ld_ro(val + k + 64), v3 = ld_ro(val + k + 96);
         a0 = ST<T>::fma_(v0, ld_ro(x + c0), a0);
