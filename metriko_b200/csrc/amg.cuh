@@ -510,6 +510,8 @@ struct AmgPrecond : Precond<T> {
     ReduceWs dummy_ws{nullptr, nullptr};
     CoarseHandoff<T>* handoff = nullptr;  // levels >= handoff_level are solved by it (lv[handoff_level] only holds x and b)
     int handoff_level = -1;
+    bool level0_initialised = false;      // the caller already wrote lv[0].r = b and lv[0].d = dinv b / theta (fused hand-over kernel)
+    double inv_theta0() const { return 1.0 / (0.5 * (lv[0].lmax + lv[0].lmax / prm.cheb_ratio)); }
 
     void apply_A(int l, const T* x, T* y, const PcgState* st, cudaStream_t s) {
         if (l == 0 && fine_op) fine_op->apply(x, y, const_cast<PcgState*>(st), dummy_ws, s, false);
@@ -530,7 +532,8 @@ struct AmgPrecond : Precond<T> {
         T* d1 = L.q.p;
         bool fused = true;
         if (zero_guess) {
-            k_cheb_init<T><<<grid, kThreads, 0, s>>>(L.n, b, (const T*)nullptr, L.dinv.p, L.r.p, d0, 1.0 / theta, st);
+            if (!(l == 0 && level0_initialised))
+                k_cheb_init<T><<<grid, kThreads, 0, s>>>(L.n, b, (const T*)nullptr, L.dinv.p, L.r.p, d0, 1.0 / theta, st);
         } else {
             if (ext) fused = fine_op->cheb_resid(x, b, L.r.p, d0, L.dinv.p, 1.0 / theta, st, s);
             else spmv_cheb_resid<T>(L.A, 0.0, x, b, L.r.p, d0, L.dinv.p, 1.0 / theta, st, s);
@@ -643,6 +646,39 @@ struct Fp64Tail : CoarseHandoff<typename LowOf<T>::type> {
     int launches() const override { return 2 + hi->launches_from_level(level); }
 };
 
+// hand-over fused with the start of the level-0 smoother: b = r / |r| (fp32), r0 = b, d0 = dinv b / theta
+template <class T, class Tlo>
+static __global__ void __launch_bounds__(kThreads) k_precond_in_init(int n, const T* __restrict__ r, const Tlo* __restrict__ dinv, Tlo* __restrict__ b,
+                                                              Tlo* __restrict__ r0, Tlo* __restrict__ d0, double inv_theta, const PcgState* st) {
+    if (st->done) return;
+    const double s = st->rr > 0.0 ? rsqrt(st->rr) : 1.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const Tlo bi = to_low<Tlo, T>(ld_ro(r + i), s);
+        st_rw(b + i, bi);
+        st_rw(r0 + i, bi);
+        st_rw(d0 + i, ST<Tlo>::scale(inv_theta, ld_ro(dinv + i) * bi));
+    }
+}
+// hand-back fused with the PCG reduction: z = x |r| (fp64), rho_new = <r, z>, beta = rho_new / rho
+template <class T, class Tlo>
+static __global__ void __launch_bounds__(kThreads) k_precond_out_dot(int n, const Tlo* __restrict__ x, const T* __restrict__ r, T* __restrict__ z,
+                                                              PcgState* st, ReduceWs ws) {
+    __shared__ double red[32];
+    if (st->done) return;
+    const double s = st->rr > 0.0 ? sqrt(st->rr) : 1.0;
+    double acc = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const T zi = to_high<T, Tlo>(ld_ro(x + i), s);
+        st_rw(z + i, zi);
+        acc += ST<T>::hdot(ld_ro(r + i), zi);
+    }
+    double v[1] = {acc};
+    grid_reduce<1>(v, ws.partials, ws.ticket, red, [&](const double* t) {
+        st->beta = t[0] / st->rho;
+        st->rho = t[0];
+    });
+}
+
 template <class T>
 struct MixedPrecond : Precond<T> {
     using Tlo = typename LowOf<T>::type;
@@ -652,14 +688,26 @@ struct MixedPrecond : Precond<T> {
     std::unique_ptr<LinOp<Tlo>> fine_lo;  // level-0 operator in fp32 storage (owned here)
     DevBuf<Tlo> b_lo, z_lo;
     int n = 0;
-    void apply(const T* r, T* z, const PcgState* st, cudaStream_t s) override {
-        const int grid = stream_grid(n);
-        k_precond_in<T, Tlo><<<grid, kThreads, 0, s>>>(n, r, b_lo.p, st);
+    void cycle(const T* r, const PcgState* st, cudaStream_t s) {
+        // hand-over + first smoother kernel of level 0 in one launch (the cycle starts from a zero guess)
+        AmgLevelDev<Tlo>& L0 = lo->lv[0];
+        k_precond_in_init<T, Tlo><<<stream_grid(n), kThreads, 0, s>>>(n, r, L0.dinv.p, b_lo.p, L0.r.p, L0.d.p, lo->inv_theta0(), st);
+        lo->level0_initialised = true;
         lo->apply(b_lo.p, z_lo.p, st, s);
-        k_precond_out<T, Tlo><<<grid, kThreads, 0, s>>>(n, z_lo.p, z, st);
+        lo->level0_initialised = false;
+    }
+    void apply(const T* r, T* z, const PcgState* st, cudaStream_t s) override {
+        cycle(r, st, s);
+        k_precond_out<T, Tlo><<<stream_grid(n), kThreads, 0, s>>>(n, z_lo.p, z, st);
         MK_CHECK_LAUNCH();
     }
-    int launches_per_apply() const override { return lo->launches_per_apply() + 2; }
+    bool apply_dot(const T* r, T* z, PcgState* st, ReduceWs ws, cudaStream_t s) override {
+        cycle(r, st, s);
+        k_precond_out_dot<T, Tlo><<<stream_grid(n), kThreads, 0, s>>>(n, z_lo.p, r, z, st, ws);
+        MK_CHECK_LAUNCH();
+        return true;
+    }
+    int launches_per_apply() const override { return lo->launches_per_apply() + 1; }
 };
 
 template <class T, class Tlo>

@@ -299,6 +299,9 @@ struct Precond {
     virtual ~Precond() = default;
     virtual void apply(const T* r, T* z, const PcgState* st, cudaStream_t s) = 0;  // z = M^{-1} r
     virtual int launches_per_apply() const = 0;
+    // z = M^{-1} r and, fused into its last kernel, the PCG reduction rho_new = <r, z>, beta = rho_new / rho (what k_dot_rz does).
+    // Return false when unsupported (the caller then runs apply + k_dot_rz).
+    virtual bool apply_dot(const T*, T*, PcgState*, ReduceWs, cudaStream_t) { return false; }
 };
 
 // In-place projection onto the feasible subspace (IGM constraint elimination); null for unconstrained solves.
@@ -427,9 +430,12 @@ private:
         if (P_) P_->apply(q_.p, st_.p, stream_);
         if (M_) {
             k_update_xr<T, true><<<grid_, kThreads, 0, stream_>>>(n_, x, r_.p, p_.p, q_.p, st_.p, ws());
-            M_->apply(r_.p, z_.p, st_.p, stream_);
-            if (P_) P_->apply(z_.p, st_.p, stream_);
-            k_dot_rz<T><<<grid_, kThreads, 0, stream_>>>(n_, r_.p, z_.p, st_.p, ws());
+            // without a projector the preconditioner may finish <r, z> in its own last kernel
+            if (P_ || !M_->apply_dot(r_.p, z_.p, st_.p, ws(), stream_)) {
+                M_->apply(r_.p, z_.p, st_.p, stream_);
+                if (P_) P_->apply(z_.p, st_.p, stream_);
+                k_dot_rz<T><<<grid_, kThreads, 0, stream_>>>(n_, r_.p, z_.p, st_.p, ws());
+            }
             k_update_p<T><<<grid_, kThreads, 0, stream_>>>(n_, p_.p, z_.p, st_.p);
         } else {
             k_update_xr<T, false><<<grid_, kThreads, 0, stream_>>>(n_, x, r_.p, p_.p, q_.p, st_.p, ws());
