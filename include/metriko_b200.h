@@ -190,6 +190,10 @@ int mk_amg_dev_build(mk_ctx* ctx, int n, const int* ptr, const int* col, const d
  * strictly increasing columns per row; the result is level 0 / which 0 of the returned container (B ignored for op 1, 2). */
 int mk_dev_sparse_op(mk_ctx* ctx, int op, int is_complex, int a_rows, int a_cols, const int* a_ptr, const int* a_col, const double* a_val, int b_rows,
                      int b_cols, const int* b_ptr, const int* b_col, const double* b_val, mk_amg_host** out);
+/* The same two builds with a dof-type label per row (types[n], may be NULL): dofs of different type never share an aggregate, on any
+ * level. mk_igm_create derives the labels of the IGM operator (u-type / v-type reduced dofs) from UFull and uses them internally. */
+int mk_amg_host_build_typed(int n, const int* ptr, const int* col, const double* val, int is_complex, const int* types, mk_amg_host** out);
+int mk_amg_dev_build_typed(mk_ctx* ctx, int n, const int* ptr, const int* col, const double* val, int is_complex, const int* types, mk_amg_host** out);
 int mk_amg_host_num_levels(mk_amg_host* h);
 int mk_amg_host_level_info(mk_amg_host* h, int level, int which, int* rows, int* cols, int64_t* nnz, double* lmax);
 int mk_amg_host_level_get(mk_amg_host* h, int level, int which, int* ptr, int* col, double* val);

@@ -102,6 +102,8 @@ def lib() -> C.CDLL:
         L.mk_amg_host_build.argtypes = [C.c_int, vp, vp, vp, C.c_int, vp, C.POINTER(vp)]
         L.mk_amg_dev_build.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, C.POINTER(vp)]
         L.mk_dev_sparse_op.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, C.POINTER(vp)]
+        L.mk_amg_host_build_typed.argtypes = [C.c_int, vp, vp, vp, C.c_int, vp, C.POINTER(vp)]
+        L.mk_amg_dev_build_typed.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, vp, C.POINTER(vp)]
         L.mk_amg_host_num_levels.argtypes = [vp]
         L.mk_amg_host_level_info.argtypes = [vp, C.c_int, C.c_int, ip, ip, i64p, dp]
         L.mk_amg_host_level_get.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
@@ -203,26 +205,33 @@ def _canonical_csr(A):
     return A, cx, (np.complex128 if cx else np.float64)
 
 
-def amg_host_hierarchy(A, cand=None):
+def amg_host_hierarchy(A, cand=None, types=None):
     """Builds the solvers' smoothed-aggregation hierarchy with the host mirror (no device) and returns
-    [(A_l, P_l or None, lmax_l, dinv_l)] (scipy CSR matrices, smoother diagonal) -- for CPU tests of the set-up."""
+    [(A_l, P_l or None, lmax_l, dinv_l)] (scipy CSR matrices, smoother diagonal) -- for CPU tests of the set-up.
+    types: optional dof-type label per row (typed aggregation, what mk_igm_create uses for the IGM operator)."""
     A, cx, dt = _canonical_csr(A)
     L = lib()
     h = C.c_void_p()
     val = np.ascontiguousarray(A.data, dt)
     c = as_f64(cand) if cand is not None else None
-    rc = L.mk_amg_host_build(A.shape[0], ptr(as_i32(A.indptr)), ptr(as_i32(A.indices)), ptr(val), int(cx), ptr(c), C.byref(h))
+    if types is not None:
+        assert cand is None
+        ty = as_i32(types)
+        rc = L.mk_amg_host_build_typed(A.shape[0], ptr(as_i32(A.indptr)), ptr(as_i32(A.indices)), ptr(val), int(cx), ptr(ty), C.byref(h))
+    else:
+        rc = L.mk_amg_host_build(A.shape[0], ptr(as_i32(A.indptr)), ptr(as_i32(A.indices)), ptr(val), int(cx), ptr(c), C.byref(h))
     if rc != MK_OK:
         raise MkError(rc, "mk_amg_host_build")
     return _read_hierarchy(L, h, dt)
 
 
-def amg_dev_hierarchy(ctx: "Context", A):
+def amg_dev_hierarchy(ctx: "Context", A, types=None):
     """The same hierarchy built by the device set-up (what the solvers run), copied back level by level."""
     A, cx, dt = _canonical_csr(A)
     h = C.c_void_p()
     val = np.ascontiguousarray(A.data, dt)
-    ctx.check(ctx.L.mk_amg_dev_build(ctx.h, A.shape[0], ptr(as_i32(A.indptr)), ptr(as_i32(A.indices)), ptr(val), int(cx), C.byref(h)))
+    ty = as_i32(types) if types is not None else None
+    ctx.check(ctx.L.mk_amg_dev_build_typed(ctx.h, A.shape[0], ptr(as_i32(A.indptr)), ptr(as_i32(A.indices)), ptr(val), int(cx), ptr(ty), C.byref(h)))
     return _read_hierarchy(ctx.L, h, dt)
 
 
@@ -248,3 +257,18 @@ def dev_sparse_op(ctx: "Context", op: str, A, B=None):
         args += [0, 0, None, None, None]
     ctx.check(ctx.L.mk_dev_sparse_op(*args, C.byref(h)))
     return _read_hierarchy(ctx.L, h, dt)[0][0]
+
+
+def igm_dof_types(UFull, n: int = 2) -> np.ndarray:
+    """Dof-type labels of the reduced IGM unknowns as mk_igm_create derives them: the full dof a column of UFull contributes to most
+    strongly has index n * vertex + k; the label is k (u- or v-type). Mirror of igm_types_from_ufull (csrc/capi_igm.cu) for the tests."""
+    import scipy.sparse as sp
+    U = sp.csr_matrix(UFull).tocoo()
+    best = np.zeros(U.shape[1])
+    ty = np.zeros(U.shape[1], np.int32)
+    order = np.lexsort((U.col, U.row))           # row-major traversal, like the CSR loop of the C++ side
+    for r, c, v in zip(U.row[order], U.col[order], np.abs(U.data[order])):
+        if v > best[c]:
+            best[c] = v
+            ty[c] = r % n
+    return ty

@@ -202,7 +202,7 @@ __host__ __device__ inline int mis_key_index(uint64_t k) { return (int)(~(uint32
 
 template <class S>
 inline int aggregate_mis2(const HostCsr<S>& A, double theta, const std::vector<char>& dense, std::vector<int>& agg, std::vector<S>& tval,
-                          std::vector<int>& dense_coarse) {
+                          std::vector<int>& dense_coarse, const std::vector<int>* types = nullptr) {
     const int n = A.rows;
     const bool has_dense = !dense.empty();
     std::vector<double> dabs(n, 0.0);
@@ -210,9 +210,11 @@ inline int aggregate_mis2(const HostCsr<S>& A, double theta, const std::vector<c
     for (int i = 0; i < n; i++)
         for (int k = A.ptr[i]; k < A.ptr[i + 1]; k++)
             if (A.col[k] == i) dabs[i] = std::abs(A.val[k]);
+    const bool typed = types && !types->empty();
     auto strong = [&](int i, int k) {
         const int j = A.col[k];
         if (j == i || (has_dense && (dense[j] || dense[i]))) return false;
+        if (typed && (*types)[i] != (*types)[j]) return false;  // dofs of different type never share an aggregate (see AmgParams / DESIGN.md)
         const double a = std::abs(A.val[k]);
         return a > 0 && a * a >= theta * theta * dabs[i] * dabs[j];
     };
@@ -288,8 +290,12 @@ inline int aggregate_mis2(const HostCsr<S>& A, double theta, const std::vector<c
     return nagg;
 }
 
+// `types` (optional, one int per row): dofs of different type are never put into the same aggregate, on any level (a coarse dof inherits
+// the type of its members). The IGM operator needs it: its near-kernel is two-dimensional (u- and v-translation) and ONE transported
+// value per aggregate cannot represent both where an aggregate would mix u- and v-type dofs across a seam.
 template <class S>
-inline std::vector<AmgHostLevel<S>> build_hierarchy(HostCsr<S> A, std::vector<S> cand, bool use_cand, const AmgParams& prm) {
+inline std::vector<AmgHostLevel<S>> build_hierarchy(HostCsr<S> A, std::vector<S> cand, bool use_cand, const AmgParams& prm,
+                                                    std::vector<int> types = {}) {
     std::vector<AmgHostLevel<S>> lv;
     StageTimer tm("build_hierarchy");
     // dense dofs (e.g. the seam-translation / constraint-kernel columns of the IGM operator: a few rows with thousands of
@@ -328,7 +334,7 @@ inline std::vector<AmgHostLevel<S>> build_hierarchy(HostCsr<S> A, std::vector<S>
         if (n - n_dense <= prm.coarse_max || (int)lv.size() + 1 >= prm.max_levels) { lv.push_back(std::move(L)); break; }
         std::vector<int> agg, dense_coarse;
         std::vector<S> tv;
-        const int nc = (prm.agg == 1 && !use_cand) ? aggregate_mis2(L.A, prm.theta, dense, agg, tv, dense_coarse)
+        const int nc = (prm.agg == 1 && !use_cand) ? aggregate_mis2(L.A, prm.theta, dense, agg, tv, dense_coarse, &types)
                                                    : aggregate(L.A, prm.theta, use_cand ? &cand : nullptr, dense, agg, tv, dense_coarse);
         tm.lap("aggregate");
         if (nc >= n * 0.8 || nc == 0) { lv.push_back(std::move(L)); break; }  // stagnation: stop here
@@ -391,6 +397,11 @@ inline std::vector<AmgHostLevel<S>> build_hierarchy(HostCsr<S> A, std::vector<S>
         A = matmul(L.R, AP);
         tm.lap("R (A P)");
         cand = std::move(ccand);
+        if (!types.empty()) {
+            std::vector<int> ctypes(nc, 0);
+            for (int i = 0; i < n; i++) ctypes[agg[i]] = types[i];  // all members of an aggregate carry the same type
+            types = std::move(ctypes);
+        }
         if (n_dense) {
             dense.assign(nc, 0);
             for (int c : dense_coarse) dense[c] = 1;
@@ -783,6 +794,12 @@ inline std::unique_ptr<MixedPrecond<T>> lower_precision(cudaStream_t s, std::uni
     return mp;
 }
 
+// MK_AMG_TYPED=0 switches the typed aggregation of the IGM hierarchy off (one candidate for mixed u / v aggregates, as before)
+inline bool typed_aggregation() {
+    const char* e = getenv("MK_AMG_TYPED");
+    return !(e && std::strcmp(e, "0") == 0);
+}
+
 // MK_PRECOND_FP32=0 keeps the V-cycle in fp64
 inline bool precond_fp32() {
     const char* e = getenv("MK_PRECOND_FP32");
@@ -803,14 +820,14 @@ inline void upload_host_csr(DeviceCsr<T>& D, const HostCsr<typename HostScalar<T
 template <class T>
 inline std::unique_ptr<AmgPrecond<T>> build_amg(cudaStream_t s, HostCsr<typename HostScalar<T>::type> A,
                                                 std::vector<typename HostScalar<T>::type> cand, bool use_cand, LinOp<T>* fine_op,
-                                                const AmgParams& prm) {
+                                                const AmgParams& prm, std::vector<int> types = {}) {
     using S = typename HostScalar<T>::type;
     auto amg = std::make_unique<AmgPrecond<T>>();
     amg->prm = prm;
     amg->fine_op = fine_op;
     const double nnz0 = (double)A.nnz(), n0 = (double)A.rows;
     StageTimer tm("build_amg");
-    std::vector<AmgHostLevel<S>> H = build_hierarchy<S>(std::move(A), std::move(cand), use_cand, prm);
+    std::vector<AmgHostLevel<S>> H = build_hierarchy<S>(std::move(A), std::move(cand), use_cand, prm, std::move(types));
     tm.lap("hierarchy (host)");
     amg->lv.resize(H.size());
     double nnz_sum = 0, n_sum = 0;

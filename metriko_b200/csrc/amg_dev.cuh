@@ -72,22 +72,25 @@ static __global__ void k_diag_dinv(int n, const int* __restrict__ ptr, const int
 
 // ---- MIS(2): the synchronous rounds of aggregate_mis2 (amg.cuh), one thread per node ----
 template <class T>
-__device__ __forceinline__ bool dev_strong(int i, int j, T v, const char* __restrict__ dense, const double* __restrict__ dabs, double theta2) {
+__device__ __forceinline__ bool dev_strong(int i, int j, T v, const char* __restrict__ dense, const double* __restrict__ dabs, double theta2,
+                                           const int* __restrict__ type) {
     if (j == i || (dense && (dense[j] || dense[i]))) return false;
+    if (type && type[i] != type[j]) return false;
     const double a = dev_abs<T>(v);
     return a > 0 && a * a >= theta2 * dabs[i] * dabs[j];
 }
 
 template <class T>
 static __global__ void k_mis_t1(int n, const int* __restrict__ ptr, const int* __restrict__ col, const T* __restrict__ val, const char* __restrict__ dense,
-                                const double* __restrict__ dabs, double theta2, const int* __restrict__ state, int hashed, uint64_t* __restrict__ t1) {
+                                const double* __restrict__ dabs, double theta2, const int* __restrict__ type, const int* __restrict__ state, int hashed,
+                                uint64_t* __restrict__ t1) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint64_t m = mis_key(state[i], i, hashed != 0);
     if (!(dense && dense[i]))
         for (int k = ptr[i]; k < ptr[i + 1]; k++) {
             const int j = col[k];
-            if (dev_strong<T>(i, j, ld_ro(val + k), dense, dabs, theta2)) {
+            if (dev_strong<T>(i, j, ld_ro(val + k), dense, dabs, theta2, type)) {
                 const uint64_t kj = mis_key(state[j], j, hashed != 0);
                 m = kj > m ? kj : m;
             }
@@ -97,7 +100,8 @@ static __global__ void k_mis_t1(int n, const int* __restrict__ ptr, const int* _
 
 template <class T>
 static __global__ void k_mis_t2_update(int n, const int* __restrict__ ptr, const int* __restrict__ col, const T* __restrict__ val, const char* __restrict__ dense,
-                                       const double* __restrict__ dabs, double theta2, const uint64_t* __restrict__ t1, const int* __restrict__ state,
+                                       const double* __restrict__ dabs, double theta2, const int* __restrict__ type, const uint64_t* __restrict__ t1,
+                                       const int* __restrict__ state,
                                        int* __restrict__ state_out, int* __restrict__ undecided) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -107,7 +111,7 @@ static __global__ void k_mis_t2_update(int n, const int* __restrict__ ptr, const
         uint64_t m = t1[i];
         for (int k = ptr[i]; k < ptr[i + 1]; k++) {
             const int j = col[k];
-            if (dev_strong<T>(i, j, ld_ro(val + k), dense, dabs, theta2)) {
+            if (dev_strong<T>(i, j, ld_ro(val + k), dense, dabs, theta2, type)) {
                 const uint64_t kj = t1[j];
                 m = kj > m ? kj : m;
             }
@@ -137,7 +141,7 @@ static __global__ void k_agg_roots(int n, const int* __restrict__ state, const i
 // (round 1: roots only). Reads agg_in / tv_in, writes agg_out / tv_out.
 template <class T>
 static __global__ void k_agg_join(int n, const int* __restrict__ ptr, const int* __restrict__ col, const T* __restrict__ val, const char* __restrict__ dense,
-                                  const double* __restrict__ dabs, double theta2, const int* __restrict__ state, int roots_only,
+                                  const double* __restrict__ dabs, double theta2, const int* __restrict__ type, const int* __restrict__ state, int roots_only,
                                   const int* __restrict__ agg_in, const T* __restrict__ tv_in, int* __restrict__ agg_out, T* __restrict__ tv_out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -149,7 +153,7 @@ static __global__ void k_agg_join(int n, const int* __restrict__ ptr, const int*
         for (int k = ptr[i]; k < ptr[i + 1]; k++) {
             const int j = col[k];
             const T v = ld_ro(val + k);
-            if (!dev_strong<T>(i, j, v, dense, dabs, theta2)) continue;
+            if (!dev_strong<T>(i, j, v, dense, dabs, theta2, type)) continue;
             if (roots_only ? (state[j] != 2) : (agg_in[j] == -1)) continue;
             const double w = dev_abs<T>(v);
             if (w > best * kStrongerBy) { best = w; bk = k; }
@@ -283,10 +287,17 @@ inline double estimate_rho_dev(const DeviceCsr<T>& A, const T* dinv, cudaStream_
     return std::sqrt(h[0] / h[1]);
 }
 
+// a coarse dof inherits the type of its members (all equal: typed aggregation never mixes them; the racing writes store the same value)
+static __global__ void k_coarse_types(int n, const int* __restrict__ agg, const int* __restrict__ type, int* __restrict__ ctype) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ctype[agg[i]] = type[i];
+}
+
 // Aggregation of one level on the device. Outputs the tentative prolongator T (n x nc, one entry per row); returns nc.
 // dense (may be null): dense dofs of this level; dense_next (size >= n): flags of the coarse level (its last n_dense ids).
 template <class T>
-inline int aggregate_dev(const DeviceCsr<T>& A, double theta, const char* dense, int n_dense, const double* dabs, DeviceCsr<T>& Tm, cudaStream_t s) {
+inline int aggregate_dev(const DeviceCsr<T>& A, double theta, const char* dense, int n_dense, const double* dabs, DeviceCsr<T>& Tm, cudaStream_t s,
+                         const int* type = nullptr, DevBuf<int>* type_next = nullptr) {
     const int n = A.rows;
     const int g = (n + 255) / 256;
     const double theta2 = theta * theta;
@@ -302,8 +313,8 @@ inline int aggregate_dev(const DeviceCsr<T>& A, double theta, const char* dense,
     for (int round = 0; round < kMisMaxRounds; round++) {
         const int hashed = round >= kMisIndexRounds ? 1 : 0;
         counter.zero(s);
-        k_mis_t1<T><<<g, 256, 0, s>>>(n, A.ptr.p, A.col.p, A.val.p, dense, dabs, theta2, cur, hashed, t1.p);
-        k_mis_t2_update<T><<<g, 256, 0, s>>>(n, A.ptr.p, A.col.p, A.val.p, dense, dabs, theta2, t1.p, cur, nxt, counter.p);
+        k_mis_t1<T><<<g, 256, 0, s>>>(n, A.ptr.p, A.col.p, A.val.p, dense, dabs, theta2, type, cur, hashed, t1.p);
+        k_mis_t2_update<T><<<g, 256, 0, s>>>(n, A.ptr.p, A.col.p, A.val.p, dense, dabs, theta2, type, t1.p, cur, nxt, counter.p);
         MK_CHECK_LAUNCH();
         std::swap(cur, nxt);
         if (dev_read_int(counter.p, s) == 0) break;
@@ -313,8 +324,8 @@ inline int aggregate_dev(const DeviceCsr<T>& A, double theta, const char* dense,
     dev_exclusive_scan(flag.p, id.p, n, s);
     int nagg = dev_read_int(id.p + n, s);
     k_agg_roots<T><<<g, 256, 0, s>>>(n, cur, id.p, agg.p, tv.p);
-    k_agg_join<T><<<g, 256, 0, s>>>(n, A.ptr.p, A.col.p, A.val.p, dense, dabs, theta2, cur, 1, agg.p, tv.p, agg2.p, tv2.p);
-    k_agg_join<T><<<g, 256, 0, s>>>(n, A.ptr.p, A.col.p, A.val.p, dense, dabs, theta2, cur, 0, agg2.p, tv2.p, agg.p, tv.p);
+    k_agg_join<T><<<g, 256, 0, s>>>(n, A.ptr.p, A.col.p, A.val.p, dense, dabs, theta2, type, cur, 1, agg.p, tv.p, agg2.p, tv2.p);
+    k_agg_join<T><<<g, 256, 0, s>>>(n, A.ptr.p, A.col.p, A.val.p, dense, dabs, theta2, type, cur, 0, agg2.p, tv2.p, agg.p, tv.p);
     // leftovers, then dense dofs, as singletons in index order
     k_flag_singletons<<<g, 256, 0, s>>>(n, agg.p, dense, 0, flag.p);
     dev_exclusive_scan(flag.p, id.p, n, s);
@@ -338,6 +349,11 @@ inline int aggregate_dev(const DeviceCsr<T>& A, double theta, const char* dense,
     Tm.col.alloc(n);
     Tm.val.alloc(n);
     k_build_tentative<T><<<(n + 256) / 256, 256, 0, s>>>(n, agg.p, tv.p, size.p, Tm.ptr.p, Tm.col.p, Tm.val.p);
+    if (type && type_next) {
+        type_next->alloc((size_t)std::max(nagg, 1));
+        type_next->zero(s);
+        k_coarse_types<<<g, 256, 0, s>>>(n, agg.p, type, type_next->p);
+    }
     MK_CHECK_LAUNCH();
     MK_CUDA(cudaStreamSynchronize(s));
     return nagg;
@@ -352,7 +368,8 @@ static __global__ void k_flag_tail(int n, int first, char* __restrict__ dense) {
 // `fine_op` non-null: level 0 applies that operator in the V-cycle, the CSR copy of level 0 is released after the set-up.
 // keep_csr: keep every level's plain CSR arrays (tests read them back).
 template <class T>
-inline std::unique_ptr<AmgPrecond<T>> build_amg_device(cudaStream_t s, DeviceCsr<T>&& A0, LinOp<T>* fine_op, const AmgParams& prm) {
+inline std::unique_ptr<AmgPrecond<T>> build_amg_device(cudaStream_t s, DeviceCsr<T>&& A0, LinOp<T>* fine_op, const AmgParams& prm,
+                                                       DevBuf<int> types = DevBuf<int>()) {
     using S = typename HostScalar<T>::type;
     auto amg = std::make_unique<AmgPrecond<T>>();
     amg->prm = prm;
@@ -390,9 +407,10 @@ inline std::unique_ptr<AmgPrecond<T>> build_amg_device(cudaStream_t s, DeviceCsr
         tm.lap("dinv + rho");
         bool last = (n - n_dense <= prm.coarse_max) || (l + 1 >= prm.max_levels);
         DeviceCsr<T> Tm;
+        DevBuf<int> types_next;
         int nc = 0;
         if (!last) {
-            nc = aggregate_dev<T>(A, prm.theta, n_dense ? dense.p : nullptr, n_dense, dabs.p, Tm, s);
+            nc = aggregate_dev<T>(A, prm.theta, n_dense ? dense.p : nullptr, n_dense, dabs.p, Tm, s, types.p, &types_next);
             tm.lap("aggregate");
             if (nc >= n * 0.8 || nc == 0) last = true;
         }
@@ -444,6 +462,7 @@ inline std::unique_ptr<AmgPrecond<T>> build_amg_device(cudaStream_t s, DeviceCsr
             MK_CHECK_LAUNCH();
         }
         A = std::move(Ac);
+        if (types.p) types = std::move(types_next);
     }
     // coarsest level: dense inverse on the host (<= 1500 rows) or Chebyshev
     AmgLevelDev<T>& C = amg->lv.back();

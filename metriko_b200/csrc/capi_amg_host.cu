@@ -25,8 +25,11 @@ static const HostCsr<S>* pick(const std::vector<AmgHostLevel<S>>& lv, int level,
 
 extern "C" {
 
+int mk_amg_host_build_typed(int n, const int* ptr, const int* col, const double* val, int is_complex, const int* types, mk_amg_host** out);
+
 int mk_amg_host_build(int n, const int* ptr, const int* col, const double* val, int is_complex, const double* cand, mk_amg_host** out) {
     if (n <= 0 || !ptr || !col || !val || !out) return MK_ERR_ARG;
+    if (!cand) return mk_amg_host_build_typed(n, ptr, col, val, is_complex, nullptr, out);
     try {
         auto h = std::make_unique<mk_amg_host>();
         h->is_complex = is_complex != 0;
@@ -80,7 +83,12 @@ static void upload_abi_csr(DeviceCsr<T>& A, int rows, int cols, const int* ptr, 
 
 extern "C" {
 
+int mk_amg_dev_build_typed(mk_ctx* ctx, int n, const int* ptr, const int* col, const double* val, int is_complex, const int* types, mk_amg_host** out);
 int mk_amg_dev_build(mk_ctx* ctx, int n, const int* ptr, const int* col, const double* val, int is_complex, mk_amg_host** out) {
+    return mk_amg_dev_build_typed(ctx, n, ptr, col, val, is_complex, nullptr, out);
+}
+
+int mk_amg_dev_build_typed(mk_ctx* ctx, int n, const int* ptr, const int* col, const double* val, int is_complex, const int* types, mk_amg_host** out) {
     if (!ctx || n <= 0 || !ptr || !col || !val || !out) return MK_ERR_ARG;
     MK_API_BEGIN(ctx)
     MK_CUDA(cudaSetDevice(ctx->c.device));
@@ -92,13 +100,17 @@ int mk_amg_dev_build(mk_ctx* ctx, int n, const int* ptr, const int* col, const d
         DeviceCsr<cdouble> A;
         upload_abi_csr<cdouble>(A, n, n, ptr, col, val, s);
         if (!rows_sorted_strict(A, s)) throw std::invalid_argument("mk_amg_dev_build: rows must have strictly increasing columns");
-        auto amg = build_amg_device<cdouble>(s, std::move(A), nullptr, prm);
+        DevBuf<int> ty;
+        if (types) { ty.alloc(n); ty.upload(types, n, s); MK_CUDA(cudaStreamSynchronize(s)); }
+        auto amg = build_amg_device<cdouble>(s, std::move(A), nullptr, prm, std::move(ty));
         device_levels_to_host<cdouble, std::complex<double>>(s, *amg, h->cx);
     } else {
         DeviceCsr<double> A;
         upload_abi_csr<double>(A, n, n, ptr, col, val, s);
         if (!rows_sorted_strict(A, s)) throw std::invalid_argument("mk_amg_dev_build: rows must have strictly increasing columns");
-        auto amg = build_amg_device<double>(s, std::move(A), nullptr, prm);
+        DevBuf<int> ty;
+        if (types) { ty.alloc(n); ty.upload(types, n, s); MK_CUDA(cudaStreamSynchronize(s)); }
+        auto amg = build_amg_device<double>(s, std::move(A), nullptr, prm, std::move(ty));
         device_levels_to_host<double, double>(s, *amg, h->re);
     }
     *out = h.release();
@@ -139,6 +151,38 @@ int mk_dev_sparse_op(mk_ctx* ctx, int op, int is_complex, int a_rows, int a_cols
     }
     *out = h.release();
     MK_API_END(ctx)
+}
+
+int mk_amg_host_build_typed(int n, const int* ptr, const int* col, const double* val, int is_complex, const int* types, mk_amg_host** out) {
+    if (n <= 0 || !ptr || !col || !val || !out) return MK_ERR_ARG;
+    try {
+        auto h = std::make_unique<mk_amg_host>();
+        h->is_complex = is_complex != 0;
+        const AmgParams prm = amg_params_from_env(!is_complex);
+        const int64_t nnz = ptr[n];
+        std::vector<int> ty;
+        if (types) ty.assign(types, types + n);
+        if (is_complex) {
+            HostCsr<std::complex<double>> A;
+            A.rows = A.cols = n;
+            A.ptr.assign(ptr, ptr + n + 1);
+            A.col.assign(col, col + nnz);
+            A.val.resize(nnz);
+            for (int64_t k = 0; k < nnz; k++) A.val[k] = {val[2 * k], val[2 * k + 1]};
+            h->cx = build_hierarchy<std::complex<double>>(std::move(A), {}, false, prm, std::move(ty));
+        } else {
+            HostCsr<double> A;
+            A.rows = A.cols = n;
+            A.ptr.assign(ptr, ptr + n + 1);
+            A.col.assign(col, col + nnz);
+            A.val.assign(val, val + nnz);
+            h->re = build_hierarchy<double>(std::move(A), {}, false, prm, std::move(ty));
+        }
+        *out = h.release();
+        return MK_OK;
+    } catch (...) {
+        return MK_ERR_INTERNAL;
+    }
 }
 
 int mk_amg_host_num_levels(mk_amg_host* h) { return !h ? 0 : (int)(h->is_complex ? h->cx.size() : h->re.size()); }

@@ -230,6 +230,20 @@ struct mk_igm {
     double setup_ms = 0;
 };
 
+// Dof-type labels of the reduced unknowns for the typed aggregation of the IGM hierarchy: the full dofs are numbered n * vertex + k
+// (k = 0: u, 1: v; parameterization_setup.ipp:157-169), a column of UFull gets the k of the full dof it contributes to most strongly
+// (first maximum in row-major order). Python mirror: metriko_b200.capi.igm_dof_types.
+static std::vector<int> igm_types_from_ufull(const HostCsr<double>& U, int n_per_vertex = 2) {
+    std::vector<int> ty(U.cols, 0);
+    std::vector<double> best(U.cols, 0.0);
+    for (int i = 0; i < U.rows; i++)
+        for (int k = U.ptr[i]; k < U.ptr[i + 1]; k++) {
+            const double a = std::fabs(U.val[k]);
+            if (a > best[U.col[k]]) { best[U.col[k]] = a; ty[U.col[k]] = i % n_per_vertex; }
+        }
+    return ty;
+}
+
 static HostCsr<double> csr_from_abi(int rows, int cols, const int64_t* ptr, const int* col, const double* val) {
     HostCsr<double> A;
     A.rows = rows;
@@ -340,7 +354,14 @@ static int igm_create_impl(mk_ctx* ctx, int rows, int cols, const int64_t* x2f_p
             g->opA = std::make_unique<CsrOp<double>>(&g->A0, 1e-4);  // wClose^2 = 0.01^2 (ir_loop.h:109)
             tm.lap("rhs0 + layouts");
             if (g->o.precond == 1) {
-                g->amg = build_amg_device<double>(s, std::move(As), g->opA.get(), amg_params_from_env(true));
+                DevBuf<int> ty;
+                if (typed_aggregation()) {
+                    const std::vector<int> hty = igm_types_from_ufull(g->UFull);
+                    ty.alloc(cols);
+                    ty.upload(hty.data(), cols, s);
+                    MK_CUDA(cudaStreamSynchronize(s));
+                }
+                g->amg = build_amg_device<double>(s, std::move(As), g->opA.get(), amg_params_from_env(true), std::move(ty));
                 tm.lap("build_amg_device");
                 if (precond_fp32()) {
                     lower_csr<double, float>(g->A0, g->A0_lo, s);
@@ -374,7 +395,8 @@ static int igm_create_impl(mk_ctx* ctx, int rows, int cols, const int64_t* x2f_p
             for (int i = 0; i < A0.rows; i++)
                 for (int k = A0.ptr[i]; k < A0.ptr[i + 1]; k++)
                     if (A0.col[k] == i) A0.val[k] += 1e-4;
-            g->amg = build_amg<double>(s, std::move(A0), {}, false, g->opA.get(), amg_params_from_env(true));
+            g->amg = build_amg<double>(s, std::move(A0), {}, false, g->opA.get(), amg_params_from_env(true),
+                                       typed_aggregation() ? igm_types_from_ufull(g->UFull) : std::vector<int>());
             tm.lap("build_amg");
         }
     }

@@ -124,6 +124,12 @@ def test_device_hierarchy_with_dense_dofs(ctx):
     Hd2 = capi.amg_dev_hierarchy(ctx, A)
     for a, b in zip(Hd, Hd2):   # bit-reproducible set-up
         assert np.array_equal(a[0].data.view(np.uint8), b[0].data.view(np.uint8))
+    # typed aggregation (u- / v-type dofs never share an aggregate; what mk_igm_create builds): device == host mirror, and
+    # it is a different hierarchy from the untyped one
+    ty = capi.igm_dof_types(inp["UFull"])
+    Ht_d, Ht_h = capi.amg_dev_hierarchy(ctx, A, types=ty), capi.amg_host_hierarchy(A, types=ty)
+    _compare_hierarchies(Ht_d, Ht_h)
+    assert [h[0].shape for h in Ht_h] != [h[0].shape for h in Hh]
 
 
 def test_host_and_device_setup_give_the_same_rounding(ctx):
