@@ -38,6 +38,7 @@ struct AmgParams {
     int cheb_degree = 1;       // SpMVs per pre- and per post-smoothing (measured at 1M vertices: degree 1 = 2330 ms of solves, 2 = 2593, 3 = 2978)
     double cheb_ratio = 8.0;   // smoother targets [lmax / ratio, lmax] of D^{-1} A
     double omega_scale = 4.0 / 3.0;  // prolongator smoothing omega = omega_scale / rho(D^{-1}A)
+    int cheb_degree_coarse = 0;  // > 0: degree on the levels below the finest (they are latency-bound: launches, not bytes); 0 = cheb_degree
     int dense_row = 64;        // fine-level rows longer than this are "dense dofs": never aggregated with others, carried
                                // as singletons to the coarsest level (solved exactly there), l1-scaled in the smoother
     int agg = 1;               // 0 = sequential greedy (Vanek), 1 = MIS(2) roots (parallel; what the device set-up runs)
@@ -50,6 +51,7 @@ inline AmgParams amg_params_from_env(bool real_op = false) {
     AmgParams p;
     if (real_op) p.theta = 0.1;
     if (const char* e = getenv("MK_AMG_DEG")) p.cheb_degree = atoi(e);
+    if (const char* e = getenv("MK_AMG_DEG_COARSE")) p.cheb_degree_coarse = atoi(e);
     if (const char* e = getenv("MK_AMG_RATIO")) p.cheb_ratio = atof(e);
     if (const char* e = getenv("MK_AMG_THETA")) p.theta = atof(e);
     if (const char* e = getenv("MK_AMG_COARSE")) p.coarse_max = atoi(e);
@@ -522,6 +524,8 @@ struct AmgPrecond : Precond<T> {
     CoarseHandoff<T>* handoff = nullptr;  // levels >= handoff_level are solved by it (lv[handoff_level] only holds x and b)
     int handoff_level = -1;
     bool level0_initialised = false;      // the caller already wrote lv[0].r = b and lv[0].d = dinv b / theta (fused hand-over kernel)
+    int degree(int l) const { return (l > 0 && prm.cheb_degree_coarse > 0 && !coarsest_smoothing) ? prm.cheb_degree_coarse : prm.cheb_degree; }
+    bool coarsest_smoothing = false;  // the non-dense coarsest level is "solved" by 8 Chebyshev steps (cheb_degree is overridden there)
     double inv_theta0() const { return 1.0 / (0.5 * (lv[0].lmax + lv[0].lmax / prm.cheb_ratio)); }
 
     void apply_A(int l, const T* x, T* y, const PcgState* st, cudaStream_t s) {
@@ -553,7 +557,7 @@ struct AmgPrecond : Precond<T> {
                 k_cheb_init<T><<<grid, kThreads, 0, s>>>(L.n, b, L.q.p, L.dinv.p, L.r.p, d0, 1.0 / theta, st);
             }
         }
-        for (int k = 0; k < prm.cheb_degree; k++) {
+        for (int k = 0; k < degree(l); k++) {
             const double rho1 = 1.0 / (2.0 * sigma - rho);
             const int first = (zero_guess && k == 0) ? 1 : 0;
             if (fused && ext) fused = fine_op->cheb_step(d0, d1, L.r.p, x, L.dinv.p, rho1 * rho, 2.0 * rho1 / delta, first, st, s);
@@ -579,7 +583,9 @@ struct AmgPrecond : Precond<T> {
             } else {
                 const int save = prm.cheb_degree;
                 prm.cheb_degree = 8;
+                coarsest_smoothing = true;
                 smooth(l, b, x, true, st, s);
+                coarsest_smoothing = false;
                 prm.cheb_degree = save;
             }
             return;
@@ -597,14 +603,16 @@ struct AmgPrecond : Precond<T> {
 
     int launches_per_apply() const override {
         const int nl = (int)lv.size();
-        const int per = 4 + 2 * prm.cheb_degree;  // fused smoothing: init, degree, restrict, prolong, resid, degree
-        if (handoff) return handoff_level * per + handoff->launches();
-        return (nl - 1) * per + (coarse_dense ? 1 : 17);
+        // fused smoothing: init, degree, restrict, prolong, resid, degree
+        if (handoff) return levels_launches(0, handoff_level) + handoff->launches();
+        return levels_launches(0, nl - 1) + (coarse_dense ? 1 : 17);
     }
-    int launches_from_level(int l0) const {
-        const int per = 4 + 2 * prm.cheb_degree;
-        return ((int)lv.size() - 1 - l0) * per + (coarse_dense ? 1 : 17);
+    int levels_launches(int l0, int l1) const {
+        int sum = 0;
+        for (int l = l0; l < l1; l++) sum += 4 + 2 * degree(l);
+        return sum;
     }
+    int launches_from_level(int l0) const { return levels_launches(l0, (int)lv.size() - 1) + (coarse_dense ? 1 : 17); }
 };
 
 // ---- mixed precision: the V-cycle in fp32 storage and arithmetic, wrapped as a preconditioner of the fp64 PCG ----
