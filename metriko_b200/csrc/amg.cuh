@@ -38,7 +38,9 @@ struct AmgParams {
     int cheb_degree = 1;       // SpMVs per pre- and per post-smoothing (measured at 1M vertices: degree 1 = 2330 ms of solves, 2 = 2593, 3 = 2978)
     double cheb_ratio = 8.0;   // smoother targets [lmax / ratio, lmax] of D^{-1} A
     double omega_scale = 4.0 / 3.0;  // prolongator smoothing omega = omega_scale / rho(D^{-1}A)
-    int cheb_degree_coarse = 0;  // > 0: degree on the levels below the finest (they are latency-bound: launches, not bytes); 0 = cheb_degree
+    int cheb_degree_coarse = 2;  // degree on the levels below the finest (latency-bound: launches, not bytes); 0 = cheb_degree. Measured at
+                                 // 1M vertices (profiles/amg_tuning_r01g_typed_degcoarse.txt): field solve 533 / 506 / 531 ms at 1 / 2 / 3
+                                 // (1186 / 1017 / 988 iterations), IGM solve 619 / 595 ms at 1 / 2 (1537 / 1350 iterations)
     int dense_row = 64;        // fine-level rows longer than this are "dense dofs": never aggregated with others, carried
                                // as singletons to the coarsest level (solved exactly there), l1-scaled in the smoother
     int agg = 1;               // 0 = sequential greedy (Vanek), 1 = MIS(2) roots (parallel; what the device set-up runs)
@@ -802,10 +804,12 @@ inline std::unique_ptr<MixedPrecond<T>> lower_precision(cudaStream_t s, std::uni
     return mp;
 }
 
-// MK_AMG_TYPED=0 switches the typed aggregation of the IGM hierarchy off (one candidate for mixed u / v aggregates, as before)
+// MK_AMG_TYPED=1 switches the typed aggregation of the IGM hierarchy on (u- and v-type dofs never share an aggregate). Off by default:
+// it saves ~20 % of the PCG iterations up to 262k vertices (CPU mirror and device) but costs +44 % at 1M vertices on the device
+// (2215 against 1537 inner iterations, profiles/amg_tuning_r01g_typed_degcoarse.txt) -- not understood yet, see profiles/README.md.
 inline bool typed_aggregation() {
     const char* e = getenv("MK_AMG_TYPED");
-    return !(e && std::strcmp(e, "0") == 0);
+    return e && std::strcmp(e, "1") == 0;
 }
 
 // MK_PRECOND_FP32=0 keeps the V-cycle in fp64
