@@ -651,6 +651,15 @@ static __global__ void k_narrow_vector_st(int n, const T* __restrict__ in, Tlo* 
 // cancel to ~1e-6 of the diagonal in fp32), not from the coarse solve -- while the conversions cost 4 % of the step. Hence disabled
 // (hand-off level beyond any hierarchy depth); the fp32 cycle is still the faster one overall (field solve -23 %, IGM solve -3 %).
 constexpr int kMixedHandoffLevel = 99;
+// MK_FP64_TAIL=k overrides it at run time: k > 0 = hand-off level k, k < 0 counts from the coarsest level (-1: only the coarsest dense
+// solve runs in fp64). The coarsest IGM operator has a condition number of 5e6 (4.8e8 with typed aggregation) at 1M vertices, beyond
+// what an fp32 inverse resolves.
+inline int mixed_handoff_level(int nl) {
+    int k = kMixedHandoffLevel;
+    if (const char* e = getenv("MK_FP64_TAIL")) k = atoi(e);
+    if (k < 0) k = nl + k;
+    return (k >= 1 && k < nl) ? k : -1;  // -1: everything in fp32
+}
 template <class T>
 struct Fp64Tail : CoarseHandoff<typename LowOf<T>::type> {
     using Tlo = typename LowOf<T>::type;
@@ -753,7 +762,7 @@ inline std::unique_ptr<MixedPrecond<T>> lower_precision(cudaStream_t s, std::uni
     lo.op_complexity = hi.op_complexity;
     lo.grid_complexity = hi.grid_complexity;
     const int nl = (int)hi.lv.size();
-    const int K = nl > kMixedHandoffLevel ? kMixedHandoffLevel : -1;  // -1: hierarchy too shallow, everything in fp32
+    const int K = mixed_handoff_level(nl);  // -1: hierarchy too shallow / no fp64 tail, everything in fp32
     const int n_lo = K > 0 ? K + 1 : nl;
     lo.lv.resize(n_lo);
     for (int l = 0; l < n_lo; l++) {

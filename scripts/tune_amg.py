@@ -30,7 +30,7 @@ X2F.sort_indices()
 UFull.sort_indices()
 for cfg in configs:
     for k in list(os.environ):
-        if k.startswith("MK_AMG_"):
+        if k.startswith("MK_AMG_") or k in ("MK_FP64_TAIL", "MK_PRECOND_FP32"):
             del os.environ[k]
     for k, v in cfg.items():
         os.environ[k] = str(v)
