@@ -483,6 +483,8 @@ struct IgmRun {
     RowBank bank;
     ConstraintSet cs;
     ConstraintProjector proj;
+    ConstraintPrecond cprec;  // MK_IGM_CPREC=1: M^{-1} corrected so that Q z = 0 (igm.cuh)
+    bool use_cprec = false;
     DevBuf<double> qtmp, xS_dev;
     std::vector<double> xS;
     size_t applied = 0;  // constraints already eliminated from x
@@ -504,12 +506,15 @@ struct IgmRun {
         if ((size_t)(m + proj.kmax) * sizeof(double) > 48 * 1024)
             MK_CUDA(cudaFuncSetAttribute(k_project, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((m + proj.kmax) * sizeof(double))));
         MK_CUDA(cudaStreamSynchronize(s));
+        use_cprec = constraint_precond_enabled() && g->precond() != nullptr && m > 0;
+        if (use_cprec) cprec.init(g->precond(), &proj, g->cols, s);
     }
     void reset_constraints() {
         cs.Q.clear();
         cs.beta.clear();
         proj.k = 0;
         applied = 0;
+        cprec.reset();
         g->pcg->invalidate_graph();
     }
     void fetch_xS() {
@@ -533,6 +538,11 @@ struct IgmRun {
             const int j = (int)cs.Q.size() - 1;
             MK_CUDA(cudaMemcpyAsync(proj.Q.p + (size_t)j * proj.m, cs.Q[j].data(), sizeof(double) * proj.m, cudaMemcpyHostToDevice, s));
             MK_CUDA(cudaStreamSynchronize(s));
+            if (use_cprec) {
+                const long before = cprec.setup_launches;
+                cprec.add_column(cs.Q, s);
+                st.kernel_launches += cprec.setup_launches - before;
+            }
             return true;
         }
         return resid <= 10e-7;
@@ -550,7 +560,7 @@ struct IgmRun {
         }
     }
     SolveStats solve(CsrOp<double>* op) {
-        g->pcg->bind(op, g->precond(), &proj);
+        g->pcg->bind(op, use_cprec ? (Precond<double>*)&cprec : g->precond(), &proj);
         SolveStats ss = g->pcg->solve(g->b.p, g->x.p, g->o.tol, g->o.max_iter, false, 16, g->o.use_graph != 0);
         st.outer_iterations++;
         st.inner_iterations += ss.iterations;

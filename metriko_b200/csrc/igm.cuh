@@ -4,6 +4,7 @@
 // projector P = I - Q^T Q) and the re-solve is a warm-started projected PCG on (A0 + 1e-4 I).
 #pragma once
 #include <cmath>
+#include <cstring>
 #include <unordered_map>
 #include <vector>
 
@@ -75,6 +76,149 @@ struct ConstraintProjector : Projector<double> {
         MK_CHECK_LAUNCH();
     }
 };
+
+// ---- constraint preconditioner -------------------------------------------------------------------------------------------------
+// The projected preconditioner P M^{-1} P differs from the inverse of the constrained operator by a term of rank 2k, and PCG pays
+// ~10-20 iterations per constraint for it (more, the better M^{-1} resolves the low modes: profiles/igm_per_solve_iterations_r01_*).
+// The constraint preconditioner removes that term exactly:
+//     z = M^{-1} r - W (Q W)^{-1} Q M^{-1} r,      W = M^{-1} Q^T  (n x k, one V-cycle per added constraint row),
+// so that Q z = 0 and the preconditioned operator on the feasible subspace is as well conditioned as M^{-1} A is on the whole space.
+// CPU mirror (65k vertices, Poisson + 16 re-solves): 1101 -> 710 iterations, with typed aggregation 1374 -> 630.
+constexpr int kCprecMax = 32;  // constraints beyond this many are left to the projector alone
+
+// y = (Q W)^{-1} Q z_S: one CTA (Q is k x m over the support S, Sinv is k x k with leading dimension ld)
+static __global__ void __launch_bounds__(kThreads) k_cprec_coef(int k, int m, const int* __restrict__ S, const double* __restrict__ Q,
+                                                        const double* __restrict__ Sinv, int ld, const double* __restrict__ z,
+                                                        double* __restrict__ y, const PcgState* st) {
+    extern __shared__ double sm[];
+    if (st && st->done) return;
+    double* vS = sm;     // m
+    double* t = sm + m;  // k
+    for (int s = threadIdx.x; s < m; s += blockDim.x) vS[s] = z[S[s]];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int j = wid; j < k; j += nw) {
+        double a = 0.0;
+        for (int s = lane; s < m; s += 32) a += Q[(size_t)j * m + s] * vS[s];
+        a = warp_sum(a);
+        if (lane == 0) t[j] = a;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        double a = 0.0;
+        for (int j = 0; j < k; j++) a += Sinv[(size_t)i * ld + j] * t[j];
+        y[i] = a;
+    }
+}
+
+// z -= sum_j y_j W_j (W column-major n x k)
+static __global__ void __launch_bounds__(kThreads) k_cprec_axpy(int n, int k, const double* __restrict__ W, const double* __restrict__ y,
+                                                        double* __restrict__ z, const PcgState* st) {
+    __shared__ double c[kCprecMax];
+    if (st && st->done) return;
+    if ((int)threadIdx.x < k) c[threadIdx.x] = y[threadIdx.x];
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double a = z[i];
+#pragma unroll 4
+        for (int j = 0; j < k; j++) a -= c[j] * ld_ro(W + (size_t)j * n + i);
+        z[i] = a;
+    }
+}
+
+// v[S[i]] = q[i] (v zeroed before)
+static __global__ void k_scatter(int m, const int* __restrict__ S, const double* __restrict__ q, double* __restrict__ v) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) v[S[i]] = q[i];
+}
+
+struct ConstraintPrecond : Precond<double> {
+    Precond<double>* inner = nullptr;
+    ConstraintProjector* proj = nullptr;
+    int n = 0, k = 0;
+    DevBuf<double> W, Sinv, y, qfull, wS;
+    DevBuf<PcgState> unit;                // rr = 1, done = 0: solver state for V-cycle applications outside a solve
+    std::vector<std::vector<double>> WS;  // host copies of W_j restricted to the support
+    long setup_launches = 0;
+
+    void init(Precond<double>* inner_, ConstraintProjector* proj_, int n_, cudaStream_t s) {
+        inner = inner_; proj = proj_; n = n_; k = 0;
+        W.alloc((size_t)n * kCprecMax);
+        Sinv.alloc((size_t)kCprecMax * kCprecMax);
+        y.alloc(kCprecMax);
+        qfull.alloc(n);
+        wS.alloc(std::max(proj->m, 1));
+        unit.alloc(1);
+        PcgState h;
+        std::memset(&h, 0, sizeof(h));
+        h.rr = 1.0; h.rho = 1.0; h.bnorm2 = 1.0;
+        unit.upload(&h, 1, s);
+        if ((size_t)(proj->m + kCprecMax) * sizeof(double) > 48 * 1024)
+            MK_CUDA(cudaFuncSetAttribute(k_cprec_coef, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((proj->m + kCprecMax) * sizeof(double))));
+        MK_CUDA(cudaStreamSynchronize(s));
+    }
+    void reset() { k = 0; WS.clear(); }
+    // column j = M^{-1} q_j for the constraint row just appended to `Qh` (rows 0..j are on the device in proj->Q); rebuilds (Q W)^{-1}
+    void add_column(const std::vector<std::vector<double>>& Qh, cudaStream_t s) {
+        const int j = (int)Qh.size() - 1, m = proj->m;
+        if (j != k || j >= kCprecMax) return;  // beyond the capacity: the projector alone handles the row
+        qfull.zero(s);
+        k_scatter<<<(m + 127) / 128, 128, 0, s>>>(m, proj->S.p, proj->Q.p + (size_t)j * m, qfull.p);
+        inner->apply(qfull.p, W.p + (size_t)j * n, unit.p, s);
+        k_gather<<<(m + 127) / 128, 128, 0, s>>>(m, proj->S.p, W.p + (size_t)j * n, wS.p);
+        MK_CHECK_LAUNCH();
+        WS.emplace_back(m);
+        wS.download(WS.back().data(), m, s);
+        MK_CUDA(cudaStreamSynchronize(s));
+        setup_launches += inner->launches_per_apply() + 2;
+        const int kk = j + 1;
+        std::vector<double> A((size_t)kk * kk), I((size_t)kk * kk, 0.0);
+        for (int a = 0; a < kk; a++)
+            for (int b = 0; b < kk; b++) {
+                double d = 0;
+                for (int t = 0; t < m; t++) d += Qh[a][t] * WS[b][t];
+                A[(size_t)a * kk + b] = d;
+            }
+        for (int a = 0; a < kk; a++) I[(size_t)a * kk + a] = 1.0;
+        // Gauss-Jordan with partial pivoting (kk <= 32)
+        for (int c = 0; c < kk; c++) {
+            int piv = c;
+            for (int r = c + 1; r < kk; r++)
+                if (std::fabs(A[(size_t)r * kk + c]) > std::fabs(A[(size_t)piv * kk + c])) piv = r;
+            if (!(std::fabs(A[(size_t)piv * kk + c]) > 0.0)) return;  // singular: keep the previous k (projector still exact)
+            if (piv != c)
+                for (int b = 0; b < kk; b++) { std::swap(A[(size_t)piv * kk + b], A[(size_t)c * kk + b]); std::swap(I[(size_t)piv * kk + b], I[(size_t)c * kk + b]); }
+            const double inv = 1.0 / A[(size_t)c * kk + c];
+            for (int b = 0; b < kk; b++) { A[(size_t)c * kk + b] *= inv; I[(size_t)c * kk + b] *= inv; }
+            for (int r = 0; r < kk; r++) {
+                if (r == c) continue;
+                const double f = A[(size_t)r * kk + c];
+                if (f == 0.0) continue;
+                for (int b = 0; b < kk; b++) { A[(size_t)r * kk + b] -= f * A[(size_t)c * kk + b]; I[(size_t)r * kk + b] -= f * I[(size_t)c * kk + b]; }
+            }
+        }
+        std::vector<double> padded((size_t)kCprecMax * kCprecMax, 0.0);
+        for (int a = 0; a < kk; a++)
+            for (int b = 0; b < kk; b++) padded[(size_t)a * kCprecMax + b] = I[(size_t)a * kk + b];
+        Sinv.upload(padded.data(), padded.size(), s);
+        MK_CUDA(cudaStreamSynchronize(s));
+        k = kk;
+    }
+    void apply(const double* r, double* z, const PcgState* st, cudaStream_t s) override {
+        inner->apply(r, z, st, s);
+        if (k == 0) return;
+        k_cprec_coef<<<1, kThreads, (size_t)(proj->m + k) * sizeof(double), s>>>(k, proj->m, proj->S.p, proj->Q.p, Sinv.p, kCprecMax, z, y.p, st);
+        k_cprec_axpy<<<stream_grid(n), kThreads, 0, s>>>(n, k, W.p, y.p, z, st);
+        MK_CHECK_LAUNCH();
+    }
+    int launches_per_apply() const override { return inner->launches_per_apply() + (k ? 2 : 0); }
+};
+
+// MK_IGM_CPREC=1 switches the constraint preconditioner on (off by default until it is measured on the device)
+inline bool constraint_precond_enabled() {
+    const char* e = getenv("MK_IGM_CPREC");
+    return e && std::strcmp(e, "1") == 0;
+}
 
 // Host-side bookkeeping of the constraint rows restricted to the support S (tiny dense algebra, exact to round-off).
 struct ConstraintSet {
