@@ -813,12 +813,15 @@ inline std::unique_ptr<MixedPrecond<T>> lower_precision(cudaStream_t s, std::uni
     return mp;
 }
 
-// MK_AMG_TYPED=1 switches the typed aggregation of the IGM hierarchy on (u- and v-type dofs never share an aggregate). Off by default:
-// it saves ~20 % of the PCG iterations up to 262k vertices (CPU mirror and device) but costs +44 % at 1M vertices on the device
-// (2215 against 1537 inner iterations, profiles/amg_tuning_r01g_typed_degcoarse.txt) -- not understood yet, see profiles/README.md.
+// Typed aggregation of the IGM hierarchy (u- and v-type dofs never share an aggregate). It resolves the two near-kernel vectors better
+// (Poisson solve 116 -> 100 iterations at 1M vertices), which only pays together with the constraint preconditioner (igm.cuh): under the
+// plain projected preconditioner every added rounding constraint then costs 10-20 extra iterations (2215 against 1537 in total), with
+// it the 1M-vertex rounding loop needs 698 instead of 841 (profiles/cprec_probe_r01.txt). Default: on iff MK_IGM_CPREC is not 0;
+// MK_AMG_TYPED=0 / 1 forces it.
 inline bool typed_aggregation() {
-    const char* e = getenv("MK_AMG_TYPED");
-    return e && std::strcmp(e, "1") == 0;
+    if (const char* e = getenv("MK_AMG_TYPED")) return std::strcmp(e, "0") != 0;
+    const char* c = getenv("MK_IGM_CPREC");
+    return !(c && std::strcmp(c, "0") == 0);
 }
 
 // MK_PRECOND_FP32=0 keeps the V-cycle in fp64

@@ -214,10 +214,11 @@ struct ConstraintPrecond : Precond<double> {
     int launches_per_apply() const override { return inner->launches_per_apply() + (k ? 2 : 0); }
 };
 
-// MK_IGM_CPREC=1 switches the constraint preconditioner on (off by default until it is measured on the device)
+// On by default (1M vertices, B200: IGM solve 594 -> 412 ms, 1347 -> 841 inner iterations, same integers, fullx within 1.5e-9;
+// profiles/cprec_probe_r01.txt); MK_IGM_CPREC=0 restores the projected preconditioner P M^{-1} P.
 inline bool constraint_precond_enabled() {
     const char* e = getenv("MK_IGM_CPREC");
-    return e && std::strcmp(e, "1") == 0;
+    return !(e && std::strcmp(e, "0") == 0);
 }
 
 // Host-side bookkeeping of the constraint rows restricted to the support S (tiny dense algebra, exact to round-off).
