@@ -117,3 +117,35 @@ def test_full_size_rounding_properties(ctx):
     out2 = api.IgmProblem(ctx, inp["X2F"], inp["UFull"], inp["F2"], inp["length"], tol=1e-9).round(
         inp["fixedIdcs"], inp["fixedVals"], inp["singularIdcs"], inp["integerIdcs"], True, False)
     assert _ints(out2) == _ints(out) and np.abs(out2["fullx"] - out["fullx"]).max() < 1e-5
+
+
+def test_constraint_preconditioner_against_projected(ctx):
+    """The defaults (constraint preconditioner z = M^-1 r - W (Q W)^-1 Q M^-1 r + typed aggregation, csrc/igm.cuh) against the projected
+    preconditioner P M^-1 P with untyped aggregates (MK_IGM_CPREC=0) on a 4,098-vertex sphere: identical integers, fullx within
+    1e-7, clearly fewer inner iterations (measured on the B200: 762 -> 410; 1,347 -> 698 at 1M vertices, profiles/cprec_probe_r01.txt)."""
+    import os
+    s = Session().make_sphere(8, 5, bump=0.08)
+    fi = s.field_inputs()
+    F = api.FaceRosyField(ctx, fi["face2half"], fi["next"], fi["twin"], fi["face"], fi["heArgOnFace"], fi["faceArea"], 4)
+    z = F.solveSmallestEig(oracle.random_u0(s.dims["nF"], 0), 50)
+    s.field_post(z, 4, "curl")
+    s.igm_setup(0.02)
+    inp = s.igm_inputs()
+    outs = []
+    for env in ({"MK_IGM_CPREC": "0"}, {}):
+        saved = {k: os.environ.pop(k, None) for k in ("MK_IGM_CPREC", "MK_AMG_TYPED")}
+        os.environ.update(env)
+        try:
+            prob = api.IgmProblem(ctx, inp["X2F"], inp["UFull"], inp["F2"], inp["length"])
+            outs.append(prob.round(inp["fixedIdcs"], inp["fixedVals"], inp["singularIdcs"], inp["integerIdcs"], True, False))
+            prob.close()
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+            os.environ.update({k: v for k, v in saved.items() if v is not None})
+    old, new = outs
+    assert old["success"] and new["success"]
+    assert _ints(old) == _ints(new)
+    assert np.abs(old["fullx"] - new["fullx"]).max() < 1e-7
+    assert max(old["stats"]["relres_max"], new["stats"]["relres_max"]) <= 1.001e-10
+    assert new["stats"]["inner_iterations"] < 0.8 * old["stats"]["inner_iterations"]
