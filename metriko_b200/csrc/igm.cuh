@@ -83,7 +83,7 @@ struct ConstraintProjector : Projector<double> {
 // The constraint preconditioner removes that term exactly:
 //     z = M^{-1} r - W (Q W)^{-1} Q M^{-1} r,      W = M^{-1} Q^T  (n x k, one V-cycle per added constraint row),
 // so that Q z = 0 and the preconditioned operator on the feasible subspace is as well conditioned as M^{-1} A is on the whole space.
-// CPU mirror (65k vertices, Poisson + 16 re-solves): 1101 -> 710 iterations, with typed aggregation 1374 -> 630.
+// CPU mirror (tests/tools/mirror_rounding.py, 65k vertices, Poisson + 16 re-solves): 985 -> 693 iterations, with typed aggregation 1179 -> 580.
 constexpr int kCprecMax = 32;  // constraints beyond this many are left to the projector alone
 
 // y = (Q W)^{-1} Q z_S: one CTA (Q is k x m over the support S, Sinv is k x k with leading dimension ld)

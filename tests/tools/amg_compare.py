@@ -1,8 +1,9 @@
 """Development tool: PCG iteration counts of the mirrored V-cycle for different aggregation modes (CPU only)."""
 import os, sys, time
 import numpy as np, scipy.sparse as sp
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle
 from amg_mirror import VCycle, pcg, describe
 from metriko_b200 import capi

@@ -1,7 +1,8 @@
 """Exploratory GPU run: field + IGM parity against the oracle on small meshes, SpMV bandwidth on a large one."""
 import json, os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
 from metriko_b200.hostglue import Session
 from metriko_b200 import api, capi
 import oracle
