@@ -118,7 +118,7 @@ def iterative_rounding(fixedIdcs, fixedVals, singularIdcs, integerIdcs, length, 
 
 
 def iterative_rounding_x2f(fixedIdcs, fixedVals, singularIdcs, integerIdcs, length, UFull, X2F, N, n, seamless, roundSeams, F2,
-                           ni_mode="lm", stats=None):
+                           ni_mode="lm", stats=None, localInjectivity=False, iter_cb=None):
     """The body of ir.h:33-113. G2 enters the algorithm only through X2F = (G2 UFull).pruned() (ir_init.h:173,
     ir_loop.h:123; gInteg * UExt = [-length X2F | I], ir_init.h:40-55), so X2F is the operator input here.
     Returns dict(success, fullx, x_small, fixedIdcs, fixedVals, n_solves, min_margin, ...).
@@ -127,6 +127,11 @@ def iterative_rounding_x2f(fixedIdcs, fixedVals, singularIdcs, integerIdcs, leng
     ni_mode = "closed" : uses the closed form the linear LM converges to:
                          x = Poisson solution, f* = (1e8 * length * B x + F2) / (1e8 + 1). Agreement of the two
                          modes is ~1e-8 relative (the reference's own round-off floor) and is tested on small inputs.
+
+    localInjectivity = True (example_qgp / example_qex flags): every LM carries the per-face injectivity barrier
+    (oracle/barrier.py; iter_rounding_common.h:70-85, weight wBarrier = 1e-4, ir_init.h:87) and starts from lambda = 0.01
+    (ir.h:57,96,102); the NI stage always runs the LM (there is no closed form) and stops as soon as iter_cb(fullx) is true
+    (ir_init.h:28; the caller's locally_injectivity_check, integ.ipp:46-63); with !seamless the NI result is returned (ir.h:86-88).
     """
     if stats is None:
         stats = {}
@@ -141,9 +146,16 @@ def iterative_rounding_x2f(fixedIdcs, fixedVals, singularIdcs, integerIdcs, leng
     XSmall, X2F_nolen = naive_poisson(X2F, UFull, F2, fixedIdcs, fixedVals, length)
     x0_full = UFull @ XSmall
     out = dict(success=True, fixedIdcs=[], fixedVals=[], n_solves=0, min_margin=np.inf, x0_full=x0_full, x_poisson=XSmall)
-    if not seamless:  # ir.h:78-81 (localInjectivity false)
+    if not seamless and not localInjectivity:  # ir.h:78-81
         out.update(fullx=x0_full, x_small=XSmall)
         return out
+    barrier = None
+    wBarrier = 1e-4  # ir_init.h:87
+    lam0 = 0.01 if localInjectivity else 0.0  # ir.h:57
+    if localInjectivity:
+        from .barrier import InjectiveBarrier
+        barrier = InjectiveBarrier(N, l1 // (2 * N), F2)  # ir.h:60
+        ni_mode = "lm"
 
     # ---- NI stage (Integration weights ir_init.h:87: wInteg = 10e3, wConst = 10e3, wClose = 1)
     wInteg, wConst, wClose = 10e3, 10e3, 1.0
@@ -156,17 +168,33 @@ def iterative_rounding_x2f(fixedIdcs, fixedVals, singularIdcs, integerIdcs, leng
         gConst = sel @ UExt * wConst
         Jni = sp.vstack([gInteg, gClose, gConst]).tocsr()
 
-        def obj_ni(xf_):  # ir_init.h:60-72 + ir_common.h:87-93
+        def obj_ni(xf_):  # ir_init.h:60-72 + ir_common.h:60-94
             xf = UExt @ xf_
             x, f = xf[:nfull], xf[nfull:]
             fInteg = f - length * (B @ xf_[:cols])  # = f - length G2 x
             fClose = f - F2
             fConst = x[fixedIdcs] - fixedVals
-            return np.concatenate([fInteg * wInteg, fClose * wClose, fConst * wConst])
+            parts = [fInteg * wInteg, fClose * wClose, fConst * wConst]
+            if barrier is not None:
+                parts.append(barrier.update(f, False)[0] * wBarrier)
+            return np.concatenate(parts)
 
-        xf, _ = lm_solve(obj_ni, lambda _x: Jni, np.concatenate([XSmall, F2]), 0.0, 100, 10e-10, 10e-10, stats=stats)
+        def jac_ni(xf_):
+            if barrier is None:
+                return Jni
+            f = (UExt @ xf_)[nfull:]
+            # loop = false: gBarrier * imageField * gClose * wInteg (sic, ir_common.h:79)
+            return sp.vstack([Jni, barrier.jacobian_block(f, gClose, wInteg)]).tocsr()
+
+        post = None
+        if iter_cb is not None:
+            post = lambda xf_: bool(iter_cb((UExt @ xf_)[:nfull]))  # ir_init.h:28
+        xf, _ = lm_solve(obj_ni, jac_ni, np.concatenate([XSmall, F2]), lam0, 100, 10e-10, 10e-10, post_iteration=post, stats=stats)
         X_ = xf[:cols]
         F2_ = xf[cols:]
+        if not seamless:  # ir.h:86-88
+            out.update(fullx=UFull @ X_, x_small=X_)
+            return out
     else:
         X_ = XSmall
         F2_ = (1e8 * length * (B @ XSmall) + F2) / (1e8 + 1.0)
@@ -227,9 +255,19 @@ def iterative_rounding_x2f(fixedIdcs, fixedVals, singularIdcs, integerIdcs, leng
 
         def obj_si(xs, xPrev=xPrev, fi=fi, fv=fv):  # ir_loop.h:77-86
             Xf = UFull @ xs
-            return np.concatenate([(X2F @ xs - F2_) * wInteg, (xs - xPrev) * wClose, (Xf[fi] - fv) * wConst])
+            field = X2F @ xs
+            parts = [(field - F2_) * wInteg, (xs - xPrev) * wClose, (Xf[fi] - fv) * wConst]
+            if barrier is not None:
+                parts.append(barrier.update(field, False)[0] * wBarrier)
+            return np.concatenate(parts)
 
-        x_last, _ = lm_solve(obj_si, lambda _x, Jsi=Jsi: Jsi, xInit, 0.0, 100, 1e-7, 1e-7, stats=stats)
+        def jac_si(xs, Jsi=Jsi):
+            if barrier is None:
+                return Jsi
+            # loop = true: gBarrier * imageField * X2F * wBarrier (ir_common.h:78)
+            return sp.vstack([Jsi, barrier.jacobian_block(X2F @ xs, X2F, wBarrier)]).tocsr()
+
+        x_last, _ = lm_solve(obj_si, jac_si, xInit, lam0, 100, 1e-7, 1e-7, stats=stats)  # lambda reset per rounding step, ir.h:102
         out["n_solves"] += 1
         # post_checking (ir_loop.h:89-100)
         fullx = UFull @ x_last
