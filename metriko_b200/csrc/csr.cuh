@@ -38,6 +38,9 @@ constexpr int kRowModeMean = 40;          // mean row length above which SELL is
 constexpr double kMaxSellPadding = 1.5;   // stored / true entries above which SELL is dropped for the lanes-per-row kernel ...
 constexpr double kRowModeMinMean = 8.0;   // ... unless the rows are this short (a thread per row then beats lanes per row even with padding)
 constexpr int kRowModeLong = 512;         // row mode: rows longer than this get a CTA of their own
+constexpr int kRowModeSmallRows = 4096;   // operators this small are latency-bound: lanes per row (one load round trip per ~32 entries) instead
+                                          // of a thread per row (one per entry). profiles/launches_r01f / r01g: the fused kernel on the
+                                          // ~2,100-row, 29-entries-per-row IGM level takes 8.0-8.5 us as k_spmv_rows<.., 32> and 13.3 us as k_spmv_sell
 
 // ---- CSR -> SELL-32 conversion on the device (once per operator) ----
 // one warp per slice: width = longest non-long row, long rows flagged in a bit word and appended to the long-row list
@@ -146,7 +149,7 @@ inline void build_sell(DeviceCsr<T>& A, cudaStream_t s) {
     scan_lengths(kLongRow, tot, nl);
     A.padding = A.nnz ? (double)tot / (double)A.nnz : 1.0;  // long rows count as stored 0 / true len: only makes SELL look better
     const double mean = (double)A.nnz / rows;
-    if (mean > kRowModeMean || (A.padding > kMaxSellPadding && mean >= kRowModeMinMean)) {
+    if (mean > kRowModeMean || ((A.padding > kMaxSellPadding || rows <= kRowModeSmallRows) && mean >= kRowModeMinMean)) {
         A.row_mode = true;
         A.row_lanes = mean <= 6 ? 4 : (mean <= 12 ? 8 : (mean <= 24 ? 16 : 32));
         const double pad = A.padding;
