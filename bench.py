@@ -33,6 +33,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(1, os.path.join(ROOT, "tests"))  # tests/hostglue: the synthetic-input generator (host stages of the reference)
 
 METRIC = "field+IGM solve throughput at 1M verts (ms_per_step = solve ms)"
 UNIT = "verts/s"
@@ -51,7 +52,7 @@ def log(*a):
 # workload generation (host glue = the reference's unchanged host stages; untimed)
 # ---------------------------------------------------------------------------------------------------------------------
 def make_session(levels: int, rank: int):
-    from metriko_b200.hostglue import Session
+    from hostglue import Session
     return Session().make_sphere(8, levels, bump=0.08, phase=0.37 * rank)
 
 

@@ -1,7 +1,8 @@
 """In-tree builds of the native libraries (no JIT cache: the .so files travel with the repo snapshot).
 
   libmetriko_b200.so     CUDA kernels + solver drivers + the C-ABI (include/metriko_b200.h), sm_100a only
-  libmetriko_hostglue.so host-side restatement of the reference's unchanged bookkeeping stages (CPU only)
+  tests/hostglue/libmetriko_hostglue.so  test-input generator: host-side restatement of the reference's unchanged bookkeeping stages
+                         (CPU only; NOT part of the product package -- it lives under tests/ and is linked by nothing in metriko_b200/)
 """
 from __future__ import annotations
 
@@ -12,7 +13,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
-HOSTGLUE = os.path.join(PKG, "hostglue")
+HOSTGLUE = os.path.join(ROOT, "tests", "hostglue")
 LIB_CUDA = os.path.join(PKG, "libmetriko_b200.so")
 LIB_HOST = os.path.join(HOSTGLUE, "libmetriko_hostglue.so")
 

@@ -28,13 +28,19 @@ class _Factor:
 
 
 def lm_solve(objective, jacobian, x0, lam0=0.0, max_iterations=100, func_tol=10e-10, foo_tol=10e-10, post_iteration=None,
-             stats=None):
+             stats=None, reuse_factor=False):
     """LMSolver::solve (lm.h:140-231) with DiagonalDamping (lm.h:13-88), verbose = false.
 
     objective(x) -> E vector; jacobian(x) -> sparse J. Quirks kept: the first-order-optimality test never
     breaks when not verbose (lm.h:171-177); `|direction| < funcTol` returns True with x = prevx
     (lm.h:193-197); a small energy change breaks and returns False (lm.h:208-211); lambda * 10 stays 0
-    when lam0 = 0 so a non-decreasing step re-solves the same system until maxIterations (lm.h:58-62)."""
+    when lam0 = 0 so a non-decreasing step re-solves the same system until maxIterations (lm.h:58-62).
+
+    reuse_factor = True skips a factorisation whose input is BIT-IDENTICAL to the previous one of this call: with lambda = 0 and a
+    constant Jacobian (the same matrix object, linear problem) dampJ^T dampJ does not change, SuperLU is deterministic, so the factor --
+    and therefore every iterate -- is the same to the last bit (tests/test_oracle.py asserts it). It only removes redundant work; it is
+    what makes the oracle affordable at the BASELINE sizes (tests/golden/make_golden_large.py). `factorizations` still counts the
+    factorisations the reference would perform; `factorizations_done` the ones actually run."""
     LS = _Factor()
     lam = lam0
     prevx = np.array(x0, np.float64)
@@ -50,13 +56,19 @@ def lm_solve(objective, jacobian, x0, lam0=0.0, max_iterations=100, func_tol=10e
     dampJ = damp(J)
     it = 0
     ret = False
+    factored_J = None  # the Jacobian object the current factor was computed from (only tracked while lambda == 0)
+    skipped = 0
     while True:
         rhs = -(J.T @ E)
         if np.max(np.abs(rhs)) < foo_tol:
             x = prevx.copy()  # no break unless verbose
-        if not LS.factorize((dampJ.T @ dampJ).tocsc()):
+        if reuse_factor and lam == 0.0 and factored_J is J and LS.lu is not None:
+            skipped += 1
+        elif not LS.factorize((dampJ.T @ dampJ).tocsc()):
             ret = False
             break
+        else:
+            factored_J = J if lam == 0.0 else None
         direction = LS.solve(rhs)
         if np.linalg.norm(direction) < func_tol:
             x = prevx.copy()
@@ -88,7 +100,8 @@ def lm_solve(objective, jacobian, x0, lam0=0.0, max_iterations=100, func_tol=10e
             ret = False
             break
     if stats is not None:
-        stats["factorizations"] = stats.get("factorizations", 0) + LS.count
+        stats["factorizations"] = stats.get("factorizations", 0) + LS.count + skipped
+        stats["factorizations_done"] = stats.get("factorizations_done", 0) + LS.count
         stats["lm_iterations"] = stats.get("lm_iterations", 0) + it
     return x, ret
 
@@ -118,7 +131,7 @@ def iterative_rounding(fixedIdcs, fixedVals, singularIdcs, integerIdcs, length, 
 
 
 def iterative_rounding_x2f(fixedIdcs, fixedVals, singularIdcs, integerIdcs, length, UFull, X2F, N, n, seamless, roundSeams, F2,
-                           ni_mode="lm", stats=None, localInjectivity=False, iter_cb=None):
+                           ni_mode="lm", stats=None, localInjectivity=False, iter_cb=None, reuse_factor=False, progress=None):
     """The body of ir.h:33-113. G2 enters the algorithm only through X2F = (G2 UFull).pruned() (ir_init.h:173,
     ir_loop.h:123; gInteg * UExt = [-length X2F | I], ir_init.h:40-55), so X2F is the operator input here.
     Returns dict(success, fullx, x_small, fixedIdcs, fixedVals, n_solves, min_margin, ...).
@@ -189,7 +202,8 @@ def iterative_rounding_x2f(fixedIdcs, fixedVals, singularIdcs, integerIdcs, leng
         post = None
         if iter_cb is not None:
             post = lambda xf_: bool(iter_cb((UExt @ xf_)[:nfull]))  # ir_init.h:28
-        xf, _ = lm_solve(obj_ni, jac_ni, np.concatenate([XSmall, F2]), lam0, 100, 10e-10, 10e-10, post_iteration=post, stats=stats)
+        xf, _ = lm_solve(obj_ni, jac_ni, np.concatenate([XSmall, F2]), lam0, 100, 10e-10, 10e-10, post_iteration=post, stats=stats,
+                         reuse_factor=reuse_factor)
         X_ = xf[:cols]
         F2_ = xf[cols:]
         if not seamless:  # ir.h:86-88
@@ -267,7 +281,9 @@ def iterative_rounding_x2f(fixedIdcs, fixedVals, singularIdcs, integerIdcs, leng
             # loop = true: gBarrier * imageField * X2F * wBarrier (ir_common.h:78)
             return sp.vstack([Jsi, barrier.jacobian_block(X2F @ xs, X2F, wBarrier)]).tocsr()
 
-        x_last, _ = lm_solve(obj_si, jac_si, xInit, lam0, 100, 1e-7, 1e-7, stats=stats)  # lambda reset per rounding step, ir.h:102
+        x_last, _ = lm_solve(obj_si, jac_si, xInit, lam0, 100, 1e-7, 1e-7, stats=stats, reuse_factor=reuse_factor)  # lambda reset per rounding step, ir.h:102
+        if progress is not None:
+            progress(f"re-solve {out['n_solves'] + 1}: dof {idx} -> {val} (minDif {minDif:.3e}), {len(left)} left")
         out["n_solves"] += 1
         # post_checking (ir_loop.h:89-100)
         fullx = UFull @ x_last

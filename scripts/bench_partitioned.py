@@ -16,9 +16,10 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(1, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 from metriko_b200 import capi  # noqa: E402
 from metriko_b200.dist import DistContext, DistFaceField  # noqa: E402
-from metriko_b200.hostglue import Session  # noqa: E402
+from hostglue import Session  # noqa: E402
 
 
 def main():

@@ -13,8 +13,9 @@ import numpy as np
 import scipy.sparse as sp
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(1, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 from metriko_b200 import api, capi  # noqa: E402
-from metriko_b200.hostglue import Session  # noqa: E402
+from hostglue import Session  # noqa: E402
 
 FIELD_KEYS = ("face2half", "next", "twin", "face", "heArgOnFace", "faceArea")
 IGM_KEYS = ("fixedIdcs", "fixedVals", "singularIdcs", "integerIdcs", "F2")

@@ -8,8 +8,9 @@ import time
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(1, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 from metriko_b200 import api, capi  # noqa: E402
-from metriko_b200.hostglue import Session  # noqa: E402
+from hostglue import Session  # noqa: E402
 
 FIELD_KEYS = ("face2half", "next", "twin", "face", "heArgOnFace", "faceArea")
 levels = int(sys.argv[1]) if len(sys.argv) > 1 else 9

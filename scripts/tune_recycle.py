@@ -2,8 +2,9 @@
 import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(1, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 from metriko_b200 import api, capi
-from metriko_b200.hostglue import Session
+from hostglue import Session
 FIELD_KEYS = ("face2half", "next", "twin", "face", "heArgOnFace", "faceArea")
 ctx = capi.Context(0)
 s = Session().make_sphere(8, int(sys.argv[1]) if len(sys.argv) > 1 else 9, bump=0.08)

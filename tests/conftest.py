@@ -7,6 +7,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+if os.path.join(ROOT, "tests") not in sys.path:
+    sys.path.insert(1, os.path.join(ROOT, "tests"))
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
@@ -33,5 +35,5 @@ def ctx():
 
 @pytest.fixture(scope="session")
 def ico4():
-    from metriko_b200.hostglue import Session
+    from hostglue import Session
     return Session().make_sphere(20, 4, bump=0.08)

@@ -15,8 +15,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
+sys.path.insert(1, os.path.join(ROOT, "tests"))
 import oracle  # noqa: E402
-from metriko_b200.hostglue import Session  # noqa: E402
+from hostglue import Session  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 

@@ -1,6 +1,7 @@
 """ctypes wrapper of libmetriko_hostglue.so: the reference's unchanged host stages (mesh topology,
 matching / seam / combing, IGM index bookkeeping) restated so that hot-path inputs can be generated in
-this image (no Eigen / libigl). CPU only; not on the GPU hot path and not part of the drop-in."""
+this image (no Eigen / libigl). CPU only; TEST-INPUT INFRASTRUCTURE: it lives under tests/, is not part of the product package
+(metriko_b200/) and is linked by nothing there; tests, bench.py and smoke() use it to generate the arrays a metriko host would pass."""
 from __future__ import annotations
 
 import ctypes as C
@@ -19,7 +20,7 @@ def _lib():
     if _LIB is None:
         path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmetriko_hostglue.so")
         if not os.path.exists(path):
-            from .. import build
+            from metriko_b200 import build
             build.build_hostglue()
         L = C.CDLL(path)
         L.hg_session_new.restype = C.c_void_p

@@ -31,7 +31,7 @@ def test_galerkin_products_real_and_complex():
 def test_dense_dofs_are_carried_as_singletons():
     """The IGM operator has a few rows with hundreds to thousands of entries (seam translations / constraint-kernel
     columns). They must reach the coarsest level as their own unknowns instead of swallowing whole aggregates."""
-    from metriko_b200.hostglue import Session
+    from hostglue import Session
     s = Session().make_sphere(8, 5, bump=0.08)
     fi = s.field_inputs()
     nF = s.dims["nF"]

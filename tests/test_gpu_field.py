@@ -7,7 +7,7 @@ import pytest
 import oracle
 from conftest import load_golden
 from metriko_b200 import api
-from metriko_b200.hostglue import Session
+from hostglue import Session
 from oracle.field import field_angle_error
 
 pytestmark = pytest.mark.gpu

@@ -9,7 +9,7 @@ import scipy.sparse.linalg as spla
 import oracle
 from conftest import load_golden
 from metriko_b200 import api
-from metriko_b200.hostglue import Session
+from hostglue import Session
 
 pytestmark = pytest.mark.gpu
 

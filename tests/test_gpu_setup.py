@@ -10,7 +10,7 @@ import scipy.sparse as sp
 import oracle
 from conftest import load_golden
 from metriko_b200 import api, capi
-from metriko_b200.hostglue import Session
+from hostglue import Session
 
 pytestmark = pytest.mark.gpu
 

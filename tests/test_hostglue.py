@@ -3,7 +3,7 @@ SURVEY.md Appendix A and the reference's own runtime invariants.""
 import numpy as np
 import pytest
 
-from metriko_b200.hostglue import Session
+from hostglue import Session
 
 
 @pytest.mark.parametrize("maker,euler", [(lambda: Session().make_sphere(20, 2), 2), (lambda: Session().make_sphere(8, 3), 2),

@@ -3,7 +3,8 @@ import json, os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-from metriko_b200.hostglue import Session
+sys.path.insert(1, os.path.join(ROOT, "tests"))
+from hostglue import Session
 from metriko_b200 import api, capi
 import oracle
 from oracle.field import field_angle_error

@@ -10,7 +10,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle
 from amg_mirror import VCycle, describe, rounding_loop
 from metriko_b200 import capi
-from metriko_b200.hostglue import Session
+from hostglue import Session
 
 lv = int(sys.argv[1]) if len(sys.argv) > 1 else 6
 s = Session().make_sphere(8, lv, bump=0.08)
