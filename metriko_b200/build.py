@@ -53,16 +53,37 @@ def build_hostglue(force: bool = False, verbose: bool = False) -> str:
 
 
 def build_cuda(force: bool = False, verbose: bool = False) -> str:
+    """One nvcc -c per .cu in parallel (objects under metriko_b200/build/), then one link. `verbose` keeps the ptxas -v output
+    (registers, spills, shared memory per kernel) in metriko_b200/build/<name>.ptxas.log."""
+    from concurrent.futures import ThreadPoolExecutor
+
     deps = _sources(CSRC, (".cu", ".cuh", ".h", ".hpp", ".cpp")) + _sources(os.path.join(ROOT, "include"), (".h",))
     if not force and _newer(LIB_CUDA, deps):
         return LIB_CUDA
     srcs = _sources(CSRC, (".cu",))
-    cmd = [NVCC, *CUDA_FLAGS, "-shared", "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", LIB_CUDA, *srcs,
-           "-lcudart", "-lgomp"]
-    if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-        print(" ".join(cmd), file=sys.stderr)
+    objdir = os.path.join(PKG, "build")
+    os.makedirs(objdir, exist_ok=True)
+    headers = [d for d in deps if not d.endswith(".cu")]
+
+    def compile_one(src: str) -> str:
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        if not force and _newer(obj, [src] + headers):
+            return obj
+        cmd = [NVCC, *CUDA_FLAGS, "-c", "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", obj, src]
+        if verbose:
+            cmd[1:1] = ["-Xptxas", "-v"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose:
+            with open(obj[:-2] + ".ptxas.log", "w") as fh:
+                fh.write(r.stderr)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise subprocess.CalledProcessError(r.returncode, cmd)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=max(1, min(len(srcs), os.cpu_count() or 1))) as ex:
+        objs = list(ex.map(compile_one, srcs))
+    cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_CUDA, *objs, "-lcudart", "-lgomp"]
     subprocess.run(cmd, check=True)
     return LIB_CUDA
 

@@ -22,6 +22,7 @@
 #include "csr.cuh"
 #include "hostcsr.hpp"
 #include "solver.cuh"
+#include "vtail.cuh"
 
 namespace mk {
 
@@ -459,7 +460,17 @@ __global__ void __launch_bounds__(kThreads) k_cheb_init(int n, const T* __restri
     }
 }
 
-// x (+)= d ; r -= q ; d = c1 d + c2 dinv .* r      (one Chebyshev step after q = A d)
+// d = inv_theta * dinv .* b : the start direction of a zero-guess smoothing (no residual copy: the first fused step reads b itself)
+template <class T>
+__global__ void __launch_bounds__(kThreads) k_start_dir(int n, const T* __restrict__ b, const T* __restrict__ dinv, T* __restrict__ d, double inv_theta,
+                                                        const PcgState* st) {
+    if (st && st->done) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        st_rw(d + i, ST<T>::scale(inv_theta, ld_ro(dinv + i) * ld_ro(b + i)));
+}
+
+// x (+)= d ; r -= q ; d = c1 d + c2 dinv .* r      (one Chebyshev step after q = A d; the partitioned operator, whose SpMV is split
+// around the halo exchange, cannot fuse it)
 template <class T>
 __global__ void __launch_bounds__(kThreads) k_cheb_step(int n, const T* __restrict__ q, const T* __restrict__ dinv, T* __restrict__ r,
                                                         T* __restrict__ x, T* __restrict__ d, double c1, double c2, int first,
@@ -500,7 +511,7 @@ struct AmgLevelDev {
     int n = 0;
     DeviceCsr<T> A;  // unused on level 0 when an external fine operator is given
     DeviceCsr<T> P, R;
-    DevBuf<T> dinv, x, b, r, d, q;
+    DevBuf<T> dinv, x, xo, b, r, d, q;  // x: the iterate of the cycle on this level, xo: its result (the last smoothing kernel writes out of place)
     double lmax = 2.0;
 };
 
@@ -512,12 +523,22 @@ struct CoarseHandoff {
     virtual int launches() const = 0;
 };
 
+// The V-cycle. Schedule per level l (degree k_l Chebyshev smoothing, every smoother step fused into the operator's SpMV, csr.cuh SpmvMode):
+//     pre   : k_l fused steps from a zero guess (the start direction dinv b / theta was written by whoever produced b: the hand-over
+//             kernel on level 0, the restriction above on the others); the last one stores no further direction
+//     down  : b_{l+1} = R r fused with the child's start direction
+//     child : recursion; the levels with <= kTailRows rows run as ONE cluster kernel (vtail.cuh); dense inverse on the coarsest
+//     up    : x += P x_{l+1}
+//     post  : residual + k_l - 1 steps, the last of them writing the result out of place -- k_l SpMVs, not k_l + 1: the step that
+//             would only refresh r and the next direction after the last update is dead code and is not run
+// i.e. 2 k_l + 2 launches per level above the tail (4 + 2 k_l in round 1) and one for the whole tail (was ~8 per level).
 template <class T>
 struct AmgPrecond : Precond<T> {
     using S = typename HostScalar<T>::type;
     AmgParams prm;
     std::vector<AmgLevelDev<T>> lv;
     LinOp<T>* fine_op = nullptr;  // level-0 operator (e.g. the face stencil); falls back to lv[0].A
+    std::unique_ptr<CsrOp<T>> own_op0;
     DevBuf<T> coarse_inv;
     int coarse_n = 0;
     bool coarse_dense = false;
@@ -525,114 +546,237 @@ struct AmgPrecond : Precond<T> {
     ReduceWs dummy_ws{nullptr, nullptr};
     CoarseHandoff<T>* handoff = nullptr;  // levels >= handoff_level are solved by it (lv[handoff_level] only holds x and b)
     int handoff_level = -1;
-    bool level0_initialised = false;      // the caller already wrote lv[0].r = b and lv[0].d = dinv b / theta (fused hand-over kernel)
-    int degree(int l) const { return (l > 0 && prm.cheb_degree_coarse > 0 && !coarsest_smoothing) ? prm.cheb_degree_coarse : prm.cheb_degree; }
-    bool coarsest_smoothing = false;  // the non-dense coarsest level is "solved" by 8 Chebyshev steps (cheb_degree is overridden there)
-    double inv_theta0() const { return 1.0 / (0.5 * (lv[0].lmax + lv[0].lmax / prm.cheb_ratio)); }
+    // coarse tail (vtail.cuh)
+    bool prepared = false;
+    bool allow_tail = true;
+    int first_level = 0;              // levels below it hold no work buffers (the partitioned mode runs level 0 itself)
+    int tail_start = -1;              // first level inside the tail kernel; -1: no tail
+    TailDesc<T> tail{};
+    std::vector<DevBuf<int>> tail_long;
 
-    void apply_A(int l, const T* x, T* y, const PcgState* st, cudaStream_t s) {
-        if (l == 0 && fine_op) fine_op->apply(x, y, const_cast<PcgState*>(st), dummy_ws, s, false);
-        else spmv_plain(lv[l].A, x, y, false, st, s);
+    int degree(int l) const { return (l > 0 && prm.cheb_degree_coarse > 0) ? prm.cheb_degree_coarse : prm.cheb_degree; }
+    double theta(int l) const { return 0.5 * (lv[l].lmax + lv[l].lmax / prm.cheb_ratio); }
+    double delta(int l) const { return 0.5 * (lv[l].lmax - lv[l].lmax / prm.cheb_ratio); }
+    double inv_theta0() const { return 1.0 / theta(0); }
+    // where the zero-guess start direction of level l lives: in the iterate buffer itself for degree 1 (x = d0 needs no copy then)
+    T* start_dir(int l, T* x) { return degree(l) == 1 ? x : lv[l].d.p; }
+    LinOp<T>* op(int l) { return (l == 0 && fine_op) ? fine_op : nullptr; }
+
+    // work buffers + the tail descriptor; called before the first cycle (and before any graph capture: it allocates and synchronises)
+    void prepare(cudaStream_t s) {
+        if (prepared) return;
+        prepared = true;
+        const int nl = (int)lv.size();
+        for (int l = first_level; l < nl; l++) {
+            AmgLevelDev<T>& L = lv[l];
+            if (handoff && l == handoff_level) { if (!L.xo.p) L.xo.alloc(L.n); break; }
+            if (!L.x.p) L.x.alloc(L.n);
+            if (!L.xo.p) L.xo.alloc(L.n);
+            if (!L.b.p && l > 0) L.b.alloc(L.n);
+            if (!L.r.p) L.r.alloc(L.n);
+            if (!L.d.p) L.d.alloc(L.n);
+            if (!L.q.p) L.q.alloc(L.n);
+        }
+        build_tail(s);
     }
 
-    // Chebyshev smoothing on [lmax / ratio, lmax] of D^{-1} A. The step / residual updates are fused into the SpMV kernels when the
-    // level's operator supports it (every operator of this library except the partitioned one): 1 + degree kernels per call.
-    // The direction ping-pongs between L.d and L.q; leaves r = b - A x in L.r.
-    void smooth(int l, const T* b, T* x, bool zero_guess, const PcgState* st, cudaStream_t s) {
-        AmgLevelDev<T>& L = lv[l];
-        const int grid = stream_grid(L.n);
-        const double lmax = L.lmax, lmin = L.lmax / prm.cheb_ratio;
-        const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
-        double rho = 1.0 / sigma;
-        const bool ext = (l == 0 && fine_op);
-        T* d0 = L.d.p;
-        T* d1 = L.q.p;
-        bool fused = true;
-        if (zero_guess) {
-            if (!(l == 0 && level0_initialised))
-                k_cheb_init<T><<<grid, kThreads, 0, s>>>(L.n, b, (const T*)nullptr, L.dinv.p, L.r.p, d0, 1.0 / theta, st);
-        } else {
-            if (ext) fused = fine_op->cheb_resid(x, b, L.r.p, d0, L.dinv.p, 1.0 / theta, st, s);
-            else spmv_cheb_resid<T>(L.A, 0.0, x, b, L.r.p, d0, L.dinv.p, 1.0 / theta, st, s);
-            if (!fused) {
-                apply_A(l, x, L.q.p, st, s);
-                k_cheb_init<T><<<grid, kThreads, 0, s>>>(L.n, b, L.q.p, L.dinv.p, L.r.p, d0, 1.0 / theta, st);
+    static int lanes_for(const DeviceCsr<T>& A) {
+        const double mean = A.rows > 0 ? (double)A.nnz / A.rows : 1.0;
+        return mean <= 3 ? 2 : (mean <= 6 ? 4 : (mean <= 12 ? 8 : (mean <= 24 ? 16 : 32)));
+    }
+    void long_rows_of(const DeviceCsr<T>& A, const int*& list, int& count, cudaStream_t s) {
+        list = nullptr;
+        count = 0;
+        if (A.rows <= 0 || !A.ptr.p) return;
+        std::vector<int> ptr((size_t)A.rows + 1), rows;
+        MK_CUDA(cudaMemcpyAsync(ptr.data(), A.ptr.p, sizeof(int) * ((size_t)A.rows + 1), cudaMemcpyDeviceToHost, s));
+        MK_CUDA(cudaStreamSynchronize(s));
+        for (int i = 0; i < A.rows; i++)
+            if (ptr[i + 1] - ptr[i] > kTailLongRow) rows.push_back(i);
+        if (rows.empty()) return;
+        tail_long.emplace_back(rows.size());
+        tail_long.back().upload(rows.data(), rows.size(), s);
+        MK_CUDA(cudaStreamSynchronize(s));
+        list = tail_long.back().p;
+        count = (int)rows.size();
+    }
+    void build_tail(cudaStream_t s) {
+        tail_start = -1;
+        const int nl = (int)lv.size();
+        const int thresh = tail_rows_threshold();
+        if (thresh <= 0 || handoff || !allow_tail || !coarse_dense || nl < 2) return;
+        int t0 = nl - 1;
+        while (t0 - 1 >= std::max(1, first_level) && lv[t0 - 1].n <= thresh) t0--;
+        if (nl - t0 > kTailMaxLevels) t0 = nl - kTailMaxLevels;
+        tail.nl = nl - t0;
+        tail.coarse_n = coarse_n;
+        tail.coarse_inv = coarse_inv.p;
+        for (int l = t0; l < nl; l++) {
+            AmgLevelDev<T>& L = lv[l];
+            TailLevel<T>& D = tail.lv[l - t0];
+            D = TailLevel<T>{};
+            D.n = L.n;
+            D.deg = degree(l);
+            D.dinv = L.dinv.p;
+            D.x = L.x.p; D.xo = L.xo.p; D.b = L.b.p; D.r = L.r.p; D.d = L.d.p; D.q = L.q.p;
+            D.inv_theta = 1.0 / theta(l);
+            D.delta = delta(l);
+            D.sigma = theta(l) / delta(l);
+            if (l + 1 < nl) {
+                D.Ap = L.A.ptr.p; D.Ac = L.A.col.p; D.Av = L.A.val.p; D.gA = lanes_for(L.A);
+                D.Pp = L.P.ptr.p; D.Pc = L.P.col.p; D.Pv = L.P.val.p; D.gP = lanes_for(L.P);
+                D.Rp = L.R.ptr.p; D.Rc = L.R.col.p; D.Rv = L.R.val.p; D.gR = lanes_for(L.R);
+                long_rows_of(L.A, D.longA, D.n_longA, s);
+                long_rows_of(L.P, D.longP, D.n_longP, s);
+                long_rows_of(L.R, D.longR, D.n_longR, s);
             }
         }
-        for (int k = 0; k < degree(l); k++) {
+        tail_cluster_size<T>();  // attribute + occupancy query outside any graph capture
+        tail_start = t0;
+        if (getenv("MK_VERBOSE")) {
+            fprintf(stderr, "[mk] V-cycle tail: levels %d..%d (", t0, nl - 1);
+            for (int l = t0; l < nl; l++) fprintf(stderr, "%d%s", lv[l].n, l + 1 < nl ? " " : "");
+            fprintf(stderr, " rows) in one cluster of %d CTAs\n", tail_cluster_size<T>());
+        }
+    }
+
+    // ---- fused smoother kernels of level l: the external fine operator on level 0, the level's own CSR operator otherwise
+    void k_step(int l, const T* d_in, T* d_out, T* x, const T* b, double c1, double c2, int first, const PcgState* st, cudaStream_t s) {
+        AmgLevelDev<T>& L = lv[l];
+        if (op(l)) op(l)->cheb_step(d_in, d_out, L.r.p, x, b, L.dinv.p, c1, c2, first, st, s);
+        else spmv_cheb_step<T>(L.A, 0.0, d_in, d_out, L.r.p, x, b, L.dinv.p, c1, c2, first, st, s);
+    }
+    void k_resid(int l, const T* x, const T* b, T* d_out, const PcgState* st, cudaStream_t s) {
+        AmgLevelDev<T>& L = lv[l];
+        if (op(l)) op(l)->cheb_resid(x, b, L.r.p, d_out, L.dinv.p, 1.0 / theta(l), st, s);
+        else spmv_cheb_resid<T>(L.A, 0.0, x, b, L.r.p, d_out, L.dinv.p, 1.0 / theta(l), st, s);
+    }
+    void k_resid_last(int l, const T* x, const T* b, T* xo, const void* r_hi, PcgState* st, ReduceWs ws, cudaStream_t s) {
+        AmgLevelDev<T>& L = lv[l];
+        if (op(l)) op(l)->cheb_resid_last(x, b, xo, L.dinv.p, 1.0 / theta(l), r_hi, st, ws, s);
+        else spmv_cheb_resid_last<T>(L.A, 0.0, x, b, xo, L.dinv.p, 1.0 / theta(l), (const typename HiOf<T>::type*)r_hi, st, ws, s);
+    }
+    void k_step_last(int l, const T* d_in, T* x, T* xo, double c1, double c2, const void* r_hi, PcgState* st, ReduceWs ws, cudaStream_t s) {
+        AmgLevelDev<T>& L = lv[l];
+        if (op(l)) op(l)->cheb_step_last(d_in, L.r.p, x, xo, L.dinv.p, c1, c2, r_hi, st, ws, s);
+        else spmv_cheb_step_last<T>(L.A, 0.0, d_in, L.r.p, x, xo, L.dinv.p, c1, c2, (const typename HiOf<T>::type*)r_hi, st, ws, s);
+    }
+
+    // Generic Chebyshev smoothing x <- x + p(A) (b - A x) with `deg` steps (only the non-dense coarsest level uses it: 8 steps stand in
+    // for the solve there). Leaves r = b - A x in L.r.
+    void smooth_generic(int l, const T* b, T* x, int deg, const PcgState* st, cudaStream_t s) {
+        AmgLevelDev<T>& L = lv[l];
+        const double th = theta(l), de = delta(l), sigma = th / de;
+        double rho = 1.0 / sigma;
+        T* d0 = L.d.p;
+        T* d1 = L.q.p;
+        k_start_dir<T><<<stream_grid(L.n), kThreads, 0, s>>>(L.n, b, L.dinv.p, d0, 1.0 / th, st);
+        for (int k = 0; k < deg; k++) {
             const double rho1 = 1.0 / (2.0 * sigma - rho);
-            const int first = (zero_guess && k == 0) ? 1 : 0;
-            if (fused && ext) fused = fine_op->cheb_step(d0, d1, L.r.p, x, L.dinv.p, rho1 * rho, 2.0 * rho1 / delta, first, st, s);
-            else if (fused) spmv_cheb_step<T>(L.A, 0.0, d0, d1, L.r.p, x, L.dinv.p, rho1 * rho, 2.0 * rho1 / delta, first, st, s);
-            if (fused) {
-                std::swap(d0, d1);
-            } else {
-                apply_A(l, L.d.p, L.q.p, st, s);
-                k_cheb_step<T><<<grid, kThreads, 0, s>>>(L.n, L.q.p, L.dinv.p, L.r.p, x, L.d.p, rho1 * rho, 2.0 * rho1 / delta, first, st);
-            }
+            k_step(l, d0, d1, x, b, rho1 * rho, 2.0 * rho1 / de, k == 0 ? 1 : 0, st, s);
+            std::swap(d0, d1);
             rho = rho1;
         }
         MK_CHECK_LAUNCH();
     }
 
-    // x_l = V(b_l); on return lv[l].r holds nothing the caller may rely on
-    void vcycle(int l, const T* b, T* x, const PcgState* st, cudaStream_t s) {
+    void coarsest(const T* b, T* xo, const PcgState* st, cudaStream_t s) {
+        const int l = (int)lv.size() - 1;
         AmgLevelDev<T>& L = lv[l];
-        if (l == (int)lv.size() - 1) {
-            if (coarse_dense) {
-                k_dense_matvec<T><<<(L.n * 32 + kThreads - 1) / kThreads, kThreads, 0, s>>>(L.n, coarse_inv.p, b, x, st);
-                MK_CHECK_LAUNCH();
-            } else {
-                const int save = prm.cheb_degree;
-                prm.cheb_degree = 8;
-                coarsest_smoothing = true;
-                smooth(l, b, x, true, st, s);
-                coarsest_smoothing = false;
-                prm.cheb_degree = save;
-            }
-            return;
+        if (coarse_dense) {
+            k_dense_matvec<T><<<(L.n * 32 + kThreads - 1) / kThreads, kThreads, 0, s>>>(L.n, coarse_inv.p, b, xo, st);
+            MK_CHECK_LAUNCH();
+        } else {
+            smooth_generic(l, b, xo, 8, st, s);
         }
-        smooth(l, b, x, true, st, s);  // leaves r = b - A x in L.r
+    }
+
+    // The cycle on level l. On entry b holds the right-hand side and start_dir(l, x) the direction dinv b / theta; on return xo = V(b).
+    // r_hi (level 0 of the mixed-precision cycle only): the last kernel also finishes the PCG reduction against the fp64 residual.
+    void descend(int l, const T* b, T* x, T* xo, const void* r_hi, PcgState* st, ReduceWs ws, cudaStream_t s) {
+        const int nl = (int)lv.size();
+        AmgLevelDev<T>& L = lv[l];
         AmgLevelDev<T>& C = lv[l + 1];
-        spmv_plain(L.R, L.r.p, C.b.p, false, st, s);
-        if (handoff && l + 1 == handoff_level) handoff->solve(C.b.p, C.x.p, st, s);
-        else vcycle(l + 1, C.b.p, C.x.p, st, s);
-        spmv_plain(L.P, C.x.p, x, true, st, s);
-        smooth(l, b, x, false, st, s);
+        const int deg = degree(l);
+        const double de = delta(l), sigma = theta(l) / de;
+        // pre-smoothing from a zero guess
+        {
+            T* d_cur = start_dir(l, x);
+            double rho = 1.0 / sigma;
+            for (int k = 0; k < deg; k++) {
+                const double rho1 = 1.0 / (2.0 * sigma - rho);
+                T* d_next = (k == deg - 1) ? nullptr : (d_cur == L.d.p ? L.q.p : L.d.p);
+                k_step(l, d_cur, d_next, x, b, rho1 * rho, 2.0 * rho1 / de, k == 0 ? 1 : 0, st, s);
+                d_cur = d_next;
+                rho = rho1;
+            }
+        }
+        // restriction (+ the child's start direction) and the child
+        const bool child_handoff = handoff && l + 1 == handoff_level;
+        const bool child_last = l + 2 == nl;
+        if (child_handoff || (child_last && tail_start != l + 1)) {
+            spmv_plain(L.R, L.r.p, C.b.p, false, st, s);
+        } else {
+            spmv_restrict_init<T>(L.R, L.r.p, C.b.p, start_dir(l + 1, C.x.p), C.dinv.p, 1.0 / theta(l + 1), st, s);
+        }
+        if (child_handoff) handoff->solve(C.b.p, C.xo.p, st, s);
+        else if (tail_start == l + 1) launch_vcycle_tail<T>(tail, C.xo.p, st, s);
+        else if (child_last) coarsest(C.b.p, C.xo.p, st, s);
+        else descend(l + 1, C.b.p, C.x.p, C.xo.p, nullptr, st, ws, s);
+        // prolongation and post-smoothing
+        spmv_plain(L.P, C.xo.p, x, true, st, s);
+        if (deg == 1) {
+            k_resid_last(l, x, b, xo, r_hi, st, ws, s);
+        } else {
+            k_resid(l, x, b, L.d.p, st, s);
+            T* d_cur = L.d.p;
+            double rho = 1.0 / sigma;
+            for (int k = 0; k + 1 < deg; k++) {
+                const double rho1 = 1.0 / (2.0 * sigma - rho);
+                if (k + 2 == deg) {
+                    k_step_last(l, d_cur, x, xo, rho1 * rho, 2.0 * rho1 / de, r_hi, st, ws, s);
+                } else {
+                    T* d_next = d_cur == L.d.p ? L.q.p : L.d.p;
+                    k_step(l, d_cur, d_next, x, nullptr, rho1 * rho, 2.0 * rho1 / de, 0, st, s);
+                    d_cur = d_next;
+                }
+                rho = rho1;
+            }
+        }
+        MK_CHECK_LAUNCH();
+    }
+
+    // x_out = V(b) on level l (b and x_out are the caller's; x_out must not be lv[l].x)
+    void vcycle(int l, const T* b, T* x_out, const PcgState* st, cudaStream_t s) {
+        prepare(s);
+        AmgLevelDev<T>& L = lv[l];
+        if (l == (int)lv.size() - 1) { coarsest(b, x_out, st, s); return; }
+        k_start_dir<T><<<stream_grid(L.n), kThreads, 0, s>>>(L.n, b, L.dinv.p, start_dir(l, L.x.p), 1.0 / theta(l), st);
+        MK_CHECK_LAUNCH();
+        if (l == tail_start && b == L.b.p) launch_vcycle_tail<T>(tail, x_out, st, s);
+        else descend(l, b, L.x.p, x_out, nullptr, const_cast<PcgState*>(st), dummy_ws, s);
     }
 
     void apply(const T* r, T* z, const PcgState* st, cudaStream_t s) override { vcycle(0, r, z, st, s); }
 
-    int launches_per_apply() const override {
+    int launches_per_apply() const override { return 1 + launches_from_level(0); }
+    // kernels of descend(l): pre, restrict, child, prolong, post
+    int launches_from_level(int l) const {
         const int nl = (int)lv.size();
-        // fused smoothing: init, degree, restrict, prolong, resid, degree
-        if (handoff) return levels_launches(0, handoff_level) + handoff->launches();
-        return levels_launches(0, nl - 1) + (coarse_dense ? 1 : 17);
+        if (l >= nl - 1) return coarse_dense ? 1 : 9;
+        if (l == tail_start) return 1;
+        int child;
+        if (handoff && l + 1 == handoff_level) child = handoff->launches();
+        else child = launches_from_level(l + 1);
+        return 2 * degree(l) + 2 + child;
     }
-    int levels_launches(int l0, int l1) const {
-        int sum = 0;
-        for (int l = l0; l < l1; l++) sum += 4 + 2 * degree(l);
-        return sum;
-    }
-    int launches_from_level(int l0) const { return levels_launches(l0, (int)lv.size() - 1) + (coarse_dense ? 1 : 17); }
 };
 
 // ---- mixed precision: the V-cycle in fp32 storage and arithmetic, wrapped as a preconditioner of the fp64 PCG ----
 // The V-cycle is the bandwidth of an iteration (its operators and work vectors are ~80 % of the bytes moved), while PCG only needs
 // z ~ M^{-1} r to a few digits: halving its bytes costs nothing in the final accuracy (residuals, dots and updates stay fp64; the true
-// residual is re-checked at exit as before). r is scaled to unit 2-norm on the way down (its norm falls by 1e-10 over a solve).
-template <class T, class Tlo>
-static __global__ void __launch_bounds__(kThreads) k_precond_in(int n, const T* __restrict__ r, Tlo* __restrict__ b, const PcgState* st) {
-    if (st->done) return;
-    const double s = st->rr > 0.0 ? rsqrt(st->rr) : 1.0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) st_rw(b + i, to_low<Tlo, T>(ld_ro(r + i), s));
-}
-template <class T, class Tlo>
-static __global__ void __launch_bounds__(kThreads) k_precond_out(int n, const Tlo* __restrict__ x, T* __restrict__ z, const PcgState* st) {
-    if (st->done) return;
-    const double s = st->rr > 0.0 ? sqrt(st->rr) : 1.0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) st_rw(z + i, to_high<T, Tlo>(ld_ro(x + i), s));
-}
+// residual is re-checked at exit as before). r is scaled to roughly unit 2-norm on the way down (its norm falls by 1e-10 over a solve);
+// the cycle is linear, so the factor (PcgState::zscale) cancels exactly on the way back and need not be the current norm.
 
 template <class T, class Tlo>
 static __global__ void k_widen_vector(int n, const Tlo* __restrict__ in, T* __restrict__ out, const PcgState* st) {
@@ -673,40 +817,77 @@ struct Fp64Tail : CoarseHandoff<typename LowOf<T>::type> {
         k_narrow_vector_st<T, Tlo><<<grid, kThreads, 0, s>>>(n, x.p, x_lo, st);
         MK_CHECK_LAUNCH();
     }
-    int launches() const override { return 2 + hi->launches_from_level(level); }
+    int launches() const override { return 3 + hi->launches_from_level(level); }
 };
 
-// hand-over fused with the start of the level-0 smoother: b = r / |r| (fp32), r0 = b, d0 = dinv b / theta
+// hand-over: b = r / zscale (fp32), start direction d0 = dinv b / theta; zscale = |r|
 template <class T, class Tlo>
 static __global__ void __launch_bounds__(kThreads) k_precond_in_init(int n, const T* __restrict__ r, const Tlo* __restrict__ dinv, Tlo* __restrict__ b,
-                                                              Tlo* __restrict__ r0, Tlo* __restrict__ d0, double inv_theta, const PcgState* st) {
+                                                              Tlo* __restrict__ d0, double inv_theta, PcgState* st) {
     if (st->done) return;
-    const double s = st->rr > 0.0 ? rsqrt(st->rr) : 1.0;
+    const double rr = st->rr;
+    const double s = rr > 0.0 ? rsqrt(rr) : 1.0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->zscale = rr > 0.0 ? sqrt(rr) : 1.0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const Tlo bi = to_low<Tlo, T>(ld_ro(r + i), s);
         st_rw(b + i, bi);
-        st_rw(r0 + i, bi);
         st_rw(d0 + i, ST<Tlo>::scale(inv_theta, ld_ro(dinv + i) * bi));
     }
 }
-// hand-back fused with the PCG reduction: z = x |r| (fp64), rho_new = <r, z>, beta = rho_new / rho
+// hand-back: z = zscale x (fp64)
 template <class T, class Tlo>
-static __global__ void __launch_bounds__(kThreads) k_precond_out_dot(int n, const Tlo* __restrict__ x, const T* __restrict__ r, T* __restrict__ z,
-                                                              PcgState* st, ReduceWs ws) {
+static __global__ void __launch_bounds__(kThreads) k_precond_out(int n, const Tlo* __restrict__ x, T* __restrict__ z, const PcgState* st) {
+    if (st->done) return;
+    const double s = st->zscale;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) st_rw(z + i, to_high<T, Tlo>(ld_ro(x + i), s));
+}
+
+// The PCG update fused with the hand-over (solver.cuh Precond::update_xr_handover):
+//     x += alpha p ; r -= alpha q ; rr = <r, r> ; b_lo = r / zscale ; d0 = dinv b_lo / theta
+// zscale is the residual norm of the PREVIOUS iteration (the current one is only known after this kernel's own reduction; any factor
+// of the right magnitude serves, see above). Every CTA reads st->rr before it takes its reduction ticket and the last CTA overwrites
+// it only after all tickets are taken, so all CTAs see the same value. 48 (real) / 96 (complex) bytes of fp64 traffic per row plus
+// 12 / 24 of fp32, against the same fp64 traffic + a second pass over r in the two kernels this replaces.
+template <class T, class Tlo>
+static __global__ void __launch_bounds__(kThreads) k_update_xr_handover(int n, T* __restrict__ x, T* __restrict__ r, const T* __restrict__ p,
+                                                                 const T* __restrict__ q, const Tlo* __restrict__ dinv, Tlo* __restrict__ b,
+                                                                 Tlo* __restrict__ d0, double inv_theta, PcgState* st, ReduceWs ws) {
     __shared__ double red[32];
     if (st->done) return;
-    const double s = st->rr > 0.0 ? sqrt(st->rr) : 1.0;
+    const double alpha = st->alpha;
+    const double rr_old = st->rr;
+    const double s = rr_old > 0.0 ? rsqrt(rr_old) : 1.0;
     double acc = 0.0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const T zi = to_high<T, Tlo>(ld_ro(x + i), s);
-        st_rw(z + i, zi);
-        acc += ST<T>::hdot(ld_ro(r + i), zi);
+        const T pi = ld_ro(p + i), qi = ld_ro(q + i);
+        T xi = ld_rw(x + i), ri = ld_rw(r + i);
+        xi = xi + ST<T>::scale(alpha, pi);
+        ri = ri - ST<T>::scale(alpha, qi);
+        st_rw(x + i, xi);
+        st_rw(r + i, ri);
+        acc += ST<T>::abs2(ri);
+        const Tlo bi = to_low<Tlo, T>(ri, s);
+        st_rw(b + i, bi);
+        st_rw(d0 + i, ST<Tlo>::scale(inv_theta, ld_ro(dinv + i) * bi));
     }
     double v[1] = {acc};
     grid_reduce<1>(v, ws.partials, ws.ticket, red, [&](const double* t) {
-        st->beta = t[0] / st->rho;
-        st->rho = t[0];
+        st->zscale = rr_old > 0.0 ? sqrt(rr_old) : 1.0;
+        st->rr = t[0];
+        st->iter += 1;
+        if (t[0] <= st->thresh) st->done = 1;
+        else if (st->iter >= st->maxit) st->done = 3;
+        else if (!(t[0] == t[0])) st->done = 2;
     });
+}
+
+// p = zscale z_lo + beta p   (the hand-back fused with the direction update: z never exists in fp64)
+template <class T, class Tlo>
+static __global__ void __launch_bounds__(kThreads) k_update_p_lo(int n, T* __restrict__ p, const Tlo* __restrict__ z, const PcgState* st) {
+    if (st->done) return;
+    const double beta = st->beta, s = st->zscale;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        st_rw(p + i, to_high<T, Tlo>(ld_ro(z + i), s) + ST<T>::scale(beta, ld_rw(p + i)));
 }
 
 template <class T>
@@ -716,28 +897,42 @@ struct MixedPrecond : Precond<T> {
     Fp64Tail<T> tail;
     std::unique_ptr<AmgPrecond<Tlo>> lo;
     std::unique_ptr<LinOp<Tlo>> fine_lo;  // level-0 operator in fp32 storage (owned here)
-    DevBuf<Tlo> b_lo, z_lo;
+    DevBuf<Tlo> b_lo, z_lo, zo_lo;        // right-hand side, iterate and result of level 0
     int n = 0;
-    void cycle(const T* r, const PcgState* st, cudaStream_t s) {
-        // hand-over + first smoother kernel of level 0 in one launch (the cycle starts from a zero guess)
+    bool single_level() const { return lo->lv.size() < 2; }
+    void prepare(cudaStream_t s) {
+        lo->prepare(s);
+        if (hi) hi->prepare(s);
+    }
+    // the cycle on the residual already handed over (b_lo and the start direction are in place); result in zo_lo
+    void cycle(const void* r_hi, PcgState* st, ReduceWs ws, cudaStream_t s) {
+        lo->descend(0, b_lo.p, z_lo.p, zo_lo.p, r_hi, st, ws, s);
+    }
+    void handover(const T* r, PcgState* st, cudaStream_t s) {
         AmgLevelDev<Tlo>& L0 = lo->lv[0];
-        k_precond_in_init<T, Tlo><<<stream_grid(n), kThreads, 0, s>>>(n, r, L0.dinv.p, b_lo.p, L0.r.p, L0.d.p, lo->inv_theta0(), st);
-        lo->level0_initialised = true;
-        lo->apply(b_lo.p, z_lo.p, st, s);
-        lo->level0_initialised = false;
+        k_precond_in_init<T, Tlo><<<stream_grid(n), kThreads, 0, s>>>(n, r, L0.dinv.p, b_lo.p, lo->start_dir(0, z_lo.p), lo->inv_theta0(), st);
     }
-    void apply(const T* r, T* z, const PcgState* st, cudaStream_t s) override {
-        cycle(r, st, s);
-        k_precond_out<T, Tlo><<<stream_grid(n), kThreads, 0, s>>>(n, z_lo.p, z, st);
+    void apply(const T* r, T* z, const PcgState* st_c, cudaStream_t s) override {
+        PcgState* st = const_cast<PcgState*>(st_c);
+        prepare(s);
+        handover(r, st, s);
+        if (single_level()) lo->coarsest(b_lo.p, zo_lo.p, st, s);
+        else cycle(nullptr, st, ReduceWs{nullptr, nullptr}, s);
+        k_precond_out<T, Tlo><<<stream_grid(n), kThreads, 0, s>>>(n, zo_lo.p, z, st);
         MK_CHECK_LAUNCH();
     }
-    bool apply_dot(const T* r, T* z, PcgState* st, ReduceWs ws, cudaStream_t s) override {
-        cycle(r, st, s);
-        k_precond_out_dot<T, Tlo><<<stream_grid(n), kThreads, 0, s>>>(n, z_lo.p, r, z, st, ws);
-        MK_CHECK_LAUNCH();
-        return true;
+    int launches_per_apply() const override { return 2 + lo->launches_from_level(0); }
+    // fused PCG body
+    bool fused_pcg() const override { return !single_level(); }
+    void update_xr_handover(int n_, T* x, T* r, const T* p, const T* q, PcgState* st, ReduceWs ws, cudaStream_t s) override {
+        AmgLevelDev<Tlo>& L0 = lo->lv[0];
+        k_update_xr_handover<T, Tlo><<<stream_grid(n_), kThreads, 0, s>>>(n_, x, r, p, q, L0.dinv.p, b_lo.p, lo->start_dir(0, z_lo.p), lo->inv_theta0(), st, ws);
     }
-    int launches_per_apply() const override { return lo->launches_per_apply() + 1; }
+    void cycle_dot(const T* r, PcgState* st, ReduceWs ws, cudaStream_t s) override { cycle(r, st, ws, s); }
+    void update_p(int n_, T* p, const PcgState* st, cudaStream_t s) override {
+        k_update_p_lo<T, Tlo><<<stream_grid(n_), kThreads, 0, s>>>(n_, p, zo_lo.p, st);
+    }
+    int launches_fused() const override { return 2 + lo->launches_from_level(0); }
 };
 
 template <class T, class Tlo>
@@ -791,6 +986,7 @@ inline std::unique_ptr<MixedPrecond<T>> lower_precision(cudaStream_t s, std::uni
         mp->tail.x.alloc(mp->tail.n);
         lo.handoff = &mp->tail;
         lo.handoff_level = K;
+        hi.allow_tail = false;  // its fine levels are dropped below
         MK_CUDA(cudaStreamSynchronize(s));
         for (int l = 0; l < K; l++) hi.lv[l] = AmgLevelDev<T>();  // the fine fp64 levels are no longer needed
         hi.lv[0].n = lo.lv[0].n;
@@ -809,6 +1005,7 @@ inline std::unique_ptr<MixedPrecond<T>> lower_precision(cudaStream_t s, std::uni
     mp->n = lo.lv[0].n;
     mp->b_lo.alloc(mp->n);
     mp->z_lo.alloc(mp->n);
+    mp->zo_lo.alloc(mp->n);
     MK_CUDA(cudaStreamSynchronize(s));
     return mp;
 }

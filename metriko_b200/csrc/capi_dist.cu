@@ -177,6 +177,8 @@ int mk_dfield_set_global(mk_dfield* f, int nF, const int* nbr, const double* val
         L0.P = DeviceCsr<cdouble>();
         L0.R = DeviceCsr<cdouble>();
         L0.r.release(); L0.d.release(); L0.q.release(); L0.dinv.release();
+        g->G->first_level = 1;   // level 0 runs distributed (DistAmgPrecond): no replicated work vectors of global length
+        g->G->prepare(s);
         f->gamg = std::move(g);
     }
     MK_CUDA(cudaStreamSynchronize(s));

@@ -257,26 +257,46 @@ __device__ __forceinline__ cfloat block_sum_t(cfloat v, double* red) {
     return make_cf((float)re, (float)im);
 }
 
-// What happens to a finished row sum (A v)_row. One code path serves the three row shapes (SELL slice lane, long row, warp-per-row):
+// What happens to a finished row sum q = (A v)_row. One code path serves the three row shapes (SELL slice lane, long row, warp-per-row):
 //   kPlain : y = q                     kAcc  : y += q (prolongation)            kDot : y = q and <v, q> (the PCG step)
-//   kStep  : x (+)= v ; r -= q ; out = c1 v + c2 dinv .* r      (Chebyshev step fused into the SpMV; v = direction d, out = the next one)
+//   kStep  : x (+)= v ; r -= q ; out = c1 v + c2 dinv .* r      (Chebyshev step fused into the SpMV; v = direction d, out = the next one).
+//            `first`: zero initial guess, i.e. x = v and r = b - q (b is read, r need not be initialised); when x aliases v (degree-1
+//            smoothing keeps the start direction in the iterate buffer) the x store is skipped. out == nullptr: last pre-smoothing step,
+//            no further direction is needed.
 //   kResid : r = b - q ; out = c1 dinv .* r                     (residual + first direction; v = the iterate, c1 = 1 / theta)
-// `out` must not alias `v` (other rows still gather the old direction). Fusing the smoother saves a kernel and ~25% of the traffic per
-// smoothing step against SpMV + update.
-enum SpmvMode { kPlain = 0, kAcc = 1, kDot = 2, kStep = 3, kResid = 4 };
+//   kRestrictInit : y = q ; out = c1 dinv .* q                  (restriction b_c = R r fused with the coarse level's start direction
+//            d0 = dinv_c b_c / theta_c: the coarse pre-smoother needs no kernel of its own)
+//   kResidLast : out = v + c1 dinv .* (b - q)                   (degree-1 post-smoothing in ONE SpMV: the step that would only have
+//            updated r and the next direction -- both dead after the last step -- is not run)
+//   kStepLast  : r' = r - q ; out = x + v + (c1 v + c2 dinv .* r')   (last post-smoothing step of degree >= 2, same saving)
+//   k*LastDot  : the same on level 0 of the mixed-precision cycle, plus the PCG reduction <r_hi, out> against the fp64 residual:
+//            rho_new = zscale * sum, beta = rho_new / rho  (what k_dot_rz / k_precond_out_dot did in a kernel of their own)
+// `out` must not alias `v` (other rows still gather it). Fusing the smoother saves a kernel and ~25% of the traffic per smoothing step
+// against SpMV + update.
+enum SpmvMode { kPlain = 0, kAcc = 1, kDot = 2, kStep = 3, kResid = 4, kRestrictInit = 5, kResidLast = 6, kStepLast = 7, kResidLastDot = 8, kStepLastDot = 9 };
+
+template <class T> struct HiOf { using type = T; };
+template <> struct HiOf<float> { using type = double; };
+template <> struct HiOf<cfloat> { using type = cdouble; };
+// Re(conj(a) b) of a high-precision a and a working-precision b
+__device__ __forceinline__ double hdot_hi(double a, float b) { return a * (double)b; }
+__device__ __forceinline__ double hdot_hi(cdouble a, cfloat b) { return a.x * (double)b.x + a.y * (double)b.y; }
+__device__ __forceinline__ double hdot_hi(double a, double b) { return a * b; }
+__device__ __forceinline__ double hdot_hi(cdouble a, cdouble b) { return a.x * b.x + a.y * b.y; }
 
 template <class T>
 struct SpmvEpi {
     const T* v;        // the vector A is applied to
     double shift;      // (A + shift I)
-    T* y;              // kPlain / kAcc / kDot
-    const T* b;        // kResid
-    const T* dinv;     // kStep / kResid
-    T* r;              // kStep / kResid
-    T* x;              // kStep
-    T* out;            // kStep / kResid
+    T* y;              // kPlain / kAcc / kDot / kRestrictInit
+    const T* b;        // kResid / kResidLast / kStep with `first`
+    const T* dinv;     // kStep / kResid / kRestrictInit / k*Last
+    T* r;              // kStep / kResid / kStepLast
+    T* x;              // kStep / kStepLast
+    T* out;            // kStep / kResid / kRestrictInit / k*Last
     double c1, c2;
-    int first;         // kStep: x = v instead of x += v
+    int first;         // kStep: x = v, r = b - q
+    const typename HiOf<T>::type* r_hi;  // k*LastDot: the fp64 PCG residual
 };
 
 template <class T, int MODE>
@@ -293,16 +313,34 @@ __device__ __forceinline__ double row_epilogue(const SpmvEpi<T>& e, int row, T a
     } else if (MODE == kStep) {
         const T di = ld_ro(e.v + row);
         if (e.shift != 0.0) acc = acc + ST<T>::scale(e.shift, di);
-        const T xi = e.first ? di : ld_rw(e.x + row) + di;
-        const T ri = ld_rw(e.r + row) - acc;
-        st_rw(e.x + row, xi);
+        const T ri = (e.first ? ld_ro(e.b + row) : ld_rw(e.r + row)) - acc;
+        if (!e.first) st_rw(e.x + row, ld_rw(e.x + row) + di);
+        else if (e.x != e.v) st_rw(e.x + row, di);
         st_rw(e.r + row, ri);
-        st_rw(e.out + row, ST<T>::scale(e.c1, di) + ST<T>::scale(e.c2, ld_ro(e.dinv + row) * ri));
-    } else {
+        if (e.out) st_rw(e.out + row, ST<T>::scale(e.c1, di) + ST<T>::scale(e.c2, ld_ro(e.dinv + row) * ri));
+    } else if (MODE == kResid) {
         if (e.shift != 0.0) acc = acc + ST<T>::scale(e.shift, ld_ro(e.v + row));
         const T ri = ld_ro(e.b + row) - acc;
         st_rw(e.r + row, ri);
         st_rw(e.out + row, ST<T>::scale(e.c1, ld_ro(e.dinv + row) * ri));
+    } else if (MODE == kRestrictInit) {
+        st_rw(e.y + row, acc);
+        st_rw(e.out + row, ST<T>::scale(e.c1, ld_ro(e.dinv + row) * acc));
+    } else if (MODE == kResidLast || MODE == kResidLastDot) {
+        const T xi = ld_ro(e.v + row);
+        if (e.shift != 0.0) acc = acc + ST<T>::scale(e.shift, xi);
+        const T ri = ld_ro(e.b + row) - acc;
+        const T xo = xi + ST<T>::scale(e.c1, ld_ro(e.dinv + row) * ri);
+        st_rw(e.out + row, xo);
+        if (MODE == kResidLastDot) dot = hdot_hi(ld_ro(e.r_hi + row), xo);
+    } else {  // kStepLast / kStepLastDot
+        const T di = ld_ro(e.v + row);
+        if (e.shift != 0.0) acc = acc + ST<T>::scale(e.shift, di);
+        const T ri = ld_rw(e.r + row) - acc;
+        const T dn = ST<T>::scale(e.c1, di) + ST<T>::scale(e.c2, ld_ro(e.dinv + row) * ri);
+        const T xo = ld_rw(e.x + row) + di + dn;
+        st_rw(e.out + row, xo);
+        if (MODE == kStepLastDot) dot = hdot_hi(ld_ro(e.r_hi + row), xo);
     }
     return dot;
 }
@@ -317,7 +355,16 @@ __device__ __forceinline__ void finish_dot(double dot, PcgState* st, ReduceWs ws
             if (!(s[0] > 0.0)) st->done = 2;  // not positive definite / breakdown
         });
     }
+    if (MODE == kResidLastDot || MODE == kStepLastDot) {
+        double v[1] = {dot};
+        grid_reduce<1>(v, ws.partials, ws.ticket, red, [&](const double* s) {
+            const double rho_new = st->zscale * s[0];   // z = zscale * (fp32 cycle output)
+            st->beta = rho_new / st->rho;
+            st->rho = rho_new;
+        });
+    }
 }
+constexpr bool spmv_mode_reduces(int mode) { return mode == kDot || mode == kResidLastDot || mode == kStepLastDot; }
 
 // one CTA sums a long row: four independent loads in flight per thread (a 15k-entry dense-dof row would otherwise serialise ~60 load
 // round trips and set the duration of the whole kernel)
@@ -487,7 +534,7 @@ template <class T, int MODE, int G>
 inline void spmv_rows_launch(const DeviceCsr<T>& A, const SpmvEpi<T>& e, PcgState* st, ReduceWs ws, cudaStream_t s) {
     const int extra = extra_blocks(A.n_huge, A.n_long);
     int row_blocks = stream_grid((int64_t)A.rows * G, kThreads, 16);
-    if (MODE == kDot && row_blocks + extra > kMaxPartials) row_blocks = std::max(1, kMaxPartials - extra);
+    if (spmv_mode_reduces(MODE) && row_blocks + extra > kMaxPartials) row_blocks = std::max(1, kMaxPartials - extra);
     k_spmv_rows<T, MODE, G><<<row_blocks + extra, kThreads, 0, s>>>(A.rows, A.ptr.p, A.col.p, A.val.p, extra ? A.long_bits.p : nullptr, extra, A.n_huge,
                                                                     A.huge_rows.p, A.n_long, A.long_rows.p, e, st, ws);
 }
@@ -504,7 +551,7 @@ inline void spmv_launch(const DeviceCsr<T>& A, const SpmvEpi<T>& e, PcgState* st
     } else {
         const int extra = extra_blocks(A.n_huge, A.n_long);
         int sell_blocks = stream_grid((int64_t)A.n_slices * 32, kThreads, 16);
-        if (MODE == kDot && sell_blocks + extra > kMaxPartials) sell_blocks = std::max(1, kMaxPartials - extra);
+        if (spmv_mode_reduces(MODE) && sell_blocks + extra > kMaxPartials) sell_blocks = std::max(1, kMaxPartials - extra);
         k_spmv_sell<T, MODE><<<sell_blocks + extra, kThreads, 0, s>>>(A.rows, A.n_slices, A.sl_ptr.p, A.sl_col.p, A.sl_val.p,
                                                                      extra ? A.long_bits.p : nullptr, extra, A.n_huge, A.huge_rows.p, A.n_long,
                                                                      A.long_rows.p, A.ptr.p, A.col.p, A.val.p, e, st, ws);
@@ -540,10 +587,10 @@ inline void spmv(const DeviceCsr<T>& A, const T* x, T* y, double shift, bool acc
 }
 
 template <class T>
-inline void spmv_cheb_step(const DeviceCsr<T>& A, double shift, const T* d_in, T* d_out, T* r, T* x, const T* dinv, double c1, double c2, int first,
-                           const PcgState* st, cudaStream_t s) {
+inline void spmv_cheb_step(const DeviceCsr<T>& A, double shift, const T* d_in, T* d_out, T* r, T* x, const T* b, const T* dinv, double c1, double c2,
+                           int first, const PcgState* st, cudaStream_t s) {
     SpmvEpi<T> e{};
-    e.v = d_in; e.shift = shift; e.dinv = dinv; e.r = r; e.x = x; e.out = d_out; e.c1 = c1; e.c2 = c2; e.first = first;
+    e.v = d_in; e.shift = shift; e.dinv = dinv; e.r = r; e.x = x; e.b = b; e.out = d_out; e.c1 = c1; e.c2 = c2; e.first = first;
     spmv_launch<T, kStep>(A, e, const_cast<PcgState*>(st), ReduceWs{nullptr, nullptr}, s);
 }
 
@@ -555,8 +602,37 @@ inline void spmv_cheb_resid(const DeviceCsr<T>& A, double shift, const T* x, con
     spmv_launch<T, kResid>(A, e, const_cast<PcgState*>(st), ReduceWs{nullptr, nullptr}, s);
 }
 
+// y = A x ; out = c dinv .* y   (restriction fused with the coarse level's Chebyshev start direction)
+template <class T>
+inline void spmv_restrict_init(const DeviceCsr<T>& A, const T* x, T* y, T* out, const T* dinv, double c, const PcgState* st, cudaStream_t s) {
+    SpmvEpi<T> e{};
+    e.v = x; e.y = y; e.out = out; e.dinv = dinv; e.c1 = c;
+    spmv_launch<T, kRestrictInit>(A, e, const_cast<PcgState*>(st), ReduceWs{nullptr, nullptr}, s);
+}
+
+// xo = x + inv_theta dinv .* (b - A x); r_hi != nullptr: also the PCG reduction <r_hi, xo> (needs st and ws)
+template <class T>
+inline void spmv_cheb_resid_last(const DeviceCsr<T>& A, double shift, const T* x, const T* b, T* xo, const T* dinv, double inv_theta,
+                                 const typename HiOf<T>::type* r_hi, PcgState* st, ReduceWs ws, cudaStream_t s) {
+    SpmvEpi<T> e{};
+    e.v = x; e.shift = shift; e.b = b; e.dinv = dinv; e.out = xo; e.c1 = inv_theta; e.r_hi = r_hi;
+    if (r_hi) spmv_launch<T, kResidLastDot>(A, e, st, ws, s);
+    else spmv_launch<T, kResidLast>(A, e, st, ReduceWs{nullptr, nullptr}, s);
+}
+
+// xo = x + d + (c1 d + c2 dinv .* (r - A d))
+template <class T>
+inline void spmv_cheb_step_last(const DeviceCsr<T>& A, double shift, const T* d_in, T* r, T* x, T* xo, const T* dinv, double c1, double c2,
+                                const typename HiOf<T>::type* r_hi, PcgState* st, ReduceWs ws, cudaStream_t s) {
+    SpmvEpi<T> e{};
+    e.v = d_in; e.shift = shift; e.dinv = dinv; e.r = r; e.x = x; e.out = xo; e.c1 = c1; e.c2 = c2; e.r_hi = r_hi;
+    if (r_hi) spmv_launch<T, kStepLastDot>(A, e, st, ws, s);
+    else spmv_launch<T, kStepLast>(A, e, st, ReduceWs{nullptr, nullptr}, s);
+}
+
 template <class T>
 struct CsrOp : LinOp<T> {
+    using Hi = typename HiOf<T>::type;
     const DeviceCsr<T>* A = nullptr;
     double shift = 0.0;
     explicit CsrOp(const DeviceCsr<T>* A_, double shift_ = 0.0) : A(A_), shift(shift_) { this->n = A_->rows; }
@@ -564,13 +640,20 @@ struct CsrOp : LinOp<T> {
     void apply(const T* x, T* y, PcgState* st, ReduceWs ws, cudaStream_t s, bool dot = true) override {
         spmv<T>(*A, x, y, shift, false, dot && st != nullptr, st, ws, s);
     }
-    bool cheb_step(const T* d_in, T* d_out, T* r, T* x, const T* dinv, double c1, double c2, int first, const PcgState* st, cudaStream_t s) override {
-        spmv_cheb_step<T>(*A, shift, d_in, d_out, r, x, dinv, c1, c2, first, st, s);
-        return true;
+    void cheb_step(const T* d_in, T* d_out, T* r, T* x, const T* b, const T* dinv, double c1, double c2, int first, const PcgState* st,
+                   cudaStream_t s) override {
+        spmv_cheb_step<T>(*A, shift, d_in, d_out, r, x, b, dinv, c1, c2, first, st, s);
     }
-    bool cheb_resid(const T* x, const T* b, T* r, T* d_out, const T* dinv, double inv_theta, const PcgState* st, cudaStream_t s) override {
+    void cheb_resid(const T* x, const T* b, T* r, T* d_out, const T* dinv, double inv_theta, const PcgState* st, cudaStream_t s) override {
         spmv_cheb_resid<T>(*A, shift, x, b, r, d_out, dinv, inv_theta, st, s);
-        return true;
+    }
+    void cheb_resid_last(const T* x, const T* b, T* xo, const T* dinv, double inv_theta, const void* r_hi, PcgState* st, ReduceWs ws,
+                         cudaStream_t s) override {
+        spmv_cheb_resid_last<T>(*A, shift, x, b, xo, dinv, inv_theta, (const Hi*)r_hi, st, ws, s);
+    }
+    void cheb_step_last(const T* d_in, T* r, T* x, T* xo, const T* dinv, double c1, double c2, const void* r_hi, PcgState* st, ReduceWs ws,
+                        cudaStream_t s) override {
+        spmv_cheb_step_last<T>(*A, shift, d_in, r, x, xo, dinv, c1, c2, (const Hi*)r_hi, st, ws, s);
     }
 };
 

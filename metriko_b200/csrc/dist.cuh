@@ -296,13 +296,13 @@ struct DistAmgPrecond : Precond<cdouble> {
         AmgLevelDev<cdouble>& C = G->lv[1];
         spmv_plain(R0, r.p, C.b.p, false, st, s);
         dc->allreduce_sum(reinterpret_cast<double*>(C.b.p), 2 * n1, s);
-        G->vcycle(1, C.b.p, C.x.p, st, s);
-        spmv_plain(P0, C.x.p, z, true, st, s);
+        G->vcycle(1, C.b.p, C.xo.p, st, s);
+        spmv_plain(P0, C.xo.p, z, true, st, s);
         smooth(rin, z, false, st, s);
     }
     int launches_per_apply() const override {
         const int per_spmv = A->launches_per_apply();
-        return (2 * prm.cheb_degree + 1) * (per_spmv + 1) + 1 + 2 + (G ? G->launches_per_apply() - (4 + 2 * prm.cheb_degree) : 0);
+        return (2 * prm.cheb_degree + 1) * (per_spmv + 1) + 1 + 2 + (G ? 1 + G->launches_from_level(1) : 0);
     }
 };
 

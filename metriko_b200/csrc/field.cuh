@@ -107,96 +107,95 @@ static __global__ void __launch_bounds__(kThreads) k_spmv_face(int nF, double di
     }
 }
 
-// Chebyshev smoothing step / residual fused into the face-stencil SpMV (see k_spmv_sell_cheb, csr.cuh, for the two modes)
-template <int MODE>
-static __global__ void __launch_bounds__(kThreads) k_spmv_face_cheb(int nF, double diag, const int* __restrict__ nbr, const cdouble* __restrict__ val,
-                                                             const cdouble* __restrict__ v, const cdouble* __restrict__ b, const cdouble* __restrict__ dinv,
-                                                             cdouble* __restrict__ r, cdouble* __restrict__ x, cdouble* __restrict__ out, double c1,
-                                                             double c2, int first, const PcgState* st) {
+// Chebyshev smoothing fused into the face-stencil SpMV, for the fp64 (T = cdouble) and the fp32 (T = cfloat: level 0 of the
+// mixed-precision V-cycle, 36 B/face of operator instead of 60) storage of the stencil values. MODE as SpmvMode (csr.cuh):
+// kPlain y = L v; kStep / kResid / kResidLast / kStepLast the fused smoother forms; DOT: the PCG reduction <r_hi, out> in the same kernel.
+template <class T, int MODE, bool DOT>
+static __global__ void __launch_bounds__(kThreads) k_spmv_face_cheb(int nF, double diag_, const int* __restrict__ nbr, const T* __restrict__ val,
+                                                             const T* __restrict__ v, const T* __restrict__ b, const T* __restrict__ dinv,
+                                                             T* __restrict__ r, T* __restrict__ x, T* __restrict__ out, double c1, double c2, int first,
+                                                             const typename HiOf<T>::type* __restrict__ r_hi, PcgState* st, ReduceWs ws) {
+    __shared__ double red[32];
     if (st && st->done) return;
+    double dot = 0.0;
     for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nF; f += gridDim.x * blockDim.x) {
         const int n0 = __ldg(nbr + f), n1 = __ldg(nbr + (size_t)nF + f), n2 = __ldg(nbr + 2 * (size_t)nF + f);
-        const cdouble v0 = ldc_nc(val + f), v1 = ldc_nc(val + (size_t)nF + f), v2 = ldc_nc(val + 2 * (size_t)nF + f);
-        const cdouble vf = ldc_nc(v + f);
-        const cdouble x0 = ldc_nc(v + n0), x1 = ldc_nc(v + n1), x2 = ldc_nc(v + n2);
-        cdouble acc = make_c(diag * vf.x, diag * vf.y);
-        acc = ST<cdouble>::fma_(v0, x0, acc);
-        acc = ST<cdouble>::fma_(v1, x1, acc);
-        acc = ST<cdouble>::fma_(v2, x2, acc);
-        if (MODE == 1) {
-            const cdouble xi = first ? vf : ldc(x + f) + vf;
-            const cdouble ri = ldc(r + f) - acc;
-            stc(x + f, xi);
-            stc(r + f, ri);
-            stc(out + f, ST<cdouble>::scale(c1, vf) + ST<cdouble>::scale(c2, ldc_nc(dinv + f) * ri));
-        } else {
-            const cdouble ri = ldc_nc(b + f) - acc;
-            stc(r + f, ri);
-            stc(out + f, ST<cdouble>::scale(c1, ldc_nc(dinv + f) * ri));
+        const T v0 = ld_ro(val + f), v1 = ld_ro(val + (size_t)nF + f), v2 = ld_ro(val + 2 * (size_t)nF + f);
+        const T vf = ld_ro(v + f);
+        const T x0 = ld_ro(v + n0), x1 = ld_ro(v + n1), x2 = ld_ro(v + n2);
+        T acc = ST<T>::scale(diag_, vf);
+        acc = ST<T>::fma_(v0, x0, acc);
+        acc = ST<T>::fma_(v1, x1, acc);
+        acc = ST<T>::fma_(v2, x2, acc);
+        if (MODE == kPlain) {
+            st_rw(out + f, acc);
+        } else if (MODE == kStep) {
+            const T ri = (first ? ld_ro(b + f) : ld_rw(r + f)) - acc;
+            if (!first) st_rw(x + f, ld_rw(x + f) + vf);
+            else if (x != v) st_rw(x + f, vf);
+            st_rw(r + f, ri);
+            if (out) st_rw(out + f, ST<T>::scale(c1, vf) + ST<T>::scale(c2, ld_ro(dinv + f) * ri));
+        } else if (MODE == kResid) {
+            const T ri = ld_ro(b + f) - acc;
+            st_rw(r + f, ri);
+            st_rw(out + f, ST<T>::scale(c1, ld_ro(dinv + f) * ri));
+        } else if (MODE == kResidLast) {
+            const T ri = ld_ro(b + f) - acc;
+            const T xo = vf + ST<T>::scale(c1, ld_ro(dinv + f) * ri);
+            st_rw(out + f, xo);
+            if (DOT) dot += hdot_hi(ld_ro(r_hi + f), xo);
+        } else {  // kStepLast
+            const T ri = ld_rw(r + f) - acc;
+            const T dn = ST<T>::scale(c1, vf) + ST<T>::scale(c2, ld_ro(dinv + f) * ri);
+            const T xo = ld_rw(x + f) + vf + dn;
+            st_rw(out + f, xo);
+            if (DOT) dot += hdot_hi(ld_ro(r_hi + f), xo);
         }
     }
+    if (DOT) finish_dot<kResidLastDot>(dot, st, ws, red);
 }
 
-struct FaceOp : LinOp<cdouble> {
-    const FaceStencil* S;
-    explicit FaceOp(const FaceStencil* S_) : S(S_) { n = S_->nF; }
+// the fused-smoother interface of LinOp for a face stencil with values of type T
+template <class T>
+struct FaceChebOps : LinOp<T> {
+    using Hi = typename HiOf<T>::type;
+    const FaceStencil* S = nullptr;
+    const T* vals = nullptr;
+    int grid() const { return stream_grid(S->nF, kThreads, 8); }
+    template <int MODE, bool DOT>
+    void launch(const T* v, const T* b, const T* dinv, T* r, T* x, T* out, double c1, double c2, int first, const Hi* r_hi, PcgState* st, ReduceWs ws,
+                cudaStream_t s) {
+        k_spmv_face_cheb<T, MODE, DOT><<<grid(), kThreads, 0, s>>>(S->nF, S->diag, S->nbr.p, vals, v, b, dinv, r, x, out, c1, c2, first, r_hi, st, ws);
+        MK_CHECK_LAUNCH();
+    }
+    void cheb_step(const T* d_in, T* d_out, T* r, T* x, const T* b, const T* dinv, double c1, double c2, int first, const PcgState* st,
+                   cudaStream_t s) override {
+        launch<kStep, false>(d_in, b, dinv, r, x, d_out, c1, c2, first, nullptr, const_cast<PcgState*>(st), ReduceWs{nullptr, nullptr}, s);
+    }
+    void cheb_resid(const T* x, const T* b, T* r, T* d_out, const T* dinv, double inv_theta, const PcgState* st, cudaStream_t s) override {
+        launch<kResid, false>(x, b, dinv, r, nullptr, d_out, inv_theta, 0.0, 0, nullptr, const_cast<PcgState*>(st), ReduceWs{nullptr, nullptr}, s);
+    }
+    void cheb_resid_last(const T* x, const T* b, T* xo, const T* dinv, double inv_theta, const void* r_hi, PcgState* st, ReduceWs ws,
+                         cudaStream_t s) override {
+        if (r_hi) launch<kResidLast, true>(x, b, dinv, nullptr, nullptr, xo, inv_theta, 0.0, 0, (const Hi*)r_hi, st, ws, s);
+        else launch<kResidLast, false>(x, b, dinv, nullptr, nullptr, xo, inv_theta, 0.0, 0, nullptr, st, ws, s);
+    }
+    void cheb_step_last(const T* d_in, T* r, T* x, T* xo, const T* dinv, double c1, double c2, const void* r_hi, PcgState* st, ReduceWs ws,
+                        cudaStream_t s) override {
+        if (r_hi) launch<kStepLast, true>(d_in, nullptr, dinv, r, x, xo, c1, c2, 0, (const Hi*)r_hi, st, ws, s);
+        else launch<kStepLast, false>(d_in, nullptr, dinv, r, x, xo, c1, c2, 0, nullptr, st, ws, s);
+    }
+};
+
+struct FaceOp : FaceChebOps<cdouble> {
+    explicit FaceOp(const FaceStencil* S_) { S = S_; vals = S_->val.p; n = S_->nF; }
     void apply(const cdouble* x, cdouble* y, PcgState* st, ReduceWs ws, cudaStream_t s, bool dot = true) override {
         int grid = stream_grid(S->nF, kThreads, 8);
         if (st && dot) k_spmv_face<true><<<grid, kThreads, 0, s>>>(S->nF, S->diag, S->nbr.p, S->val.p, x, y, st, ws);
         else k_spmv_face<false><<<grid, kThreads, 0, s>>>(S->nF, S->diag, S->nbr.p, S->val.p, x, y, st, ws);
         MK_CHECK_LAUNCH();
     }
-    bool cheb_step(const cdouble* d_in, cdouble* d_out, cdouble* r, cdouble* x, const cdouble* dinv, double c1, double c2, int first,
-                   const PcgState* st, cudaStream_t s) override {
-        k_spmv_face_cheb<1><<<stream_grid(S->nF, kThreads, 8), kThreads, 0, s>>>(S->nF, S->diag, S->nbr.p, S->val.p, d_in, nullptr, dinv, r, x, d_out, c1, c2,
-                                                                                 first, st);
-        MK_CHECK_LAUNCH();
-        return true;
-    }
-    bool cheb_resid(const cdouble* x, const cdouble* b, cdouble* r, cdouble* d_out, const cdouble* dinv, double inv_theta, const PcgState* st,
-                    cudaStream_t s) override {
-        k_spmv_face_cheb<2><<<stream_grid(S->nF, kThreads, 8), kThreads, 0, s>>>(S->nF, S->diag, S->nbr.p, S->val.p, x, b, dinv, r, nullptr, d_out, inv_theta,
-                                                                                 0.0, 0, st);
-        MK_CHECK_LAUNCH();
-        return true;
-    }
 };
-
-// ---- the face stencil in fp32 storage: level 0 of the mixed-precision V-cycle (amg.cuh MixedPrecond). 36 B/face of operator
-// (24 values + 12 indices) against 60 B/face in fp64; the vectors are complex fp32 too. MODE 0: y = L v; 1 / 2: fused Chebyshev step /
-// residual exactly as k_spmv_face_cheb. ----
-template <int MODE>
-static __global__ void __launch_bounds__(kThreads) k_spmv_face_lo(int nF, float diag, const int* __restrict__ nbr, const cfloat* __restrict__ val,
-                                                           const cfloat* __restrict__ v, const cfloat* __restrict__ b, const cfloat* __restrict__ dinv,
-                                                           cfloat* __restrict__ r, cfloat* __restrict__ x, cfloat* __restrict__ out, float c1, float c2,
-                                                           int first, const PcgState* st) {
-    if (st && st->done) return;
-    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nF; f += gridDim.x * blockDim.x) {
-        const int n0 = __ldg(nbr + f), n1 = __ldg(nbr + (size_t)nF + f), n2 = __ldg(nbr + 2 * (size_t)nF + f);
-        const cfloat v0 = ld_ro(val + f), v1 = ld_ro(val + (size_t)nF + f), v2 = ld_ro(val + 2 * (size_t)nF + f);
-        const cfloat vf = ld_ro(v + f);
-        const cfloat x0 = ld_ro(v + n0), x1 = ld_ro(v + n1), x2 = ld_ro(v + n2);
-        cfloat acc = make_cf(diag * vf.x, diag * vf.y);
-        acc = ST<cfloat>::fma_(v0, x0, acc);
-        acc = ST<cfloat>::fma_(v1, x1, acc);
-        acc = ST<cfloat>::fma_(v2, x2, acc);
-        if (MODE == 0) {
-            st_rw(out + f, acc);
-        } else if (MODE == 1) {
-            const cfloat xi = first ? vf : ld_rw(x + f) + vf;
-            const cfloat ri = ld_rw(r + f) - acc;
-            const cfloat t = ld_ro(dinv + f) * ri;
-            st_rw(x + f, xi);
-            st_rw(r + f, ri);
-            st_rw(out + f, make_cf(c1 * vf.x + c2 * t.x, c1 * vf.y + c2 * t.y));
-        } else {
-            const cfloat ri = ld_ro(b + f) - acc;
-            const cfloat t = ld_ro(dinv + f) * ri;
-            st_rw(r + f, ri);
-            st_rw(out + f, make_cf(c1 * t.x, c1 * t.y));
-        }
-    }
-}
 
 static __global__ void __launch_bounds__(kThreads) k_narrow_stencil(size_t n, const cdouble* __restrict__ in, cfloat* __restrict__ out) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -205,31 +204,18 @@ static __global__ void __launch_bounds__(kThreads) k_narrow_stencil(size_t n, co
     }
 }
 
-struct FaceOpLo : LinOp<cfloat> {
-    const FaceStencil* S;  // shares the neighbour indices
-    DevBuf<cfloat> val;
-    FaceOpLo(const FaceStencil* S_, cudaStream_t s) : S(S_) {
+struct FaceOpLo : FaceChebOps<cfloat> {
+    DevBuf<cfloat> val;  // fp32 copy of the stencil values; the neighbour indices are shared with the fp64 stencil
+    FaceOpLo(const FaceStencil* S_, cudaStream_t s) {
+        S = S_;
         n = S_->nF;
         val.alloc((size_t)3 * n);
+        vals = val.p;
         k_narrow_stencil<<<stream_grid((int64_t)3 * n), kThreads, 0, s>>>((size_t)3 * n, S->val.p, val.p);
         MK_CHECK_LAUNCH();
     }
-    int grid() const { return stream_grid(S->nF, kThreads, 8); }
     void apply(const cfloat* x, cfloat* y, PcgState* st, ReduceWs, cudaStream_t s, bool = true) override {
-        k_spmv_face_lo<0><<<grid(), kThreads, 0, s>>>(S->nF, (float)S->diag, S->nbr.p, val.p, x, nullptr, nullptr, nullptr, nullptr, y, 0.f, 0.f, 0, st);
-        MK_CHECK_LAUNCH();
-    }
-    bool cheb_step(const cfloat* d_in, cfloat* d_out, cfloat* r, cfloat* x, const cfloat* dinv, double c1, double c2, int first, const PcgState* st,
-                   cudaStream_t s) override {
-        k_spmv_face_lo<1><<<grid(), kThreads, 0, s>>>(S->nF, (float)S->diag, S->nbr.p, val.p, d_in, nullptr, dinv, r, x, d_out, (float)c1, (float)c2, first, st);
-        MK_CHECK_LAUNCH();
-        return true;
-    }
-    bool cheb_resid(const cfloat* x, const cfloat* b, cfloat* r, cfloat* d_out, const cfloat* dinv, double inv_theta, const PcgState* st,
-                    cudaStream_t s) override {
-        k_spmv_face_lo<2><<<grid(), kThreads, 0, s>>>(S->nF, (float)S->diag, S->nbr.p, val.p, x, b, dinv, r, nullptr, d_out, (float)inv_theta, 0.f, 0, st);
-        MK_CHECK_LAUNCH();
-        return true;
+        launch<kPlain, false>(x, nullptr, nullptr, nullptr, nullptr, y, 0.0, 0.0, 0, nullptr, st, ReduceWs{nullptr, nullptr}, s);
     }
 };
 

@@ -147,6 +147,7 @@ struct PcgState {
     double bnorm2;    // <b, b>
     double thresh;    // tol^2 * bnorm2
     double aux0, aux1, aux2;  // scratch reductions for drivers (e.g. <u, M u>)
+    double zscale;    // mixed-precision hand-over: the fp32 cycle ran on r / zscale, its output is z / zscale (set by the hand-over kernel)
     int iter;
     int done;         // 1 = converged (kernels become no-ops), 2 = breakdown
     int maxit;
@@ -287,11 +288,17 @@ struct LinOp {
     // kernel finishes the fused reduction pq = <x, y>, alpha = rho / pq (the PCG step).
     virtual void apply(const T* x, T* y, PcgState* st, ReduceWs ws, cudaStream_t s, bool dot = true) = 0;
     virtual int launches_per_apply() const { return 1; }
-    // Chebyshev smoothing fused into the operator kernel (the multigrid V-cycle, amg.cuh). Return false when unsupported.
-    //   cheb_step : q = A d_in ; x (+)= d_in ; r -= q ; d_out = c1 d_in + c2 dinv .* r      (x = d_in when `first`)
-    //   cheb_resid: r = b - A x ; d_out = inv_theta dinv .* r
-    virtual bool cheb_step(const T*, T*, T*, T*, const T*, double, double, int, const PcgState*, cudaStream_t) { return false; }
-    virtual bool cheb_resid(const T*, const T*, T*, T*, const T*, double, const PcgState*, cudaStream_t) { return false; }
+    // Chebyshev smoothing fused into the operator kernel (the multigrid V-cycle, amg.cuh; the epilogues are documented at SpmvMode, csr.cuh):
+    //   cheb_step      : q = A d_in ; x (+)= d_in ; r -= q ; d_out = c1 d_in + c2 dinv .* r   (`first`: x = d_in, r = b - q; d_out may be null)
+    //   cheb_resid     : r = b - A x ; d_out = inv_theta dinv .* r
+    //   cheb_resid_last: xo = x + inv_theta dinv .* (b - A x)                        (degree-1 post-smoothing in one SpMV)
+    //   cheb_step_last : xo = x + d_in + (c1 d_in + c2 dinv .* (r - A d_in))          (last post-smoothing step of degree >= 2)
+    // The two *_last forms take the fp64 PCG residual r_hi (HiOf<T>::type*, may be null): with it they also finish the PCG reduction
+    // rho_new = zscale <r_hi, xo>, beta = rho_new / rho in the same kernel.
+    virtual void cheb_step(const T*, T*, T*, T*, const T*, const T*, double, double, int, const PcgState*, cudaStream_t) { throw std::logic_error("cheb_step"); }
+    virtual void cheb_resid(const T*, const T*, T*, T*, const T*, double, const PcgState*, cudaStream_t) { throw std::logic_error("cheb_resid"); }
+    virtual void cheb_resid_last(const T*, const T*, T*, const T*, double, const void*, PcgState*, ReduceWs, cudaStream_t) { throw std::logic_error("cheb_resid_last"); }
+    virtual void cheb_step_last(const T*, T*, T*, T*, const T*, double, double, const void*, PcgState*, ReduceWs, cudaStream_t) { throw std::logic_error("cheb_step_last"); }
 };
 
 template <class T>
@@ -302,6 +309,16 @@ struct Precond {
     // z = M^{-1} r and, fused into its last kernel, the PCG reduction rho_new = <r, z>, beta = rho_new / rho (what k_dot_rz does).
     // Return false when unsupported (the caller then runs apply + k_dot_rz).
     virtual bool apply_dot(const T*, T*, PcgState*, ReduceWs, cudaStream_t) { return false; }
+    // Fused PCG body (solves without a projector): the preconditioner takes over the vector updates either side of its cycle, so that
+    // an iteration is  q = A p (+ <p,q>)  ->  update_xr_handover  ->  cycle_dot  ->  update_p  with no stand-alone vector kernel.
+    virtual bool fused_pcg() const { return false; }
+    //   x += alpha p ; r -= alpha q ; rr = <r,r> (+ the iteration bookkeeping of k_update_xr) and the hand-over of r to the cycle
+    virtual void update_xr_handover(int, T*, T*, const T*, const T*, PcgState*, ReduceWs, cudaStream_t) {}
+    //   the cycle on the handed-over residual; its last kernel finishes rho_new = <r, z>, beta = rho_new / rho
+    virtual void cycle_dot(const T*, PcgState*, ReduceWs, cudaStream_t) {}
+    //   p = z + beta p, z read from the cycle's own output
+    virtual void update_p(int, T*, const PcgState*, cudaStream_t) {}
+    virtual int launches_fused() const { return 0; }  // kernels of the three calls above
 };
 
 // In-place projection onto the feasible subspace (IGM constraint elimination); null for unconstrained solves.
@@ -400,7 +417,9 @@ public:
         return out;
     }
 
+    bool fused() const { return M_ && !P_ && M_->fused_pcg(); }
     int launches_per_iteration() const {
+        if (fused()) return A_->launches_per_apply() + M_->launches_fused();
         return A_->launches_per_apply() + (P_ ? (M_ ? 2 : 1) : 0) + 1 + (M_ ? M_->launches_per_apply() + 1 : 0) + 1;
     }
 
@@ -427,6 +446,13 @@ private:
     }
     void iteration_body(T* x) {
         A_->apply(p_.p, q_.p, st_.p, ws(), stream_);
+        if (fused()) {
+            M_->update_xr_handover(n_, x, r_.p, p_.p, q_.p, st_.p, ws(), stream_);
+            M_->cycle_dot(r_.p, st_.p, ws(), stream_);
+            M_->update_p(n_, p_.p, st_.p, stream_);
+            MK_CHECK_LAUNCH();
+            return;
+        }
         if (P_) P_->apply(q_.p, st_.p, stream_);
         if (M_) {
             k_update_xr<T, true><<<grid_, kThreads, 0, stream_>>>(n_, x, r_.p, p_.p, q_.p, st_.p, ws());
