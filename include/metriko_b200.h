@@ -104,6 +104,12 @@ int mk_field_decode(mk_field* f, double* field);
 /* y = L x on host vectors (tests) and a timed device loop for the roofline (reps launches, returns ms per launch). */
 int mk_field_spmv(mk_field* f, const double* x, double* y);
 int mk_field_spmv_bench(mk_field* f, int reps, int fused_dot, double* ms_per_launch);
+/* The multigrid hierarchy built for the last solve (it stands where the reference factorises, sls.h:42-43): number of levels and, for
+ * the first `cap` of them, rows, stored entries of A_l and of the prolongator P_l. Used by bench.py for the per-iteration byte count. */
+int mk_field_hierarchy(mk_field* f, int cap, int* n_levels, int64_t* rows, int64_t* nnz_a, int64_t* nnz_p);
+/* Live timing of the preconditioner of the last solve, replayed `reps` times as a CUDA graph between two events (warm, back to back, as
+ * inside a solve): us[0] = one whole application (hand-over + V-cycle + hand-back), us[l] = the cycle from level l downwards, l >= 1. */
+int mk_field_profile_cycle(mk_field* f, int reps, int cap, int* n_out, double* us);
 
 /* One-shot drop-in for solveSmallestEig(SprsC& L, SprsC& M, int nIter) on Eigen CSC arrays (sls.h:29): L Hermitian
  * n x n compressed CSC (outerIndexPtr/innerIndexPtr/valuePtr), M diagonal given as CSC too (only its diagonal is
@@ -132,6 +138,26 @@ int mk_igm_create(mk_ctx* ctx, int rows, int cols, const int64_t* x2f_ptr, const
 int mk_igm_create_dev(mk_ctx* ctx, int rows, int cols, const int64_t* x2f_ptr_dev, const int* x2f_col_dev, const double* x2f_val_dev,
                       int ufull_rows, const int64_t* uf_ptr, const int* uf_col, const double* uf_val, const double* F2_dev,
                       double length, const mk_solve_opts* opts, mk_igm** out);
+/* RosyParameterization::integ() (igm/parameterization_integ.ipp:3-98) from the arrays integ() itself reads, instead of a host-built X2F:
+ * the gradient stencil G2 (integ.ipp:9-28), rawF2Vec (integ.ipp:30-43) and X2F = (G2 * fullx2Nfunc * UFull).pruned() (integ.ipp:72,
+ * iter_rounding_init.h:173) are assembled on the device, one thread per row, then the same set-up as mk_igm_create runs.
+ *   cutF[3 nF], cutPos[3 cut_nV]  the cut mesh (param.h:126-152): corner table in F's corner order and positions; the face frames are
+ *                                 recomputed from them exactly as Hmesh does (hmesh/hmesh.h:461-489)
+ *   f2n_*                         fullx2Nfunc = vtrans2cut * uncompress (setup.ipp:52-170, integ.ipp:4): CSR, N cut_nV rows, f2n_cols = n nR
+ *   uf_*                          UFull (iter_rounding_init.h:98-154): CSR, f2n_cols rows, ufull_cols columns
+ *   F2                            rawF2Vec [2 N nF] on the host, or NULL with (field, comb_turns): the eigen-solve result still resident in
+ *                                 `field` and the per-face combing turn of compute_combbed_field (frf.h:207-249), from which F2 is formed on
+ *                                 the device (the combed extrinsic field is unit, frf.h:258-261)
+ * H2D at 1M vertices: 0.17 GB (0.31 GB with a host F2) against 1.0 GB for mk_igm_create. */
+int mk_igm_create_from_mesh(mk_ctx* ctx, int N, int nF, int cut_nV, const int* cutF, const double* cutPos, int f2n_cols, const int64_t* f2n_ptr,
+                            const int* f2n_col, const double* f2n_val, int ufull_cols, const int64_t* uf_ptr, const int* uf_col,
+                            const double* uf_val, const double* F2, mk_field* field, const int* comb_turns, double length,
+                            const mk_solve_opts* opts, mk_igm** out);
+/* The device-assembled X2F (CSR, 2 N nF rows; NULL arrays to query nnz) and F2 (may be NULL), for tests. */
+int mk_igm_get_x2f(mk_igm* g, int64_t* nnz, int64_t* ptr, int* col, double* val, double* F2);
+/* Result scatter (integ.ipp:88-98): NF = fullx2Nfunc * fullx, nfn[cut_nV x N], cfn[nF x 3N] = nfn gathered by the corner table. fullx NULL:
+ * the result of the last mk_igm_round / mk_igm_poisson, still on the device. Either output may be NULL. mk_igm_create_from_mesh handles only. */
+int mk_igm_scatter(mk_igm* g, const double* fullx, double* nfn, double* cfn);
 int mk_igm_destroy(mk_igm* g);
 /* NaiveIntegration Poisson solve (iter_rounding_init.h:173-212): min ||length X2F x - F2|| s.t. UFull[fixedIdcs] x = fixedVals.
  * x_small: cols, x0_full: ufull_rows (either may be NULL). */
@@ -147,6 +173,8 @@ int mk_igm_round(mk_igm* g, int n_fixed, const int* fixedIdcs, const double* fix
 /* Copy A0 = length^2 X2F^T X2F (assembled on the device) back as CSR for tests: pass NULLs to query nnz. */
 int mk_igm_get_matrix(mk_igm* g, int64_t* nnz, int* rowptr, int* col, double* val);
 int mk_igm_spmv_bench(mk_igm* g, int reps, int fused_dot, double* ms_per_launch);
+int mk_igm_hierarchy(mk_igm* g, int cap, int* n_levels, int64_t* rows, int64_t* nnz_a, int64_t* nnz_p);
+int mk_igm_profile_cycle(mk_igm* g, int reps, int cap, int* n_out, double* us);
 
 /* ---- partitioned face operator: one process per GPU, NCCL over NVLink (BASELINE configs[3]). The reference has no
  * distributed code; these entry points serve the same recurrence (sls.h:44-51) on a row-partitioned L. The host-side plan

@@ -18,6 +18,23 @@ from . import capi
 from .capi import Context, MkError, Stats, as_c128, as_f64, as_i32, default_opts, ptr
 
 
+def _hierarchy(ctx, fn, h):
+    """[(rows, entries of A_l, entries of P_l)] per multigrid level, from mk_*_hierarchy."""
+    cap = 16
+    n = C.c_int()
+    rows, na, npp = (np.zeros(cap, np.int64) for _ in range(3))
+    ctx.check(fn(h, cap, C.byref(n), ptr(rows), ptr(na), ptr(npp)))
+    return [(int(rows[l]), int(na[l]), int(npp[l])) for l in range(min(n.value, cap))]
+
+
+def _profile_cycle(ctx, fn, h, reps):
+    cap = 16
+    n = C.c_int()
+    us = np.zeros(cap, np.float64)
+    ctx.check(fn(h, reps, cap, C.byref(n), ptr(us)))
+    return us[: min(n.value, cap)].tolist()
+
+
 class FaceRosyField:
     """FaceRosyField(mesh, N, FieldType::Smoothest) (frf.h:17-44): connectionLaplacian + galerkinMassMatrix are
     assembled on the device from the half-edge arrays, then solveSmallestEig runs there."""
@@ -117,6 +134,13 @@ class FaceRosyField:
         self.ctx.check(self.ctx.L.mk_field_spmv_bench(self.h, reps, int(fused_dot), C.byref(ms)))
         return ms.value
 
+    def hierarchy(self):
+        return _hierarchy(self.ctx, self.ctx.L.mk_field_hierarchy, self.h)
+
+    def profile_cycle(self, reps: int = 100):
+        """[us of one preconditioner application, us of the cycle from level 1, from level 2, ...] measured live (graph replays)."""
+        return _profile_cycle(self.ctx, self.ctx.L.mk_field_profile_cycle, self.h, reps)
+
     def close(self):
         if self.h:
             self.ctx.L.mk_field_destroy(self.h)
@@ -145,7 +169,7 @@ def solveSmallestEig(ctx: Context, L, M, nIter: int = 50, u0=None, return_stats:
     o = default_opts(**opts)
     a = [as_i32(Lc.indptr), as_i32(Lc.indices), as_c128(Lc.data), as_i32(Mc.indptr), as_i32(Mc.indices), as_c128(Mc.data)]
     rc = ctx.L.mk_solve_smallest_eig_csc(ctx.h, n, *[ptr(v) for v in a], ptr(u0), nIter, C.byref(o), ptr(x), C.byref(st))
-    ctx.check(rc)
+    ctx.check(rc, allow=(-3,))   # MK_ERR_NOT_CONVERGED (fp64 floor of large meshes): x is the best iterate, stats["relres_max"] says how far it got
     return (x, st.as_dict()) if return_stats else x
 
 
@@ -239,6 +263,62 @@ class IgmProblem:
                                       ptr(a[5]), ptr(a[6]), float(length), C.byref(o), C.byref(self.h)))
         self.stats = None
 
+    @classmethod
+    def from_mesh(cls, ctx: Context, N: int, cutF, cutPos, fullx2Nfunc, UFull, length: float, F2=None, field: "FaceRosyField | None" = None,
+                  comb_turns=None, raw=None, **opts):
+        """RosyParameterization::integ() from the arrays it reads itself (mk_igm_create_from_mesh): cut-mesh corner table and positions,
+        fullx2Nfunc, UFull and either F2 = rawF2Vec (host) or (field, comb_turns): the eigen-solve result still resident in `field` plus the
+        per-face combing turns. G2 / F2 / X2F are assembled on the device. `raw` = (f2n_ptr i64, f2n_col i32, f2n_val f64, uf_ptr i64, uf_col
+        i32, uf_val f64, cutF i32, cutPos f64[, F2 f64 or comb_turns i32]) passes prepared (e.g. pinned) buffers as they are."""
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        if raw is None:
+            Fn = sp.csr_matrix(fullx2Nfunc, dtype=np.float64)
+            U = sp.csr_matrix(UFull, dtype=np.float64)
+            Fn.sort_indices()
+            U.sort_indices()
+            a = [np.ascontiguousarray(Fn.indptr, np.int64), as_i32(Fn.indices), as_f64(Fn.data),
+                 np.ascontiguousarray(U.indptr, np.int64), as_i32(U.indices), as_f64(U.data), as_i32(np.asarray(cutF).reshape(-1)),
+                 as_f64(np.asarray(cutPos).reshape(-1))]
+            f2 = as_f64(F2) if F2 is not None else None
+            turns = as_i32(comb_turns) if comb_turns is not None else None
+        else:
+            Fn, U = fullx2Nfunc, UFull
+            a = list(raw[:8])
+            f2 = raw[8] if F2 is not None else None
+            turns = raw[8] if F2 is None else None
+        nF, cut_nV = len(a[6]) // 3, len(a[7]) // 3
+        assert Fn.shape[0] == N * cut_nV and U.shape[0] == Fn.shape[1]
+        self.rows, self.cols = 2 * N * nF, U.shape[1]
+        self.ufull_rows = U.shape[0]
+        self.N, self.nF, self.cut_nV = N, nF, cut_nV
+        self.h = C.c_void_p()
+        o = default_opts(**opts)
+        ctx.check(ctx.L.mk_igm_create_from_mesh(ctx.h, N, nF, cut_nV, ptr(a[6]), ptr(a[7]), Fn.shape[1], ptr(a[0]), ptr(a[1]), ptr(a[2]), U.shape[1],
+                                                ptr(a[3]), ptr(a[4]), ptr(a[5]), ptr(f2), field.h if (f2 is None and field is not None) else None,
+                                                ptr(turns), float(length), C.byref(o), C.byref(self.h)))
+        self.stats = None
+        return self
+
+    def x2f(self):
+        """(X2F, F2) assembled on the device (mk_igm_create_from_mesh handles), copied back for tests."""
+        nnz = C.c_int64()
+        self.ctx.check(self.ctx.L.mk_igm_get_x2f(self.h, C.byref(nnz), None, None, None, None))
+        p64 = np.empty(self.rows + 1, np.int64)
+        col = np.empty(nnz.value, np.int32)
+        val = np.empty(nnz.value, np.float64)
+        f2 = np.empty(self.rows, np.float64)
+        self.ctx.check(self.ctx.L.mk_igm_get_x2f(self.h, C.byref(nnz), ptr(p64), ptr(col), ptr(val), ptr(f2)))
+        return sp.csr_matrix((val, col, p64), shape=(self.rows, self.cols)), f2
+
+    def scatter(self, fullx=None, want_cfn: bool = True):
+        """Result scatter (integ.ipp:88-98) on the device: (nfn[cut_nV x N], cfn[nF x 3N]); fullx None = the last rounding result, still resident."""
+        nfn = np.empty((self.cut_nV, self.N), np.float64)
+        cfn = np.empty((self.nF, 3 * self.N), np.float64) if want_cfn else None
+        fx = as_f64(fullx) if fullx is not None else None
+        self.ctx.check(self.ctx.L.mk_igm_scatter(self.h, ptr(fx), ptr(nfn), ptr(cfn)))
+        return nfn, cfn
+
     def matrix(self):
         nnz = C.c_int64()
         self.ctx.check(self.ctx.L.mk_igm_get_matrix(self.h, C.byref(nnz), None, None, None))
@@ -281,6 +361,12 @@ class IgmProblem:
         ms = C.c_double()
         self.ctx.check(self.ctx.L.mk_igm_spmv_bench(self.h, reps, int(fused_dot), C.byref(ms)))
         return ms.value
+
+    def hierarchy(self):
+        return _hierarchy(self.ctx, self.ctx.L.mk_igm_hierarchy, self.h)
+
+    def profile_cycle(self, reps: int = 100):
+        return _profile_cycle(self.ctx, self.ctx.L.mk_igm_profile_cycle, self.h, reps)
 
     def close(self):
         if self.h:

@@ -77,6 +77,8 @@ def lib() -> C.CDLL:
         L.mk_field_solve_square.argtypes = [vp, vp, C.POINTER(SolveOpts), vp, C.POINTER(Stats)]
         L.mk_field_spmv.argtypes = [vp, vp, vp]
         L.mk_field_spmv_bench.argtypes = [vp, C.c_int, C.c_int, dp]
+        L.mk_field_hierarchy.argtypes = [vp, C.c_int, ip, vp, vp, vp]
+        L.mk_field_profile_cycle.argtypes = [vp, C.c_int, C.c_int, ip, vp]
         L.mk_solve_smallest_eig_csc.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.POINTER(SolveOpts), vp, C.POINTER(Stats)]
         L.mk_spd_factorize.argtypes = [vp, C.c_int, vp, vp, vp, C.POINTER(SolveOpts), C.POINTER(vp)]
         L.mk_spd_solve.argtypes = [vp, vp, vp, vp, C.POINTER(Stats)]
@@ -85,10 +87,16 @@ def lib() -> C.CDLL:
         L.mk_igm_create.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp, C.c_double, C.POINTER(SolveOpts), C.POINTER(vp)]
         L.mk_igm_create_dev.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp, C.c_double, C.POINTER(SolveOpts), C.POINTER(vp)]
         L.mk_igm_destroy.argtypes = [vp]
+        L.mk_igm_create_from_mesh.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_double,
+                                              C.POINTER(SolveOpts), C.POINTER(vp)]
+        L.mk_igm_get_x2f.argtypes = [vp, i64p, vp, vp, vp, vp]
+        L.mk_igm_scatter.argtypes = [vp, vp, vp, vp]
         L.mk_igm_poisson.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.POINTER(Stats)]
         L.mk_igm_round.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp, ip, vp, vp, C.POINTER(Stats)]
         L.mk_igm_get_matrix.argtypes = [vp, i64p, vp, vp, vp]
         L.mk_igm_spmv_bench.argtypes = [vp, C.c_int, C.c_int, dp]
+        L.mk_igm_hierarchy.argtypes = [vp, C.c_int, ip, vp, vp, vp]
+        L.mk_igm_profile_cycle.argtypes = [vp, C.c_int, C.c_int, ip, vp]
         L.mk_dist_unique_id.argtypes = [C.c_char_p, C.c_int]
         L.mk_dist_create.argtypes = [vp, C.c_int, C.c_int, C.c_char_p, C.c_int, C.POINTER(vp)]
         L.mk_dist_destroy.argtypes = [vp]

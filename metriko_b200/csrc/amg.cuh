@@ -527,11 +527,12 @@ struct CoarseHandoff {
 //     pre   : k_l fused steps from a zero guess (the start direction dinv b / theta was written by whoever produced b: the hand-over
 //             kernel on level 0, the restriction above on the others); the last one stores no further direction
 //     down  : b_{l+1} = R r fused with the child's start direction
-//     child : recursion; the levels with <= kTailRows rows run as ONE cluster kernel (vtail.cuh); dense inverse on the coarsest
+//     child : recursion; dense inverse on the coarsest level (optionally the small levels as ONE cluster kernel, vtail.cuh: measured
+//             slower than separate launches on the B200 and off by default)
 //     up    : x += P x_{l+1}
 //     post  : residual + k_l - 1 steps, the last of them writing the result out of place -- k_l SpMVs, not k_l + 1: the step that
 //             would only refresh r and the next direction after the last update is dead code and is not run
-// i.e. 2 k_l + 2 launches per level above the tail (4 + 2 k_l in round 1) and one for the whole tail (was ~8 per level).
+// i.e. 2 k_l + 2 launches per level (4 + 2 k_l in round 1).
 template <class T>
 struct AmgPrecond : Precond<T> {
     using S = typename HostScalar<T>::type;
@@ -580,25 +581,35 @@ struct AmgPrecond : Precond<T> {
         build_tail(s);
     }
 
-    static int lanes_for(const DeviceCsr<T>& A) {
+    static int lanes_for(double mean) { return mean <= 3 ? 2 : (mean <= 6 ? 4 : (mean <= 12 ? 8 : (mean <= 24 ? 16 : 32))); }
+    // row classes of one operand of the tail kernel (vtail.cuh TailMat)
+    TailMat<T> tail_mat(const DeviceCsr<T>& A, cudaStream_t s) {
+        TailMat<T> M{};
+        M.ptr = A.ptr.p; M.col = A.col.p; M.val = A.val.p;
         const double mean = A.rows > 0 ? (double)A.nnz / A.rows : 1.0;
-        return mean <= 3 ? 2 : (mean <= 6 ? 4 : (mean <= 12 ? 8 : (mean <= 24 ? 16 : 32)));
-    }
-    void long_rows_of(const DeviceCsr<T>& A, const int*& list, int& count, cudaStream_t s) {
-        list = nullptr;
-        count = 0;
-        if (A.rows <= 0 || !A.ptr.p) return;
-        std::vector<int> ptr((size_t)A.rows + 1), rows;
+        M.gmax = lanes_for(mean);
+        M.cut = std::max(kTailMedRowMin, (int)(4.0 * mean));
+        if (A.rows <= 0 || !A.ptr.p) return M;
+        std::vector<int> ptr((size_t)A.rows + 1), med, huge;
         MK_CUDA(cudaMemcpyAsync(ptr.data(), A.ptr.p, sizeof(int) * ((size_t)A.rows + 1), cudaMemcpyDeviceToHost, s));
         MK_CUDA(cudaStreamSynchronize(s));
-        for (int i = 0; i < A.rows; i++)
-            if (ptr[i + 1] - ptr[i] > kTailLongRow) rows.push_back(i);
-        if (rows.empty()) return;
-        tail_long.emplace_back(rows.size());
-        tail_long.back().upload(rows.data(), rows.size(), s);
-        MK_CUDA(cudaStreamSynchronize(s));
-        list = tail_long.back().p;
-        count = (int)rows.size();
+        for (int i = 0; i < A.rows; i++) {
+            const int len = ptr[i + 1] - ptr[i];
+            if (len > kTailHugeRow) huge.push_back(i);
+            else if (len > M.cut) med.push_back(i);
+        }
+        auto put = [&](const std::vector<int>& v, const int*& out, int& cnt) {
+            cnt = (int)v.size();
+            out = nullptr;
+            if (v.empty()) return;
+            tail_long.emplace_back(v.size());
+            tail_long.back().upload(v.data(), v.size(), s);
+            MK_CUDA(cudaStreamSynchronize(s));
+            out = tail_long.back().p;
+        };
+        put(med, M.med, M.n_med);
+        put(huge, M.huge, M.n_huge);
+        return M;
     }
     void build_tail(cudaStream_t s) {
         tail_start = -1;
@@ -623,12 +634,9 @@ struct AmgPrecond : Precond<T> {
             D.delta = delta(l);
             D.sigma = theta(l) / delta(l);
             if (l + 1 < nl) {
-                D.Ap = L.A.ptr.p; D.Ac = L.A.col.p; D.Av = L.A.val.p; D.gA = lanes_for(L.A);
-                D.Pp = L.P.ptr.p; D.Pc = L.P.col.p; D.Pv = L.P.val.p; D.gP = lanes_for(L.P);
-                D.Rp = L.R.ptr.p; D.Rc = L.R.col.p; D.Rv = L.R.val.p; D.gR = lanes_for(L.R);
-                long_rows_of(L.A, D.longA, D.n_longA, s);
-                long_rows_of(L.P, D.longP, D.n_longP, s);
-                long_rows_of(L.R, D.longR, D.n_longR, s);
+                D.A = tail_mat(L.A, s);
+                D.P = tail_mat(L.P, s);
+                D.R = tail_mat(L.R, s);
             }
         }
         tail_cluster_size<T>();  // attribute + occupancy query outside any graph capture
@@ -758,6 +766,16 @@ struct AmgPrecond : Precond<T> {
     }
 
     void apply(const T* r, T* z, const PcgState* st, cudaStream_t s) override { vcycle(0, r, z, st, s); }
+
+    // rows and stored entries of A_l and P_l per level (level 0 behind an external fine operator reports 0 entries for A)
+    void describe(std::vector<int64_t>& rows, std::vector<int64_t>& nnz_a, std::vector<int64_t>& nnz_p) const {
+        rows.clear(); nnz_a.clear(); nnz_p.clear();
+        for (size_t l = 0; l < lv.size(); l++) {
+            rows.push_back(lv[l].n);
+            nnz_a.push_back(lv[l].A.ptr.p ? lv[l].A.nnz : 0);
+            nnz_p.push_back(l + 1 < lv.size() ? lv[l].P.nnz : 0);
+        }
+    }
 
     int launches_per_apply() const override { return 1 + launches_from_level(0); }
     // kernels of descend(l): pre, restrict, child, prolong, post
@@ -934,6 +952,53 @@ struct MixedPrecond : Precond<T> {
     }
     int launches_fused() const override { return 2 + lo->launches_from_level(0); }
 };
+
+// ---- live timing of the cycle, level by level (bench.py / profiles: where an iteration's time goes, measured warm and back to back as
+// in a solve, not under a profiler): `body` is captured into a CUDA graph and replayed `reps` times between two events.
+template <class F>
+inline double time_graph_us(cudaStream_t s, int reps, F body) {
+    cudaGraph_t g;
+    cudaGraphExec_t ge;
+    MK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    body();
+    MK_CUDA(cudaStreamEndCapture(s, &g));
+    MK_CUDA(cudaGraphInstantiate(&ge, g, 0));
+    cudaGraphDestroy(g);
+    for (int i = 0; i < 3; i++) MK_CUDA(cudaGraphLaunch(ge, s));
+    cudaEvent_t e0, e1;
+    MK_CUDA(cudaEventCreate(&e0));
+    MK_CUDA(cudaEventCreate(&e1));
+    MK_CUDA(cudaEventRecord(e0, s));
+    for (int i = 0; i < reps; i++) MK_CUDA(cudaGraphLaunch(ge, s));
+    MK_CUDA(cudaEventRecord(e1, s));
+    MK_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    MK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaGraphExecDestroy(ge);
+    return (double)ms * 1e3 / reps;
+}
+
+// us[0] = one application of the preconditioner `M` to a vector of length n (hand-over + cycle + hand-back), us[l] = the cycle from
+// level l downwards (start direction + descend) for every level l >= 1 of `A`
+template <class T, class TA>
+inline std::vector<double> profile_cycle(Precond<T>& M, AmgPrecond<TA>& A, int n, int reps, cudaStream_t s) {
+    DevBuf<T> r(n), z(n);
+    r.zero(s);
+    DevBuf<PcgState> unit(1);
+    PcgState h;
+    std::memset(&h, 0, sizeof(h));
+    h.rr = 1.0; h.rho = 1.0; h.bnorm2 = 1.0; h.zscale = 1.0;
+    unit.upload(&h, 1, s);
+    M.apply(r.p, z.p, unit.p, s);  // allocates the work buffers outside any capture
+    MK_CUDA(cudaStreamSynchronize(s));
+    std::vector<double> us;
+    us.push_back(time_graph_us(s, reps, [&] { M.apply(r.p, z.p, unit.p, s); }));
+    for (int l = 1; l < (int)A.lv.size(); l++)
+        us.push_back(time_graph_us(s, reps, [&] { A.vcycle(l, A.lv[l].b.p, A.lv[l].xo.p, unit.p, s); }));
+    return us;
+}
 
 template <class T, class Tlo>
 static __global__ void k_narrow_vector(int n, const T* __restrict__ in, Tlo* __restrict__ out) {

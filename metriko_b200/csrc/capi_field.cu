@@ -5,30 +5,11 @@
 
 #include "amg_dev.cuh"
 #include "capi_util.cuh"
+#include "capi_handles.cuh"
 #include "field.cuh"
 #include "metriko_b200.h"
 
 using namespace mk;
-
-struct mk_field {
-    std::shared_ptr<Arena> arena;   // first member: destroyed last, after every buffer below went back to it
-    mk_ctx* ctx = nullptr;
-    cudaStream_t stream = nullptr;  // copies, so that destruction does not depend on the context object
-    int device = 0;
-    int nF = 0, nH = 0, N = 4;
-    DevBuf<int> face2half, next, twin, face;
-    DevBuf<double> farg;
-    FaceStencil S;
-    bool assembled = false;
-    std::unique_ptr<FaceOp> op;
-    std::unique_ptr<Pcg<cdouble>> pcg;
-    std::unique_ptr<AmgPrecond<cdouble>> amg;       // fp64 hierarchy (MK_PRECOND_FP32=0, or the host mirror path)
-    std::unique_ptr<MixedPrecond<cdouble>> amg_lo;  // fp32 V-cycle (default)
-    Precond<cdouble>* precond() { return amg_lo ? (Precond<cdouble>*)amg_lo.get() : (Precond<cdouble>*)amg.get(); }
-    DevBuf<cdouble> u, x, b;
-    RecycleSpace rec;
-    bool has_solution = false;
-};
 
 extern "C" {
 
@@ -55,12 +36,7 @@ int mk_ctx_create(int device, void* stream, mk_ctx** out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return MK_ERR_CUDA;
     if (prop.major != 10) return MK_ERR_CUDA;  // sm_100a cubin only: no other architecture can run it
-    // keep freed blocks in the stream-ordered pool instead of returning them to the driver between steps
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-        unsigned long long thresh = ~0ULL;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
-    }
+    // (device memory comes from the per-context arena, solver.cuh: the process-wide stream-ordered pool of the host application is left alone)
     mk_ctx* c = new mk_ctx();
     c->c.device = device;
     c->c.arena = std::make_shared<Arena>();
@@ -128,6 +104,7 @@ int mk_field_assemble(mk_field* f) {
                                                                               f->farg.p, f->S.nbr.p, f->S.val.p);
     MK_CHECK_LAUNCH();
     f->assembled = true;
+    if (f->pcg) f->pcg->invalidate_graph();  // the captured iteration refers to the operator / hierarchy dropped below
     f->amg.reset();
     f->amg_lo.reset();
     f->op = std::make_unique<FaceOp>(&f->S);
@@ -410,6 +387,34 @@ int mk_field_spmv_bench(mk_field* f, int reps, int fused_dot, double* ms_per_lau
     init.rho = 1.0;
     MK_CUDA(cudaMemcpyAsync(f->pcg->state(), &init, sizeof(init), cudaMemcpyHostToDevice, s));
     *ms_per_launch = time_op(*f->op, dx.p, dy.p, fused_dot ? f->pcg->state() : nullptr, f->pcg->ws(), reps, s);
+    MK_API_END(f->ctx)
+}
+
+int mk_field_profile_cycle(mk_field* f, int reps, int cap, int* n_out, double* us) {
+    if (!f || reps <= 0 || !n_out || !us) return MK_ERR_ARG;
+    MK_API_BEGIN(f->ctx)
+    MK_CUDA(cudaSetDevice(f->ctx->c.device));
+    std::vector<double> v;
+    if (f->amg_lo) v = profile_cycle<cdouble, cfloat>(*f->amg_lo, *f->amg_lo->lo, f->nF, reps, f->ctx->c.stream);
+    else if (f->amg) v = profile_cycle<cdouble, cdouble>(*f->amg, *f->amg, f->nF, reps, f->ctx->c.stream);
+    *n_out = (int)v.size();
+    for (int i = 0; i < (int)v.size() && i < cap; i++) us[i] = v[i];
+    MK_API_END(f->ctx)
+}
+
+int mk_field_hierarchy(mk_field* f, int cap, int* n_levels, int64_t* rows, int64_t* nnz_a, int64_t* nnz_p) {
+    if (!f || !n_levels) return MK_ERR_ARG;
+    MK_API_BEGIN(f->ctx)
+    std::vector<int64_t> r, a, p;
+    if (f->amg_lo) f->amg_lo->lo->describe(r, a, p);
+    else if (f->amg) f->amg->describe(r, a, p);
+    if (!r.empty() && a[0] == 0) a[0] = (int64_t)4 * f->nF;  // the face stencil: diagonal + three neighbours per row
+    *n_levels = (int)r.size();
+    for (int l = 0; l < (int)r.size() && l < cap; l++) {
+        if (rows) rows[l] = r[l];
+        if (nnz_a) nnz_a[l] = a[l];
+        if (nnz_p) nnz_p[l] = p[l];
+    }
     MK_API_END(f->ctx)
 }
 

@@ -7,9 +7,11 @@
 
 #include "amg_dev.cuh"
 #include "capi_util.cuh"
+#include "capi_handles.cuh"
 #include "csr.cuh"
 #include "field.cuh"
 #include "igm.cuh"
+#include "integ.cuh"
 #include "metriko_b200.h"
 
 using namespace mk;
@@ -50,7 +52,9 @@ extern "C" int mk_solve_smallest_eig_csc(mk_ctx* ctx, int n, const int* L_outer,
             if (M_inner[k] == c) mass[c] += M_values[2 * k];
     DeviceCsr<cdouble> dA;
     upload_csr_plain<cdouble>(dA, n, n, A.ptr.data(), A.col.data(), (const cdouble*)A.val.data(), nnz, s);
-    const bool dev_setup = !setup_on_host() && rows_sorted_strict(dA, s);
+    const bool dev_setup = !setup_on_host();
+    if (dev_setup && o.precond == 1 && !rows_sorted_strict(dA, s))
+        throw std::invalid_argument("mk_solve_smallest_eig_csc: L must be compressed with sorted inner indices (Eigen's makeCompressed() form)");
     build_sell(dA, s);
     CsrOp<cdouble> op(&dA);
     DevBuf<double> dmass(n);
@@ -131,7 +135,9 @@ extern "C" int mk_spd_factorize(mk_ctx* ctx, int n, const int* outer, const int*
     A.col.assign(inner, inner + outer[n]);
     A.val.assign(values, values + outer[n]);
     upload_csr_plain<double>(h->A, n, n, A.ptr.data(), A.col.data(), A.val.data(), (int64_t)A.col.size(), s);
-    const bool dev_setup = !setup_on_host() && rows_sorted_strict(h->A, s);
+    const bool dev_setup = !setup_on_host();
+    if (dev_setup && h->o.precond == 1 && !rows_sorted_strict(h->A, s))
+        throw std::invalid_argument("mk_spd_factorize: A must be compressed with sorted inner indices (Eigen's makeCompressed() form)");
     build_sell(h->A, s);
     h->op = std::make_unique<CsrOp<double>>(&h->A);
     h->pcg = std::make_unique<Pcg<double>>(n, s);
@@ -228,6 +234,13 @@ struct mk_igm {
     std::unique_ptr<Pcg<double>> pcg;
     DevBuf<double> x, xprev, b, tmp;
     double setup_ms = 0;
+    // mk_igm_create_from_mesh only: what integ() keeps for the result scatter (integ.ipp:88-98) and the tests
+    int N = 0, nF = 0, cut_nV = 0;
+    DevBuf<int> cutF;              // cut.idx, 3 nF
+    DeviceCsr<double> F2N;         // fullx2Nfunc, N cut.nV x n nR
+    DeviceCsr<double> X2F;         // (G2 fullx2Nfunc UFull).pruned(), assembled on the device
+    DevBuf<double> F2d;            // rawF2Vec
+    bool fullx_valid = false;      // tmp holds fullx = UFull x of the last mk_igm_round / mk_igm_poisson
 };
 
 // Dof-type labels of the reduced unknowns for the typed aggregation of the IGM hierarchy: the full dofs are numbered n * vertex + k
@@ -253,6 +266,48 @@ static HostCsr<double> csr_from_abi(int rows, int cols, const int64_t* ptr, cons
     A.col.assign(col, col + ptr[rows]);
     A.val.assign(val, val + ptr[rows]);
     return A;
+}
+
+// Device set-up shared by the three creation paths, from X2F (plain CSR, strictly increasing columns) and F2 resident on the device:
+// X^T by transposition, A0 = length^2 X^T X by the atomic-free symbolic / numeric SpGEMM (the assembly of the Poisson normal matrix
+// E = X2F^T X2F, ir_init.h:174), rhs0 = length X^T F2, multigrid hierarchy of A0 + 1e-4 I (+ its fp32 copy).
+static void igm_device_setup(mk_igm* g, DeviceCsr<double>& X, const double* d_F2, StageTimer& tm, cudaStream_t s) {
+    const int cols = g->cols;
+    const double length = g->length;
+    DeviceCsr<double> Xt;
+    transpose_dev<double>(X, Xt, false, s);
+    tm.lap("transpose X (device)");
+    spgemm<double>(Xt, X, g->A0, s);
+    k_scale_values<double><<<stream_grid(g->A0.nnz), kThreads, 0, s>>>(g->A0.nnz, g->A0.val.p, length * length);
+    tm.lap("A0 = Xt X (device)");
+    csr_matvec<double>(Xt, d_F2, g->rhs0.p, length, s);
+    MK_CUDA(cudaStreamSynchronize(s));
+    DeviceCsr<double> As;
+    if (g->o.precond == 1) {
+        copy_csr(g->A0, As, s);
+        k_shift_diagonal<double><<<(cols + 255) / 256, 256, 0, s>>>(cols, As.ptr.p, As.col.p, As.val.p, 1e-4);
+        MK_CHECK_LAUNCH();
+    }
+    build_sell(g->A0, s);
+    g->opA0 = std::make_unique<CsrOp<double>>(&g->A0, 0.0);
+    g->opA = std::make_unique<CsrOp<double>>(&g->A0, 1e-4);  // wClose^2 = 0.01^2 (ir_loop.h:109)
+    tm.lap("rhs0 + layouts");
+    if (g->o.precond == 1) {
+        DevBuf<int> ty;
+        if (typed_aggregation()) {
+            const std::vector<int> hty = igm_types_from_ufull(g->UFull);
+            ty.alloc(cols);
+            ty.upload(hty.data(), cols, s);
+            MK_CUDA(cudaStreamSynchronize(s));
+        }
+        g->amg = build_amg_device<double>(s, std::move(As), g->opA.get(), amg_params_from_env(true), std::move(ty));
+        tm.lap("build_amg_device");
+        if (precond_fp32()) {
+            lower_csr<double, float>(g->A0, g->A0_lo, s);
+            g->amg_lo = lower_precision<double>(s, std::move(g->amg), std::make_unique<CsrOp<float>>(&g->A0_lo, 1e-4));
+            tm.lap("fp32 copy of the hierarchy");
+        }
+    }
 }
 
 static int igm_create_impl(mk_ctx* ctx, int rows, int cols, const int64_t* x2f_ptr, const int* x2f_col, const double* x2f_val,
@@ -326,49 +381,17 @@ static int igm_create_impl(mk_ctx* ctx, int rows, int cols, const int64_t* x2f_p
             X.val.upload(x2f_val, (size_t)xnnz, s);
             MK_CUDA(cudaStreamSynchronize(s));
         }
-        dev_setup = rows_sorted_strict(X, s);
-        if (!dev_setup && on_device) throw std::invalid_argument("mk_igm_create_dev: X2F rows must have strictly increasing columns");
-        if (dev_setup) {
+        // Eigen's compressed storage keeps the inner indices of a row sorted and distinct, so a metriko caller always satisfies this; anything
+        // else is an argument error -- NOT a silent switch to the 20x slower host mirror (MK_SETUP=host selects that explicitly)
+        if (!rows_sorted_strict(X, s)) throw std::invalid_argument("mk_igm_create: X2F rows must have strictly increasing column indices");
+        {
             tm.lap("upload X2F");
-            DeviceCsr<double> Xt;
-            transpose_dev<double>(X, Xt, false, s);
-            tm.lap("transpose X (device)");
-            spgemm<double>(Xt, X, g->A0, s);
-            k_scale_values<double><<<stream_grid(g->A0.nnz), kThreads, 0, s>>>(g->A0.nnz, g->A0.val.p, length * length);
-            tm.lap("A0 = Xt X (device)");
             DevBuf<double> f2;
             if (!on_device) {
                 f2.alloc((size_t)rows);
                 f2.upload(F2, (size_t)rows, s);
             }
-            csr_matvec<double>(Xt, on_device ? d_F2 : f2.p, g->rhs0.p, length, s);
-            MK_CUDA(cudaStreamSynchronize(s));
-            DeviceCsr<double> As;
-            if (g->o.precond == 1) {
-                copy_csr(g->A0, As, s);
-                k_shift_diagonal<double><<<(cols + 255) / 256, 256, 0, s>>>(cols, As.ptr.p, As.col.p, As.val.p, 1e-4);
-                MK_CHECK_LAUNCH();
-            }
-            build_sell(g->A0, s);
-            g->opA0 = std::make_unique<CsrOp<double>>(&g->A0, 0.0);
-            g->opA = std::make_unique<CsrOp<double>>(&g->A0, 1e-4);  // wClose^2 = 0.01^2 (ir_loop.h:109)
-            tm.lap("rhs0 + layouts");
-            if (g->o.precond == 1) {
-                DevBuf<int> ty;
-                if (typed_aggregation()) {
-                    const std::vector<int> hty = igm_types_from_ufull(g->UFull);
-                    ty.alloc(cols);
-                    ty.upload(hty.data(), cols, s);
-                    MK_CUDA(cudaStreamSynchronize(s));
-                }
-                g->amg = build_amg_device<double>(s, std::move(As), g->opA.get(), amg_params_from_env(true), std::move(ty));
-                tm.lap("build_amg_device");
-                if (precond_fp32()) {
-                    lower_csr<double, float>(g->A0, g->A0_lo, s);
-                    g->amg_lo = lower_precision<double>(s, std::move(g->amg), std::make_unique<CsrOp<float>>(&g->A0_lo, 1e-4));
-                    tm.lap("fp32 copy of the hierarchy");
-                }
-            }
+            igm_device_setup(g.get(), X, on_device ? d_F2 : f2.p, tm, s);
         }
     }
     if (!dev_setup) {
@@ -418,6 +441,138 @@ extern "C" int mk_igm_create_dev(mk_ctx* ctx, int rows, int cols, const int64_t*
     return igm_create_impl(ctx, rows, cols, x2f_ptr_dev, x2f_col_dev, x2f_val_dev, ufull_rows, uf_ptr, uf_col, uf_val, F2_dev, length, opts, out, true);
 }
 
+// ------------------------------------------------------------------------------------------------
+// RosyParameterization::integ() from the cut-mesh arrays (integ.ipp:3-98): device assembly of G2 / F2 / X2F, result scatter
+// ------------------------------------------------------------------------------------------------
+extern "C" int mk_igm_create_from_mesh(mk_ctx* ctx, int N, int nF, int cut_nV, const int* cutF, const double* cutPos, int f2n_cols,
+                                       const int64_t* f2n_ptr, const int* f2n_col, const double* f2n_val, int ufull_cols, const int64_t* uf_ptr,
+                                       const int* uf_col, const double* uf_val, const double* F2, mk_field* field, const int* comb_turns,
+                                       double length, const mk_solve_opts* opts, mk_igm** out) {
+    if (!ctx || !out || N <= 0 || (N & 1) || nF <= 0 || cut_nV <= 0 || !cutF || !cutPos || f2n_cols <= 0 || !f2n_ptr || !f2n_col || !f2n_val ||
+        ufull_cols <= 0 || !uf_ptr || !uf_col || !uf_val)
+        return MK_ERR_ARG;
+    if (!F2 && !(field && comb_turns)) return MK_ERR_ARG;
+    MK_API_BEGIN(ctx)
+    MK_CUDA(cudaSetDevice(ctx->c.device));
+    cudaStream_t s = ctx->c.stream;
+    auto t0 = hclock::now();
+    const int64_t rows64 = (int64_t)2 * N * nF;
+    if (rows64 > 2000000000LL || (int64_t)N * cut_nV > 2000000000LL) throw std::invalid_argument("mk_igm_create_from_mesh: mesh too large for int32 CSR");
+    const int rows = (int)rows64, ufull_rows = f2n_cols, cols = ufull_cols, f2n_rows = N * cut_nV;
+    auto g = std::make_unique<mk_igm>();
+    g->arena = ctx->c.arena;
+    g->ctx = ctx;
+    g->stream = s;
+    g->device = ctx->c.device;
+    g->rows = rows; g->cols = cols; g->ufull_rows = ufull_rows;
+    g->length = length;
+    g->o = opts_or_default(opts);
+    g->N = N; g->nF = nF; g->cut_nV = cut_nV;
+    StageTimer tm("igm_create_from_mesh");
+    g->UFull = csr_from_abi(ufull_rows, cols, uf_ptr, uf_col, uf_val);
+    upload_host_csr<double>(g->dUFull, g->UFull, s);
+    g->rhs0.alloc(cols);
+    g->pcg = std::make_unique<Pcg<double>>(cols, s);
+    g->x.alloc(cols); g->xprev.alloc(cols); g->b.alloc(cols);
+    g->tmp.alloc(std::max(std::max(cols, ufull_rows), f2n_rows));
+    // fullx2Nfunc (setup.ipp:52-170 + integ.ipp:4), the corner table and the positions of the cut mesh (param.h:126-152)
+    {
+        const int64_t fnnz = f2n_ptr[f2n_rows];
+        g->F2N.rows = f2n_rows; g->F2N.cols = f2n_cols; g->F2N.nnz = fnnz;
+        g->F2N.ptr.alloc((size_t)f2n_rows + 1);
+        g->F2N.col.alloc((size_t)std::max<int64_t>(fnnz, 1));
+        g->F2N.val.alloc((size_t)std::max<int64_t>(fnnz, 1));
+        DevBuf<int64_t> p64((size_t)f2n_rows + 1);
+        p64.upload(f2n_ptr, (size_t)f2n_rows + 1, s);
+        k_narrow_ptr<<<(f2n_rows + 256) / 256, 256, 0, s>>>(f2n_rows + 1, p64.p, g->F2N.ptr.p);
+        MK_CHECK_LAUNCH();
+        g->F2N.col.upload(f2n_col, (size_t)fnnz, s);
+        g->F2N.val.upload(f2n_val, (size_t)fnnz, s);
+        MK_CUDA(cudaStreamSynchronize(s));
+        if (!rows_sorted_strict(g->F2N, s)) throw std::invalid_argument("mk_igm_create_from_mesh: fullx2Nfunc rows must have strictly increasing column indices");
+    }
+    g->cutF.alloc((size_t)3 * nF);
+    g->cutF.upload(cutF, (size_t)3 * nF, s);
+    DevBuf<double> pos((size_t)3 * cut_nV);
+    pos.upload(cutPos, (size_t)3 * cut_nV, s);
+    g->F2d.alloc((size_t)rows);
+    if (F2) {
+        g->F2d.upload(F2, (size_t)rows, s);
+    } else {
+        if (!field->has_solution || field->nF != nF || field->N != N) throw std::invalid_argument("mk_igm_create_from_mesh: the field handle holds no solution of this mesh");
+        DevBuf<int> turns((size_t)nF);
+        turns.upload(comb_turns, (size_t)nF, s);
+        k_f2_from_field<<<stream_grid(nF), kThreads, 0, s>>>(nF, N, field->x.p, turns.p, g->F2d.p);
+        MK_CHECK_LAUNCH();
+        MK_CUDA(cudaStreamSynchronize(s));
+    }
+    tm.lap("uploads (corner table, positions, fullx2Nfunc, UFull, F2 / turns)");
+    {
+        DeviceCsr<double> T;  // fullx2Nfunc * UFull: which reduced dofs (with which sign / kernel weight) a cut-vertex function reads
+        DeviceCsr<double> U;
+        copy_csr(g->dUFull, U, s);
+        spgemm<double>(g->F2N, U, T, s);
+        tm.lap("T = fullx2Nfunc UFull (device SpGEMM)");
+        build_x2f(N, nF, g->cutF.p, pos.p, T, g->X2F, s);
+        MK_CUDA(cudaStreamSynchronize(s));
+        tm.lap("X2F rows (per-face gradient stencil, 3-way merge)");
+    }
+    igm_device_setup(g.get(), g->X2F, g->F2d.p, tm, s);
+    MK_CUDA(cudaStreamSynchronize(s));
+    g->setup_ms = ms_since(t0);
+    *out = g.release();
+    MK_API_END(ctx)
+}
+
+extern "C" int mk_igm_get_x2f(mk_igm* g, int64_t* nnz, int64_t* ptr, int* col, double* val, double* F2) {
+    if (!g || !nnz || !g->X2F.ptr.p) return MK_ERR_ARG;
+    MK_API_BEGIN(g->ctx)
+    cudaStream_t s = g->ctx->c.stream;
+    *nnz = g->X2F.nnz;
+    if (ptr && col && val) {
+        std::vector<int> p32((size_t)g->rows + 1);
+        g->X2F.ptr.download(p32.data(), (size_t)g->rows + 1, s);
+        g->X2F.col.download(col, (size_t)g->X2F.nnz, s);
+        g->X2F.val.download(val, (size_t)g->X2F.nnz, s);
+        MK_CUDA(cudaStreamSynchronize(s));
+        for (int i = 0; i <= g->rows; i++) ptr[i] = p32[i];
+    }
+    if (F2) {
+        g->F2d.download(F2, (size_t)g->rows, s);
+        MK_CUDA(cudaStreamSynchronize(s));
+    }
+    MK_API_END(g->ctx)
+}
+
+// integ.ipp:88-98: NF = fullx2Nfunc * fullx ; nfn = NF as cut.nV x N ; cfn(f, N j + k) = nfn(cut.idx(f, j), k)
+extern "C" int mk_igm_scatter(mk_igm* g, const double* fullx, double* nfn, double* cfn) {
+    if (!g || !g->F2N.ptr.p || (!nfn && !cfn)) return MK_ERR_ARG;
+    if (!fullx && !g->fullx_valid) return MK_ERR_ARG;
+    MK_API_BEGIN(g->ctx)
+    MK_CUDA(cudaSetDevice(g->ctx->c.device));
+    cudaStream_t s = g->ctx->c.stream;
+    DevBuf<double> fx;
+    const double* d_fullx = g->tmp.p;
+    if (fullx) {
+        fx.alloc((size_t)g->ufull_rows);
+        fx.upload(fullx, (size_t)g->ufull_rows, s);
+        d_fullx = fx.p;
+    }
+    const size_t nn = (size_t)g->N * g->cut_nV;
+    DevBuf<double> d_nfn(nn);
+    csr_matvec<double>(g->F2N, d_fullx, d_nfn.p, 1.0, s);
+    if (nfn) d_nfn.download(nfn, nn, s);
+    if (cfn) {
+        const size_t nc = (size_t)g->nF * 3 * g->N;
+        DevBuf<double> d_cfn(nc);
+        k_corner_gather<<<stream_grid((int64_t)nc), kThreads, 0, s>>>(g->nF, g->N, g->cutF.p, d_nfn.p, d_cfn.p);
+        MK_CHECK_LAUNCH();
+        d_cfn.download(cfn, nc, s);
+    }
+    MK_CUDA(cudaStreamSynchronize(s));
+    MK_API_END(g->ctx)
+}
+
 extern "C" int mk_igm_destroy(mk_igm* g) {
     if (!g) return MK_OK;
     AllocStreamScope sc(g->stream);
@@ -436,6 +591,34 @@ extern "C" int mk_igm_get_matrix(mk_igm* g, int64_t* nnz, int* rowptr, int* col,
         g->A0.col.download(col, g->A0.nnz, s);
         g->A0.val.download(val, g->A0.nnz, s);
         MK_CUDA(cudaStreamSynchronize(s));
+    }
+    MK_API_END(g->ctx)
+}
+
+extern "C" int mk_igm_profile_cycle(mk_igm* g, int reps, int cap, int* n_out, double* us) {
+    if (!g || reps <= 0 || !n_out || !us) return MK_ERR_ARG;
+    MK_API_BEGIN(g->ctx)
+    MK_CUDA(cudaSetDevice(g->ctx->c.device));
+    std::vector<double> v;
+    if (g->amg_lo) v = profile_cycle<double, float>(*g->amg_lo, *g->amg_lo->lo, g->cols, reps, g->ctx->c.stream);
+    else if (g->amg) v = profile_cycle<double, double>(*g->amg, *g->amg, g->cols, reps, g->ctx->c.stream);
+    *n_out = (int)v.size();
+    for (int i = 0; i < (int)v.size() && i < cap; i++) us[i] = v[i];
+    MK_API_END(g->ctx)
+}
+
+extern "C" int mk_igm_hierarchy(mk_igm* g, int cap, int* n_levels, int64_t* rows, int64_t* nnz_a, int64_t* nnz_p) {
+    if (!g || !n_levels) return MK_ERR_ARG;
+    MK_API_BEGIN(g->ctx)
+    std::vector<int64_t> r, a, p;
+    if (g->amg_lo) g->amg_lo->lo->describe(r, a, p);
+    else if (g->amg) g->amg->describe(r, a, p);
+    if (!r.empty() && a[0] == 0) a[0] = g->A0.nnz;
+    *n_levels = (int)r.size();
+    for (int l = 0; l < (int)r.size() && l < cap; l++) {
+        if (rows) rows[l] = r[l];
+        if (nnz_a) nnz_a[l] = a[l];
+        if (nnz_p) nnz_p[l] = p[l];
     }
     MK_API_END(g->ctx)
 }
@@ -569,8 +752,8 @@ struct IgmRun {
         st.kernel_launches += ss.launches;
         if (ss.status != 0 && st.status == MK_OK) st.status = status_of(ss.status);
         if (getenv("MK_VERBOSE"))
-            fprintf(stderr, "[mk] igm solve #%d: constraints %d, iterations %d (restarts %d), relres %.2e\n", st.outer_iterations, proj.k, ss.iterations,
-                    ss.restarts, ss.relres);
+            fprintf(stderr, "[mk] igm solve #%d: constraints %d, iterations %d (restarts %d), relres %.2e, iteration batches %.3f ms\n", st.outer_iterations,
+                    proj.k, ss.iterations, ss.restarts, ss.relres, ss.iter_ms);
         return ss;
     }
     // Poisson stage: min ||length X2F x - F2|| s.t. UFull[fixed] x = vals  (ir_init.h:173-212)
@@ -596,7 +779,8 @@ std::vector<int> concat_idcs(int n_fixed, const int* fixedIdcs, int n_sing, cons
 
 void full_from_small(mk_igm* g, cudaStream_t s, double* host_out) {
     spmv_plain(g->dUFull, g->x.p, g->tmp.p, false, nullptr, s);
-    g->tmp.download(host_out, g->ufull_rows, s);
+    g->fullx_valid = true;
+    if (host_out) g->tmp.download(host_out, g->ufull_rows, s);
     MK_CUDA(cudaStreamSynchronize(s));
 }
 
@@ -638,7 +822,14 @@ extern "C" int mk_igm_round(mk_igm* g, int n_fixed, const int* fixedIdcs, const 
     // ---- NI stage: Poisson solution, then the closed form of the linear LM
     run.poisson(n_fixed, fixedIdcs, fixedVals);
     bool ok = true;
-    if (seamless) {
+    // a Poisson solve that broke down (degenerate input: NaN / Inf in X2F or F2, or a non-SPD operator) must not enter the rounding loop
+    const bool poisson_failed = run.st.status == MK_ERR_NOT_SPD || !(run.st.relres_max == run.st.relres_max);
+    if (poisson_failed) {
+        if (n_fixed_out) *n_fixed_out = 0;
+        if (stats) *stats = run.st;
+        rc = run.st.status == MK_OK ? MK_ERR_NOT_SPD : run.st.status;
+    }
+    if (seamless && !poisson_failed) {
         // SI right-hand side base: X2F^T F2_ with F2_ = (1e8 length B x + F2) / (1e8 + 1)  ->  (1e8 A0 x + rhs0) / (1e8 + 1)
         DevBuf<double> base(g->cols);
         g->opA0->apply(g->x.p, g->tmp.p, nullptr, run.g->pcg->ws(), s);
@@ -666,8 +857,10 @@ extern "C" int mk_igm_round(mk_igm* g, int n_fixed, const int* fixedIdcs, const 
                 if (d < minDif) { second = minDif; minIdx = (int)i; minDif = d; }
                 else if (d < second) second = d;
             }
+            if (minIdx < 0) { ok = false; break; }  // every candidate value is NaN / Inf: a diverged solve, not a rounding decision
             const int idx = left[minIdx];
             const double X = run.value_of(idx);
+            if (!std::isfinite(X) || std::fabs(X) > 2.0e9) { ok = false; break; }
             const int val = (int)std::round(X);
             left.erase(left.begin() + minIdx);
             if (left.empty() && !roundSeams && !roundedSingulars) {
@@ -710,6 +903,6 @@ extern "C" int mk_igm_round(mk_igm* g, int n_fixed, const int* fixedIdcs, const 
     run.st.setup_ms = g->setup_ms;
     run.st.solve_ms = ms_since(t0);
     if (stats) *stats = run.st;
-    rc = !ok ? MK_ERR_ROUNDING : run.st.status;
+    if (!poisson_failed) rc = !ok ? MK_ERR_ROUNDING : run.st.status;
     MK_API_END_RC(g->ctx, rc)
 }

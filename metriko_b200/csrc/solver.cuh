@@ -334,6 +334,7 @@ struct SolveStats {
     double relres = 0.0;  // true ||b - A x|| / ||b|| at exit
     int status = 0;       // 0 ok, 1 maxit, 2 breakdown
     long launches = 0;
+    double iter_ms = 0.0;  // device time of the iteration batches alone (events; only measured when MK_VERBOSE is set)
 };
 
 template <class T>
@@ -346,6 +347,7 @@ public:
         grid_ = stream_grid(n);
     }
     ~Pcg() {
+        if (ev0_) { cudaEventDestroy(ev0_); cudaEventDestroy(ev1_); }
         if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
         PinnedStatePool::instance().put(h_st_);
     }
@@ -382,16 +384,26 @@ public:
         }
         bool breakdown = false;
         double prev_relres = 1e300;
+        static const bool timed = getenv("MK_VERBOSE") != nullptr;
+        if (timed && !ev0_) { MK_CUDA(cudaEventCreate(&ev0_)); MK_CUDA(cudaEventCreate(&ev1_)); }
         for (int attempt = 0; attempt < 4; attempt++) {
             start_direction();
             launches += 1 + (M_ ? M_->launches_per_apply() : 0);
-            int batch = hint > 0 ? std::min(std::max(hint, 1), 4 * chunk) : chunk;
+            int batch = hint > 0 ? std::min(std::max(hint, 1), 8 * chunk) : chunk;
+            if (timed) MK_CUDA(cudaEventRecord(ev0_, stream_));
             while (true) {
                 for (int c = 0; c < batch; c++) iteration(x, use_graph);
                 launches += (long)batch * launches_per_iteration();
                 fetch_state();
                 if (h_st_->done) break;
                 batch = hint > 0 ? std::max(2, chunk / 4) : chunk;
+            }
+            if (timed) {
+                MK_CUDA(cudaEventRecord(ev1_, stream_));
+                MK_CUDA(cudaEventSynchronize(ev1_));
+                float ms = 0;
+                MK_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
+                out.iter_ms += ms;
             }
             breakdown = h_st_->done == 2;
             // true residual check (recurrence residuals drift at the 1e-10 level)
@@ -497,6 +509,7 @@ private:
     Projector<T>* P_ = nullptr;
     cudaGraphExec_t graph_exec_ = nullptr;
     T* graph_x_ = nullptr;
+    cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
 };
 
 }  // namespace mk

@@ -1,16 +1,23 @@
-// The coarse tail of the multigrid V-cycle as ONE kernel: every level with at most kTailRows rows (pre-smoothing, restriction, ...,
+// The coarse tail of the multigrid V-cycle as ONE kernel: every level with at most MK_TAIL_ROWS rows (pre-smoothing, restriction, ...,
 // the dense coarsest solve, ..., prolongation, post-smoothing) runs inside a single thread-block cluster, phase after phase, separated
-// by the hardware cluster barrier (~0.2 us) instead of kernel boundaries (4-9 us each when the kernel has nothing to stream).
+// by the hardware cluster barrier instead of kernel boundaries.
 //
-// Why: at 1M vertices the levels below ~25k rows hold 1 % of the rows but were 17-25 launches = 100-150 us of the ~500 us PCG iteration
-// (profiles/launches_r01g_*: 3-18 us kernels at 1-10 % of the DRAM peak and 12 % warps active -- pure launch latency).
-// The reference has nothing to compare with (its factorisation, sls.h:42-43 / ir.h:14-20, is one sequential sparse triangular solve).
+// MEASURED NEGATIVE RESULT -- OFF BY DEFAULT (MK_TAIL_ROWS=32768 switches it on). The round-1 launch lists (profiles/launches_r01g_*)
+// showed the levels below ~25k rows as 17-25 launches of 3-18 us under ncu, and a single persistent kernel looked like the fix. Timed
+// live as graph replays on the B200 (profiles/cycle_probe_r02_*.json, 1M vertices) the separate launches cost far less than ncu's
+// serialised figures suggest -- the whole cycle from the 22k-row level downwards (13 launches) takes 43 us for the face hierarchy and
+// 70 us for the IGM one, 3.4 us per launch including its gap -- because each of them spreads over 148 SMs, while one cluster is
+// confined to 16 SMs of one GPC: every phase is a chain of 3-4 dependent L2 round trips whichever way it is launched, and 16k threads
+// need several such chains per phase where the full grid needs one. This kernel takes 105 us (face) / 172 us (IGM) for the same
+// levels with 16 CTAs and 137 / 252 us with 8; restricted to the levels below 16k rows it still loses (27 against 22.5 us).
+// It stays in the tree as the measured alternative; the defaults run one launch per phase.
 //
 // Layout: one cluster of 16 CTAs (8 if the device refuses the non-portable size) x 1024 threads on one GPC; vectors and operators stay
 // in L2 (a few MB per level), every phase is a lanes-per-row CSR SpMV with the smoother update as its epilogue, exactly the forms of
-// SpmvMode (csr.cuh). Rows longer than kTailLongRow (the dense dofs of the IGM hierarchy: coupled to every aggregate along their seam)
-// are summed by a whole CTA each before the regular rows. Vectors written in one phase and gathered in the next are accessed with
-// ld.global.cg / st.global.cg (L2 only): the barrier orders the accesses, L2 is the point of coherence between the SMs of the cluster.
+// SpmvMode (csr.cuh). Rows much longer than the mean get a warp, rows above kTailHugeRow entries (the dense dofs of the IGM hierarchy,
+// coupled to every aggregate along their seam) a whole CTA, before the regular rows. Vectors written in one phase and gathered in the
+// next are accessed with ld.global.cg / st.global.cg (L2 only): the barrier orders the accesses, L2 is the point of coherence between
+// the SMs of the cluster.
 #pragma once
 #include <cooperative_groups.h>
 
@@ -22,17 +29,22 @@ namespace cg = cooperative_groups;
 
 constexpr int kTailMaxLevels = 10;
 constexpr int kTailThreads = 1024;
-constexpr int kTailLongRow = 1024;
-constexpr int kTailRowsDefault = 32768;
+constexpr int kTailHugeRow = 2048;   // rows longer than this are summed by a whole CTA
+constexpr int kTailMedRowMin = 64;   // rows longer than max(this, 4 x the mean row length) get a warp of their own
+constexpr int kTailRowsDefault = 0;  // off: see the header comment
 
+// one CSR operand of the tail with its row classes: regular rows (<= cut entries: G lanes each), medium rows (a warp each), huge rows (a CTA each)
+template <class T>
+struct TailMat {
+    const int *ptr, *col;
+    const T* val;
+    const int *med, *huge;
+    int n_med, n_huge, cut, gmax;
+};
 template <class T>
 struct TailLevel {
     int n, deg;
-    const int *Ap, *Ac; const T* Av; int gA;  // A_l, lanes per row
-    const int *Pp, *Pc; const T* Pv; int gP;  // P_l : n_l x n_{l+1}
-    const int *Rp, *Rc; const T* Rv; int gR;  // R_l : n_{l+1} x n_l
-    const int *longA, *longP, *longR;         // rows longer than kTailLongRow
-    int n_longA, n_longP, n_longR;
+    TailMat<T> A, P, R;  // A_l ; P_l : n_l x n_{l+1} ; R_l : n_{l+1} x n_l
     const T* dinv;
     T *x, *xo, *b, *r, *d, *q;
     double inv_theta, delta, sigma;
@@ -56,11 +68,16 @@ template <> __device__ __forceinline__ void st_cg<cfloat>(cfloat* p, cfloat v) {
 template <> __device__ __forceinline__ void st_cg<cdouble>(cdouble* p, cdouble v) { __stcg(reinterpret_cast<double2*>(p), make_double2(v.x, v.y)); }
 
 // y_row = sum_k val[k] x[col[k]] over the whole cluster, `epi(row, sum)` called once per row by one thread.
+// The cluster has 16k threads and every load is an L2 round trip (~250 cycles), so the shape is chosen for memory-level parallelism, not
+// for coalescing: as few lanes per row as keeps all threads busy (G = threads / rows, a thread per row on the 22k-row level -- the first
+// version used 8-32 lanes per row there: 22 dependent rounds per thread and 200 us per cycle), four entries in flight per lane.
 template <class T, class Epi>
-__device__ __forceinline__ void tail_spmv(int n, const int* __restrict__ ptr, const int* __restrict__ col, const T* __restrict__ val, int G,
-                                          const int* __restrict__ long_rows, int n_long, const T* x, int brank, int nblocks, double* red, Epi epi) {
-    for (int i = brank; i < n_long; i += nblocks) {  // one CTA per long row (uniform per CTA: block_sum synchronises)
-        const int row = __ldg(long_rows + i);
+__device__ __forceinline__ void tail_spmv(int n, const TailMat<T>& M, const T* x, int brank, int nblocks, double* red, Epi epi) {
+    const int* __restrict__ ptr = M.ptr;
+    const int* __restrict__ col = M.col;
+    const T* __restrict__ val = M.val;
+    for (int i = brank; i < M.n_huge; i += nblocks) {  // one CTA per huge row (uniform per CTA: block_sum synchronises)
+        const int row = __ldg(M.huge + i);
         const int b = __ldg(ptr + row), en = __ldg(ptr + row + 1);
         T a0 = ST<T>::zero(), a1 = ST<T>::zero();
         int k = b + threadIdx.x;
@@ -73,9 +90,34 @@ __device__ __forceinline__ void tail_spmv(int n, const int* __restrict__ ptr, co
         const T sum = block_sum_t(a0 + a1, red);
         if (threadIdx.x == 0) epi(row, sum);
     }
+    {   // one warp per medium row
+        const int lane = threadIdx.x & 31;
+        const int nwarps = nblocks * (kTailThreads / 32);
+        for (int i = brank * (kTailThreads / 32) + (threadIdx.x >> 5); i < M.n_med; i += nwarps) {
+            const int row = __ldg(M.med + i);
+            const int b = __ldg(ptr + row), en = __ldg(ptr + row + 1);
+            T a0 = ST<T>::zero(), a1 = ST<T>::zero();
+            int k = b + lane;
+            for (; k + 96 < en; k += 128) {
+                const int c0 = __ldg(col + k), c1 = __ldg(col + k + 32), c2 = __ldg(col + k + 64), c3 = __ldg(col + k + 96);
+                const T v0 = ld_ro(val + k), v1 = ld_ro(val + k + 32), v2 = ld_ro(val + k + 64), v3 = ld_ro(val + k + 96);
+                const T x0 = ld_cg(x + c0), x1 = ld_cg(x + c1), x2 = ld_cg(x + c2), x3 = ld_cg(x + c3);
+                a0 = ST<T>::fma_(v0, x0, a0);
+                a1 = ST<T>::fma_(v1, x1, a1);
+                a0 = ST<T>::fma_(v2, x2, a0);
+                a1 = ST<T>::fma_(v3, x3, a1);
+            }
+            for (; k < en; k += 32) a0 = ST<T>::fma_(ld_ro(val + k), ld_cg(x + __ldg(col + k)), a0);
+            const T sum = group_sum<T>(a0 + a1, 32);
+            if (lane == 0) epi(row, sum);
+        }
+    }
+    const int nthreads = nblocks * kTailThreads;
+    int G = 1;
+    while (G < M.gmax && 2 * G * n <= nthreads) G <<= 1;  // lanes per row: only as many as there are idle threads
     const int tid = brank * kTailThreads + threadIdx.x;
     const int sub = tid & (G - 1);
-    const int ngroups = (nblocks * kTailThreads) / G;
+    const int ngroups = nthreads / G;
     const int nloop = (n + ngroups - 1) / ngroups;  // same trip count for every thread: the shuffles need whole warps
     int row = tid / G;
     for (int it = 0; it < nloop; it++, row += ngroups) {
@@ -84,18 +126,21 @@ __device__ __forceinline__ void tail_spmv(int n, const int* __restrict__ ptr, co
         if (live) {
             b = __ldg(ptr + row);
             en = __ldg(ptr + row + 1);
-            if (en - b > kTailLongRow) live = false;
+            if (en - b > M.cut) live = false;  // medium / huge row: served above
         }
         T a0 = ST<T>::zero(), a1 = ST<T>::zero();
         if (live) {
             int k = b + sub;
-            for (; k + G < en; k += 2 * G) {
-                const int c0 = __ldg(col + k), c1 = __ldg(col + k + G);
-                const T v0 = ld_ro(val + k), v1 = ld_ro(val + k + G);
-                a0 = ST<T>::fma_(v0, ld_cg(x + c0), a0);
-                a1 = ST<T>::fma_(v1, ld_cg(x + c1), a1);
+            for (; k + 3 * G < en; k += 4 * G) {
+                const int c0 = __ldg(col + k), c1 = __ldg(col + k + G), c2 = __ldg(col + k + 2 * G), c3 = __ldg(col + k + 3 * G);
+                const T v0 = ld_ro(val + k), v1 = ld_ro(val + k + G), v2 = ld_ro(val + k + 2 * G), v3 = ld_ro(val + k + 3 * G);
+                const T x0 = ld_cg(x + c0), x1 = ld_cg(x + c1), x2 = ld_cg(x + c2), x3 = ld_cg(x + c3);
+                a0 = ST<T>::fma_(v0, x0, a0);
+                a1 = ST<T>::fma_(v1, x1, a1);
+                a0 = ST<T>::fma_(v2, x2, a0);
+                a1 = ST<T>::fma_(v3, x3, a1);
             }
-            if (k < en) a0 = ST<T>::fma_(ld_ro(val + k), ld_cg(x + __ldg(col + k)), a0);
+            for (; k < en; k += G) a0 = ST<T>::fma_(ld_ro(val + k), ld_cg(x + __ldg(col + k)), a0);
         }
         const T sum = group_sum<T>(a0 + a1, G);
         if (live && sub == 0) epi(row, sum);
@@ -142,7 +187,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) k_vcycle_tail(const __grid_co
             T* d_next = last ? nullptr : (d_cur == L.d ? L.q : L.d);
             T* xv = L.x;
             const T* dc = d_cur;
-            tail_spmv<T>(L.n, L.Ap, L.Ac, L.Av, L.gA, L.longA, L.n_longA, dc, brank, nb, red, [&](int row, T acc) {
+            tail_spmv<T>(L.n, L.A, dc, brank, nb, red, [&](int row, T acc) {
                 const T di = ld_cg(dc + row);
                 const T ri = (first ? ld_cg(L.b + row) : ld_cg(L.r + row)) - acc;
                 if (!first) st_cg(xv + row, ld_cg(xv + row) + di);
@@ -156,7 +201,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) k_vcycle_tail(const __grid_co
         }
         const bool coarsest = j + 2 == m;
         T* cstart = C.deg == 1 ? C.x : C.d;
-        tail_spmv<T>(C.n, L.Rp, L.Rc, L.Rv, L.gR, L.longR, L.n_longR, L.r, brank, nb, red, [&](int row, T acc) {
+        tail_spmv<T>(C.n, L.R, L.r, brank, nb, red, [&](int row, T acc) {
             st_cg(C.b + row, acc);
             if (!coarsest) st_cg(cstart + row, ST<T>::scale(C.inv_theta, ld_ro(C.dinv + row) * acc));
         });
@@ -173,17 +218,17 @@ __global__ void __launch_bounds__(kTailThreads, 1) k_vcycle_tail(const __grid_co
         const TailLevel<T>& L = D.lv[j];
         const TailLevel<T>& C = D.lv[j + 1];
         T* xo = j == 0 ? xo_top : L.xo;
-        tail_spmv<T>(L.n, L.Pp, L.Pc, L.Pv, L.gP, L.longP, L.n_longP, C.xo, brank, nb, red,
+        tail_spmv<T>(L.n, L.P, C.xo, brank, nb, red,
                      [&](int row, T acc) { st_cg(L.x + row, ld_cg(L.x + row) + acc); });
         cl.sync();
         if (L.deg == 1) {
-            tail_spmv<T>(L.n, L.Ap, L.Ac, L.Av, L.gA, L.longA, L.n_longA, L.x, brank, nb, red, [&](int row, T acc) {
+            tail_spmv<T>(L.n, L.A, L.x, brank, nb, red, [&](int row, T acc) {
                 const T ri = ld_cg(L.b + row) - acc;
                 st_cg(xo + row, ld_cg(L.x + row) + ST<T>::scale(L.inv_theta, ld_ro(L.dinv + row) * ri));
             });
             cl.sync();
         } else {
-            tail_spmv<T>(L.n, L.Ap, L.Ac, L.Av, L.gA, L.longA, L.n_longA, L.x, brank, nb, red, [&](int row, T acc) {
+            tail_spmv<T>(L.n, L.A, L.x, brank, nb, red, [&](int row, T acc) {
                 const T ri = ld_cg(L.b + row) - acc;
                 st_cg(L.r + row, ri);
                 st_cg(L.d + row, ST<T>::scale(L.inv_theta, ld_ro(L.dinv + row) * ri));
@@ -197,7 +242,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) k_vcycle_tail(const __grid_co
                 const bool lastk = k + 2 == L.deg;
                 T* d_next = d_cur == L.d ? L.q : L.d;
                 const T* dc = d_cur;
-                tail_spmv<T>(L.n, L.Ap, L.Ac, L.Av, L.gA, L.longA, L.n_longA, dc, brank, nb, red, [&](int row, T acc) {
+                tail_spmv<T>(L.n, L.A, dc, brank, nb, red, [&](int row, T acc) {
                     const T di = ld_cg(dc + row);
                     const T ri = ld_cg(L.r + row) - acc;
                     const T dn = ST<T>::scale(c1, di) + ST<T>::scale(c2, ld_ro(L.dinv + row) * ri);

@@ -136,6 +136,14 @@ class Session:
             integerIdcs=self.get("integerIdcs"), singularIdcs=self.get("singularIdcs"),
         )
 
+    def igm_mesh_inputs(self) -> dict:
+        """What RosyParameterization::integ() itself reads (integ.ipp:3-43), for mk_igm_create_from_mesh: the cut mesh (corner table in F's
+        corner order + positions, param.h:126-152), fullx2Nfunc (setup.ipp:52-170, integ.ipp:4) and the per-face combing turns (frf.h:207-249)."""
+        cut2raw = self.get("cut2raw")
+        pos = self.get("pos").reshape(-1, 3)
+        return dict(cutF=self.get("cutF").reshape(-1, 3), cutPos=np.ascontiguousarray(pos[cut2raw]), fullx2Nfunc=self.csr("fullx2Nfunc"),
+                    comb_turns=self.get("comb_turns"))
+
     def igm_finish(self, fullx) -> dict:
         self.put("fullx", np.asarray(fullx, np.float64))
         self._chk(self._L.hg_igm_finish(self._h))

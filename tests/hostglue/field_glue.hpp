@@ -283,6 +283,7 @@ inline void run_field_stage(const Hmesh& m, Bag& bag, int N, int matching_type, 
     std::vector<int> seam_i(fs.seam.begin(), fs.seam.end());
     bag.put("seam", seam_i);
     bag.put("cfield", fs.cfield);
+    bag.put("comb_turns", turns);  // per-face turn of the combing BFS (frf.h:207-249): cfield(f, k) = field(f, (k + turn) % N)
     bag.put("cmatching", fs.cmatching);
     bag.put("ext", fs.ext);
     int nvisited = 0;
