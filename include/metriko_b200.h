@@ -108,7 +108,9 @@ int mk_field_spmv_bench(mk_field* f, int reps, int fused_dot, double* ms_per_lau
  * the first `cap` of them, rows, stored entries of A_l and of the prolongator P_l. Used by bench.py for the per-iteration byte count. */
 int mk_field_hierarchy(mk_field* f, int cap, int* n_levels, int64_t* rows, int64_t* nnz_a, int64_t* nnz_p);
 /* Live timing of the preconditioner of the last solve, replayed `reps` times as a CUDA graph between two events (warm, back to back, as
- * inside a solve): us[0] = one whole application (hand-over + V-cycle + hand-back), us[l] = the cycle from level l downwards, l >= 1. */
+ * inside a solve): us[0] = one whole application (hand-over + V-cycle + hand-back), us[l] = the cycle from level l downwards, 1 <= l < levels;
+ * then, when the fused PCG body is in use, three more entries: the x / r update fused with the hand-over, the cycle with the fused <r,z>
+ * reduction, the direction update. */
 int mk_field_profile_cycle(mk_field* f, int reps, int cap, int* n_out, double* us);
 
 /* One-shot drop-in for solveSmallestEig(SprsC& L, SprsC& M, int nIter) on Eigen CSC arrays (sls.h:29): L Hermitian

@@ -63,9 +63,10 @@ class FaceRosyField:
         self.ctx.check(self.ctx.L.mk_field_get_operator(self.h, ptr(rowptr), ptr(col), ptr(val), ptr(mass)))
         return sp.csr_matrix((val, col, rowptr), shape=(self.nF, self.nF)), mass
 
-    def solveSmallestEig(self, u0, nIter: int = 50, **opts):
+    def solveSmallestEig(self, u0, nIter: int = 50, out=None, **opts):
+        """`out`: preallocated (e.g. pinned) complex128 array of length nF for the result."""
         u0 = as_c128(u0)
-        x = np.empty(self.nF, np.complex128)
+        x = out if out is not None else np.empty(self.nF, np.complex128)
         st = Stats()
         o = default_opts(**opts)
         rc = self.ctx.L.mk_field_solve(self.h, ptr(u0), nIter, C.byref(o), ptr(x), C.byref(st))
@@ -311,10 +312,11 @@ class IgmProblem:
         self.ctx.check(self.ctx.L.mk_igm_get_x2f(self.h, C.byref(nnz), ptr(p64), ptr(col), ptr(val), ptr(f2)))
         return sp.csr_matrix((val, col, p64), shape=(self.rows, self.cols)), f2
 
-    def scatter(self, fullx=None, want_cfn: bool = True):
-        """Result scatter (integ.ipp:88-98) on the device: (nfn[cut_nV x N], cfn[nF x 3N]); fullx None = the last rounding result, still resident."""
-        nfn = np.empty((self.cut_nV, self.N), np.float64)
-        cfn = np.empty((self.nF, 3 * self.N), np.float64) if want_cfn else None
+    def scatter(self, fullx=None, want_cfn: bool = True, out=None):
+        """Result scatter (integ.ipp:88-98) on the device: (nfn[cut_nV x N], cfn[nF x 3N]); fullx None = the last rounding result, still resident.
+        out = (nfn, cfn) preallocated (e.g. pinned) float64 arrays of those shapes."""
+        nfn = out[0] if out is not None else np.empty((self.cut_nV, self.N), np.float64)
+        cfn = (out[1] if out is not None else np.empty((self.nF, 3 * self.N), np.float64)) if want_cfn else None
         fx = as_f64(fullx) if fullx is not None else None
         self.ctx.check(self.ctx.L.mk_igm_scatter(self.h, ptr(fx), ptr(nfn), ptr(cfn)))
         return nfn, cfn

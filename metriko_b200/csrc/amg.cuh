@@ -997,6 +997,22 @@ inline std::vector<double> profile_cycle(Precond<T>& M, AmgPrecond<TA>& A, int n
     us.push_back(time_graph_us(s, reps, [&] { M.apply(r.p, z.p, unit.p, s); }));
     for (int l = 1; l < (int)A.lv.size(); l++)
         us.push_back(time_graph_us(s, reps, [&] { A.vcycle(l, A.lv[l].b.p, A.lv[l].xo.p, unit.p, s); }));
+    // the two fused PCG vector kernels either side of the cycle (alpha = beta = 0: the vectors stay what they are)
+    if (M.fused_pcg()) {
+        DevBuf<T> x(n), p(n), q(n);
+        x.zero(s); p.zero(s); q.zero(s);
+        DevBuf<double> partials((size_t)kMaxPartials * 4);
+        DevBuf<unsigned int> ticket(1);
+        ticket.zero(s);
+        h.thresh = -1.0;
+        h.maxit = 0x7fffffff;
+        unit.upload(&h, 1, s);
+        MK_CUDA(cudaStreamSynchronize(s));
+        ReduceWs ws{partials.p, ticket.p};
+        us.push_back(time_graph_us(s, reps, [&] { M.update_xr_handover(n, x.p, r.p, p.p, q.p, unit.p, ws, s); }));
+        us.push_back(time_graph_us(s, reps, [&] { M.cycle_dot(r.p, unit.p, ws, s); }));
+        us.push_back(time_graph_us(s, reps, [&] { M.update_p(n, p.p, unit.p, s); }));
+    }
     return us;
 }
 

@@ -22,22 +22,12 @@ from metriko_b200.dist import DistContext, DistFaceField  # noqa: E402
 from hostglue import Session  # noqa: E402
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--kind", type=int, default=4)
-    ap.add_argument("--levels", type=int, default=11)
-    ap.add_argument("--reps", type=int, default=100)
-    ap.add_argument("--outer", type=int, default=0, help="also run this many inverse-iteration steps")
-    ap.add_argument("--both", action="store_true", help="also time the block-Jacobi preconditioner")
-    args = ap.parse_args()
-    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    ctx = capi.Context(local)
+def run_partitioned(ctx, rank, world, kind=4, levels=11, reps=100, outer=0, both=False):
+    """The partitioned-mode measurements on an already initialised process group / capi.Context; returns the result dict on every rank.
+    Used by this script and by bench.py (--gpus N > 1: the `partitioned` object of the bench line)."""
     d = DistContext(ctx, rank, world)
     t0 = time.time()
-    s = Session().make_sphere(args.kind, args.levels, bump=0.08)
+    s = Session().make_sphere(kind, levels, bump=0.08)
     fi = s.field_inputs()
     nF, nV = s.dims["nF"], s.dims["nV"]
     t_mesh = time.time() - t0
@@ -53,15 +43,15 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    ms_ov = maxr(F.spmv_bench(args.reps, True))
-    ms_no = maxr(F.spmv_bench(args.reps, False))
+    ms_ov = maxr(F.spmv_bench(reps, True))
+    ms_no = maxr(F.spmv_bench(reps, False))
     rng = np.random.default_rng(0)
     u0 = rng.uniform(-1, 1, nF) + 1j * rng.uniform(-1, 1, nF)
     rows = plan.owned_global()
     b = (fi["faceArea"] * u0)[rows]
     res = {}
     F.pcg(b, precond=1, max_iter=4)   # untimed warm-up: lazy NCCL connections for the level-1 all-reduce, kernel loading
-    for precond in ((1, 2) if args.both else (1,)):   # 1 = global hierarchy (coarse levels replicated), 2 = block-Jacobi hierarchy
+    for precond in ((1, 2) if both else (1,)):   # 1 = global hierarchy (coarse levels replicated), 2 = block-Jacobi hierarchy
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -72,22 +62,41 @@ def main():
             res[f"pcg_precond{precond}_error"] = repr(e)
         res[f"pcg_precond{precond}"] = dict(iterations=int(F.stats["inner_iterations"]), relres=F.stats["relres_max"], setup_ms=F.stats["setup_ms"],
                                             solve_ms=maxr(F.stats["solve_ms"]), wall_s=maxr(time.time() - t))
-    if args.outer:
+    if outer:
         t = time.time()
         try:
-            F.solveSmallestEig(u0[rows], args.outer)
+            F.solveSmallestEig(u0[rows], outer)
         except Exception as e:  # noqa: BLE001
             res["inverse_iteration_error"] = repr(e)
-        res["inverse_iteration"] = dict(outer=args.outer, inner=int(F.stats["inner_iterations"]), solve_ms=maxr(F.stats["solve_ms"]),
+        res["inverse_iteration"] = dict(outer=outer, inner=int(F.stats["inner_iterations"]), solve_ms=maxr(F.stats["solve_ms"]),
                                         relres=F.stats["relres_max"], wall_s=maxr(time.time() - t))
     halo = maxr(plan.n_halo)
-    if rank == 0:
-        alg = 116 * nF
-        print(json.dumps({"mode": "partitioned", "n_gpus": world, "verts": nV, "faces": nF, "rows_per_gpu": plan.n_local, "halo_max": int(halo),
-                          "interior_frac": plan.n_interior / plan.n_local, "spmv_ms_overlap": ms_ov, "spmv_ms_no_overlap": ms_no,
-                          "spmv_aggregate_gbs_algorithmic": alg / (ms_ov * 1e-3) / 1e9, "mesh_s": t_mesh, "operator_and_hierarchy_setup_s": t_setup, **res}), flush=True)
+    alg = 116 * nF
+    out = {"mode": "partitioned", "n_gpus": world, "verts": nV, "faces": nF, "rows_per_gpu": plan.n_local, "halo_max": int(halo),
+           "interior_frac": plan.n_interior / plan.n_local, "spmv_ms_overlap": ms_ov, "spmv_ms_no_overlap": ms_no,
+           "spmv_aggregate_gbs_algorithmic": alg / (ms_ov * 1e-3) / 1e9, "halo_bytes_per_spmv_per_gpu": int(halo) * 16,
+           "allreduces_per_pcg_iteration": 3, "mesh_s": t_mesh, "operator_and_hierarchy_setup_s": t_setup, **res}
     F.close()
     d.close()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--kind", type=int, default=4)
+    ap.add_argument("--levels", type=int, default=11)
+    ap.add_argument("--reps", type=int, default=100)
+    ap.add_argument("--outer", type=int, default=0, help="also run this many inverse-iteration steps")
+    ap.add_argument("--both", action="store_true", help="also time the block-Jacobi preconditioner")
+    args = ap.parse_args()
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = capi.Context(local)
+    out = run_partitioned(ctx, rank, world, args.kind, args.levels, args.reps, args.outer, args.both)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -24,7 +24,7 @@ F = api.FaceRosyField(ctx, fi["face2half"], fi["next"], fi["twin"], fi["face"], 
 z = F.solveSmallestEig(u0, 50)
 out = {"env": {k: v for k, v in os.environ.items() if k.startswith("MK_")}, "nF": nF}
 st = F.stats
-out["field"] = {"hierarchy": F.hierarchy(), "cycle_us": F.profile_cycle(200), "spmv_dot_us": F.spmv_bench(200, True) * 1e3,
+out["field"] = {"hierarchy": F.hierarchy(), "cycle_us (apply, from L1.., [xr+handover, cycle+dot, update_p])": F.profile_cycle(200), "spmv_dot_us": F.spmv_bench(200, True) * 1e3,
                 "solve_ms": st["solve_ms"], "inner": st["inner_iterations"], "us_per_iteration": st["solve_ms"] * 1e3 / st["inner_iterations"]}
 s.field_post(z, 4, "curl")
 s.igm_setup(0.02)
@@ -32,6 +32,6 @@ inp = s.igm_inputs()
 prob = api.IgmProblem(ctx, inp["X2F"], inp["UFull"], inp["F2"], inp["length"])
 r = prob.round(inp["fixedIdcs"], inp["fixedVals"], inp["singularIdcs"], inp["integerIdcs"], True, False)
 st = r["stats"]
-out["igm"] = {"hierarchy": prob.hierarchy(), "cycle_us": prob.profile_cycle(200), "spmv_dot_us": prob.spmv_bench(200, True) * 1e3,
+out["igm"] = {"hierarchy": prob.hierarchy(), "cycle_us (apply, from L1..)": prob.profile_cycle(200), "spmv_dot_us": prob.spmv_bench(200, True) * 1e3,
               "solve_ms": st["solve_ms"], "inner": st["inner_iterations"], "us_per_iteration": st["solve_ms"] * 1e3 / st["inner_iterations"]}
 print(json.dumps(out))
