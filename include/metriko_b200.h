@@ -172,6 +172,15 @@ int mk_igm_poisson(mk_igm* g, int n_fixed, const int* fixedIdcs, const double* f
 int mk_igm_round(mk_igm* g, int n_fixed, const int* fixedIdcs, const double* fixedVals, int n_sing, const int* singularIdcs,
                  int n_int, const int* integerIdcs, int seamless, int roundSeams, double* fullx, int* fixed_idcs, int* fixed_vals,
                  int* n_fixed_out, int* resolve_flags, int* tie_flags, mk_stats* stats);
+/* The same driver with localInjectivity = true (iter_rounding.h:57-104; the flags of example_qgp.cpp:26-29 and example_qex.cpp:59-63): every
+ * LM carries the per-face injectivity barrier (injective_barrier.h:19-109, iter_rounding_common.h:70-85) and starts from lambda = 0.01 with
+ * DiagonalDamping (levenberg_marquardt.h:13-88). The NI stage is the LM over [x; f] (iter_rounding_init.h:60-72) with f eliminated per face;
+ * with seamless = 0 its result is returned (iter_rounding.h:86-88). use_iter_cb = 1: the NI LM stops as soon as the map is locally injective
+ * (locally_injectivity_check, parameterization_integ.ipp:46-63, iter_rounding_init.h:28) -- needs a mk_igm_create_from_mesh handle. Fixed dofs
+ * are eliminated exactly instead of penalised, as in mk_igm_round. */
+int mk_igm_round_injective(mk_igm* g, int n_fixed, const int* fixedIdcs, const double* fixedVals, int n_sing, const int* singularIdcs,
+                           int n_int, const int* integerIdcs, int seamless, int roundSeams, int use_iter_cb, double* fullx, int* fixed_idcs,
+                           int* fixed_vals, int* n_fixed_out, int* resolve_flags, int* tie_flags, mk_stats* stats);
 /* Copy A0 = length^2 X2F^T X2F (assembled on the device) back as CSR for tests: pass NULLs to query nnz. */
 int mk_igm_get_matrix(mk_igm* g, int64_t* nnz, int* rowptr, int* col, double* val);
 int mk_igm_spmv_bench(mk_igm* g, int reps, int fused_dot, double* ms_per_launch);

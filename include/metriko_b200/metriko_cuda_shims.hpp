@@ -144,14 +144,15 @@ inline SprsD kernel_basis(const SprsD& Cfull) {
 }
 }  // namespace detail
 
-// B4: bool iterative_rounding(...)   (iter_rounding.h:33-113). Same arguments; localInjectivity = true (the barrier LM,
-// injective_barrier.h) is not offloaded and must go through the reference path.
+// B4: bool iterative_rounding(...)   (iter_rounding.h:33-113). Same arguments except iter_cb: with localInjectivity = true the barrier LMs
+// (injective_barrier.h) run on the device too (mk_igm_round_injective), but the reference's host callback (the NI LM's early stop
+// "locally injective now", iter_rounding_init.h:28) cannot be evaluated from here -- the integ()-level entry mk_igm_create_from_mesh +
+// mk_igm_round_injective(use_iter_cb = 1) evaluates that check on the device (seam B6).
 inline bool iterative_rounding(const VecXi& fixedIdcs, const VecXd& fixedVals, const VecXi& singularIdcs, const VecXi& integerIdcs,
                                const double length, const SprsD& Cfull, const SprsD& G2, const int N, const int n, const int nF,
                                const bool seamless, const bool roundSeams, const bool localInjectivity, const bool verbose,
                                const VecXd& intrinsicField, VecXd& fullx, Context& ctx = Context::thread_default()) {
     (void)N; (void)n; (void)nF; (void)verbose;
-    if (localInjectivity) throw std::invalid_argument("metriko_b200: localInjectivity = true is not offloaded (barrier path)");
     const SprsD UFull = detail::kernel_basis(Cfull);
     SprsD X2F = (G2 * UFull).pruned();  // iter_rounding_init.h:173 (without `length`)
     detail::CsrCopy X(X2F), U(UFull);
@@ -163,9 +164,13 @@ inline bool iterative_rounding(const VecXi& fixedIdcs, const VecXd& fixedVals, c
     const int m = (int)(singularIdcs.size() + integerIdcs.size());
     std::vector<int> oi(m + 1), ov(m + 1), rf(m + 1), tf(m + 1);
     int nfix = 0;
-    const int rc = mk_igm_round(g, (int)fixedIdcs.size(), fixedIdcs.data(), fixedVals.data(), (int)singularIdcs.size(), singularIdcs.data(),
-                                (int)integerIdcs.size(), integerIdcs.data(), seamless ? 1 : 0, roundSeams ? 1 : 0, fullx.data(), oi.data(),
-                                ov.data(), &nfix, rf.data(), tf.data(), nullptr);
+    const int rc = localInjectivity
+        ? mk_igm_round_injective(g, (int)fixedIdcs.size(), fixedIdcs.data(), fixedVals.data(), (int)singularIdcs.size(), singularIdcs.data(),
+                                 (int)integerIdcs.size(), integerIdcs.data(), seamless ? 1 : 0, roundSeams ? 1 : 0, 0, fullx.data(), oi.data(),
+                                 ov.data(), &nfix, rf.data(), tf.data(), nullptr)
+        : mk_igm_round(g, (int)fixedIdcs.size(), fixedIdcs.data(), fixedVals.data(), (int)singularIdcs.size(), singularIdcs.data(),
+                       (int)integerIdcs.size(), integerIdcs.data(), seamless ? 1 : 0, roundSeams ? 1 : 0, fullx.data(), oi.data(),
+                       ov.data(), &nfix, rf.data(), tf.data(), nullptr);
     mk_igm_destroy(g);
     return rc == MK_OK;  // MK_ERR_ROUNDING <-> "Rounding has failed!" (parameterization_integ.ipp:85)
 }

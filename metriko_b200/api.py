@@ -340,7 +340,9 @@ class IgmProblem:
         self.ctx.check(rc)
         return xs, xf
 
-    def round(self, fixedIdcs, fixedVals, singularIdcs, integerIdcs, seamless=True, roundSeams=False):
+    def round(self, fixedIdcs, fixedVals, singularIdcs, integerIdcs, seamless=True, roundSeams=False, localInjectivity=False, use_iter_cb=False):
+        """iterative_rounding (ir.h:33-113). localInjectivity: the barrier LMs (mk_igm_round_injective); use_iter_cb: stop the NI LM as soon as the
+        map is locally injective (from_mesh handles)."""
         fi, fv = as_i32(fixedIdcs), as_f64(fixedVals)
         si, ii = as_i32(singularIdcs), as_i32(integerIdcs)
         m = len(si) + len(ii)
@@ -351,8 +353,12 @@ class IgmProblem:
         ties = np.zeros(max(m, 1), np.int32)
         nfix = C.c_int()
         st = Stats()
-        rc = self.ctx.L.mk_igm_round(self.h, len(fi), ptr(fi), ptr(fv), len(si), ptr(si), len(ii), ptr(ii), int(seamless), int(roundSeams),
-                                     ptr(fullx), ptr(out_i), ptr(out_v), C.byref(nfix), ptr(resolve), ptr(ties), C.byref(st))
+        if localInjectivity:
+            rc = self.ctx.L.mk_igm_round_injective(self.h, len(fi), ptr(fi), ptr(fv), len(si), ptr(si), len(ii), ptr(ii), int(seamless), int(roundSeams),
+                                                   int(use_iter_cb), ptr(fullx), ptr(out_i), ptr(out_v), C.byref(nfix), ptr(resolve), ptr(ties), C.byref(st))
+        else:
+            rc = self.ctx.L.mk_igm_round(self.h, len(fi), ptr(fi), ptr(fv), len(si), ptr(si), len(ii), ptr(ii), int(seamless), int(roundSeams),
+                                         ptr(fullx), ptr(out_i), ptr(out_v), C.byref(nfix), ptr(resolve), ptr(ties), C.byref(st))
         self.stats = st.as_dict()
         self.ctx.check(rc, allow=(-5,))
         k = nfix.value

@@ -93,6 +93,7 @@ def lib() -> C.CDLL:
         L.mk_igm_scatter.argtypes = [vp, vp, vp, vp]
         L.mk_igm_poisson.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.POINTER(Stats)]
         L.mk_igm_round.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp, ip, vp, vp, C.POINTER(Stats)]
+        L.mk_igm_round_injective.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, ip, vp, vp, C.POINTER(Stats)]
         L.mk_igm_get_matrix.argtypes = [vp, i64p, vp, vp, vp]
         L.mk_igm_spmv_bench.argtypes = [vp, C.c_int, C.c_int, dp]
         L.mk_igm_hierarchy.argtypes = [vp, C.c_int, ip, vp, vp, vp]

@@ -11,6 +11,7 @@
 #include "csr.cuh"
 #include "field.cuh"
 #include "igm.cuh"
+#include "barrier.cuh"
 #include "integ.cuh"
 #include "metriko_b200.h"
 
@@ -238,7 +239,8 @@ struct mk_igm {
     int N = 0, nF = 0, cut_nV = 0;
     DevBuf<int> cutF;              // cut.idx, 3 nF
     DeviceCsr<double> F2N;         // fullx2Nfunc, N cut.nV x n nR
-    DeviceCsr<double> X2F;         // (G2 fullx2Nfunc UFull).pruned(), assembled on the device
+    DeviceCsr<double> X2F, Xt;     // X2F = (G2 fullx2Nfunc UFull).pruned() (uploaded, or assembled on the device) and its transpose: kept for the
+                                   // localInjectivity path, whose barrier is a function of the field X2F x (iter_rounding_common.h:70-85)
     DevBuf<double> F2d;            // rawF2Vec
     bool fullx_valid = false;      // tmp holds fullx = UFull x of the last mk_igm_round / mk_igm_poisson
 };
@@ -307,6 +309,13 @@ static void igm_device_setup(mk_igm* g, DeviceCsr<double>& X, const double* d_F2
             g->amg_lo = lower_precision<double>(s, std::move(g->amg), std::make_unique<CsrOp<float>>(&g->A0_lo, 1e-4));
             tm.lap("fp32 copy of the hierarchy");
         }
+    }
+    if (&X != &g->X2F) g->X2F = std::move(X);
+    g->Xt = std::move(Xt);
+    if (g->F2d.p != d_F2) {
+        g->F2d.alloc((size_t)g->rows);
+        MK_CUDA(cudaMemcpyAsync(g->F2d.p, d_F2, sizeof(double) * (size_t)g->rows, cudaMemcpyDeviceToDevice, s));
+        MK_CUDA(cudaStreamSynchronize(s));
     }
 }
 
@@ -769,6 +778,308 @@ struct IgmRun {
     }
 };
 
+// ---- localInjectivity: the two LMs with the per-face barrier (barrier.cuh), driven as solver/levenberg_marquardt.h:140-231 does ----
+// DiagonalDamping (lm.h:13-88): system (J^T J + lambda diag(J^T J)) d = -J^T E, lambda /= 10 after a step that lowers the energy (and is finite),
+// *= 10 otherwise; termination: |d| < funcTol, or an accepted step with |dE| < funcTol, or maxIterations, or the caller's callback.
+// Differences from the reference, by design: the 1e10 / 1e8 penalty rows of the fixed dofs are eliminated exactly (projector)
+// while their contribution to the damping diagonal is kept; the NI unknown f is eliminated per face (Schur complement); the linear
+// solves are PCG to the usual relative residual instead of a factorisation.
+struct BarrierRun {
+    mk_igm* g;
+    cudaStream_t s;
+    IgmRun* run;
+    int N = 0, nF = 0;
+    size_t nfld = 0;
+    int cols = 0;
+    double len = 1.0;
+    long launches = 0;
+    DevBuf<double> V, fB, gco, fld, fld2, t8, f, f2, gf, diagA0, D, csq, grad, d, px, x2, nfn;
+    DevBuf<int> active;
+    double n_active = 0;
+    double lm_relres_max = 0;  // worst relative residual of the LM direction solves (reported separately from the 1e-10 solves of the plain path)
+
+    BarrierRun(mk_igm* g_, cudaStream_t s_, IgmRun* run_) : g(g_), s(s_), run(run_) {}
+
+    struct SiOp : LinOp<double> {
+        BarrierRun* b;
+        double lambda = 0;
+        void apply(const double* x, double* y, PcgState* st, ReduceWs ws, cudaStream_t s, bool dot = true) override {
+            mk_igm* g = b->g;
+            spmv<double>(g->A0, x, y, 1e-4, false, false, nullptr, ws, s);
+            if (lambda != 0.0) k_vec_add_diag<<<stream_grid(b->cols), kThreads, 0, s>>>(b->cols, lambda, b->D.p, x, y);
+            if (b->n_active > 0) {
+                csr_matvec<double>(g->X2F, x, b->t8.p, b->len, s);
+                k_bar_GtG<<<stream_grid(b->nF), kThreads, 0, s>>>(b->nF, b->N, b->gco.p, b->active.p, 1e-8, b->t8.p);
+                csr_matvec<double>(g->Xt, b->t8.p, b->x2.p, b->len, s);
+                k_vec_lincomb<<<stream_grid(b->cols), kThreads, 0, s>>>(b->cols, 1.0, y, 1.0, b->x2.p, y);
+            }
+            if (st && dot) k_dot_alpha<double><<<stream_grid(b->cols), kThreads, 0, s>>>(b->cols, x, y, st, ws);
+            MK_CHECK_LAUNCH();
+        }
+        int launches_per_apply() const override { return 7; }
+    };
+    struct NiOp : LinOp<double> {
+        BarrierRun* b;
+        double lambda = 0;
+        void apply(const double* x, double* y, PcgState* st, ReduceWs ws, cudaStream_t s, bool dot = true) override {
+            mk_igm* g = b->g;
+            csr_matvec<double>(g->X2F, x, b->t8.p, b->len, s);
+            k_ni_face_solve<<<stream_grid(b->nF), kThreads, 0, s>>>(b->nF, b->N, b->gco.p, b->active.p, lambda, 1, b->t8.p);
+            csr_matvec<double>(g->Xt, b->t8.p, y, b->len, s);
+            if (lambda != 0.0) k_vec_add_diag<<<stream_grid(b->cols), kThreads, 0, s>>>(b->cols, lambda, b->D.p, x, y);
+            if (st && dot) k_dot_alpha<double><<<stream_grid(b->cols), kThreads, 0, s>>>(b->cols, x, y, st, ws);
+            MK_CHECK_LAUNCH();
+        }
+        int launches_per_apply() const override { return 5; }
+    };
+    SiOp si_op;
+    NiOp ni_op;
+    ScaledPrecond scaled;
+    JacobiPrecond jacobi;
+    DevBuf<double> jac_diag;
+
+    PcgState* st() { return g->pcg->state(); }
+    ReduceWs ws() { return g->pcg->ws(); }
+    double aux0() { g->pcg->fetch_state(); return g->pcg->host_state().aux0; }
+    double dot(const double* a, const double* b, size_t n) {
+        k_vec_dot<<<stream_grid((int64_t)n), kThreads, 0, s>>>((int64_t)n, a, b, st(), ws());
+        MK_CHECK_LAUNCH();
+        launches++;
+        return aux0();
+    }
+    void lincomb(size_t n, double a, const double* x, double b, const double* y, double* out) {
+        k_vec_lincomb<<<stream_grid((int64_t)n), kThreads, 0, s>>>((int64_t)n, a, x, b, y, out);
+        MK_CHECK_LAUNCH();
+        launches++;
+    }
+    // sum fB^2 of the barrier at `field` (2N nF); jac: also fB, the Jacobian coefficients and the active-face flags of the object
+    double eval_barrier(const double* field, bool jac) {
+        k_bar_eval<<<stream_grid(nF), kThreads, 0, s>>>(nF, N, field, V.p, jac ? fB.p : nullptr, jac ? gco.p : nullptr, jac ? active.p : nullptr, st(), ws());
+        MK_CHECK_LAUNCH();
+        launches++;
+        g->pcg->fetch_state();
+        if (jac) n_active = g->pcg->host_state().aux1;
+        return g->pcg->host_state().aux0;
+    }
+
+    void init(int n_fixed, const int* fixedIdcs) {
+        if (g->rows % 2 != 0) throw std::invalid_argument("barrier: X2F must have 2 N nF rows");
+        N = g->N > 0 ? g->N : 4;  // host-X2F handles carry no N: metriko's RoSy fields for IGM are N = 4 (example_*.cpp)
+        if (N > kBarMaxN || (N & 1)) throw std::invalid_argument("barrier: N must be 2 or 4");
+        nF = g->rows / (2 * N);
+        nfld = (size_t)g->rows;
+        cols = g->cols;
+        len = g->length;
+        V.alloc((size_t)N * nF); fB.alloc((size_t)N * nF); gco.alloc((size_t)4 * N * nF); active.alloc(nF);
+        fld.alloc(nfld); fld2.alloc(nfld); t8.alloc(nfld); f.alloc(nfld); f2.alloc(nfld); gf.alloc(nfld);
+        diagA0.alloc(cols); D.alloc(cols); csq.alloc(cols); grad.alloc(cols); d.alloc(cols); px.alloc(cols); x2.alloc(cols); jac_diag.alloc(cols);
+        k_bar_V<<<stream_grid(nF), kThreads, 0, s>>>(nF, N, g->F2d.p, V.p);   // V of the INPUT field (barrier.h:32-39)
+        k_csr_diag<<<stream_grid(cols), kThreads, 0, s>>>(cols, g->A0.ptr.p, g->A0.col.p, g->A0.val.p, diagA0.p);
+        MK_CHECK_LAUNCH();
+        launches += 2;
+        std::vector<int> fx(fixedIdcs, fixedIdcs + n_fixed);
+        set_constraint_damping(fx);
+        si_op.b = this;
+        ni_op.b = this;
+    }
+    // sum over the constrained rows c of c_j^2: their share of diag(J^T J) (times 1e8 in the NI stage, 1e10 in the rounding loop)
+    void set_constraint_damping(const std::vector<int>& rows) {
+        std::vector<double> h(cols, 0.0);
+        const HostCsr<double>& U = g->UFull;
+        for (int r : rows)
+            for (int k = U.ptr[r]; k < U.ptr[r + 1]; k++) h[U.col[k]] += U.val[k] * U.val[k];
+        csq.upload(h.data(), cols, s);
+        MK_CUDA(cudaStreamSynchronize(s));
+    }
+    Precond<double>* base_precond() { return run->use_cprec ? (Precond<double>*)&run->cprec : g->precond(); }
+
+    // d = argmin of the damped Gauss-Newton model in the feasible directions (Q d = 0): projected PCG from zero
+    // `fallback_diag`: diagonal of the operator, for the Jacobi-preconditioned retry after a breakdown of the multigrid-preconditioned solve
+    // (the fp32 cycle sees residuals whose entries differ by the 1e8 .. 1e10 damping of the constrained dofs; when it loses definiteness
+    // there PCG reports <p, A p> <= 0 -- the retry is slower but unconditionally SPD)
+    SolveStats solve_direction(LinOp<double>* op, Precond<double>* M, double* rhs, const double* fallback_diag) {
+        DevBuf<double> rhs_copy;
+        if (M != &jacobi) {
+            rhs_copy.alloc(cols);
+            MK_CUDA(cudaMemcpyAsync(rhs_copy.p, rhs, sizeof(double) * cols, cudaMemcpyDeviceToDevice, s));
+        }
+        // LM directions: relative residual 1e-9 (the accept / reject decisions and the 1e-6 agreement with the reference need far less), at
+        // most kDirMaxIter iterations; a solve that stalls at the fp64 floor of these systems (their diagonal spans 1e8 .. 1e10 through
+        // the damping of the constrained dofs: eps * cond ~ 1e-9) is accepted when its residual is below kDirAccept
+        const double dir_tol = std::max(g->o.tol, 1e-9), kDirAccept = 1e-6;
+        const int kDirMaxIter = std::min(g->o.max_iter, 20000);
+        d.zero(s);
+        g->pcg->bind(op, M, &run->proj);
+        SolveStats ss = g->pcg->solve(rhs, d.p, dir_tol, kDirMaxIter, false, 16, false);
+        if (ss.status == 1 && ss.relres <= kDirAccept) ss.status = 0;
+        if (ss.status != 0 && M != &jacobi) {
+            if (getenv("MK_VERBOSE")) fprintf(stderr, "[mk] LM direction solve: status %d after %d iterations (relres %.2e): Jacobi-preconditioned retry\n", ss.status, ss.iterations, ss.relres);
+            jacobi.d = fallback_diag; jacobi.n = cols;
+            d.zero(s);
+            g->pcg->bind(op, &jacobi, &run->proj);
+            const SolveStats s2 = g->pcg->solve(rhs_copy.p, d.p, dir_tol, kDirMaxIter, false, 16, false);
+            ss.iterations += s2.iterations;
+            ss.launches += s2.launches;
+            ss.relres = s2.relres;
+            ss.status = (s2.status == 1 && s2.relres <= kDirAccept) ? 0 : s2.status;
+        }
+        run->st.inner_iterations += ss.iterations;
+        run->st.inner_max = std::max(run->st.inner_max, ss.iterations);
+        lm_relres_max = std::max(lm_relres_max, ss.relres);
+        launches += ss.launches;
+        if (ss.status != 0 && run->st.status == MK_OK) run->st.status = status_of(ss.status);
+        return ss;
+    }
+
+    // ---------------- NI stage (ir.h:82-83; iter_rounding_init.h:60-72): unknown [x; f], x = g->x (Poisson solution), f starts at F2
+    double ni_energy(const double* x, const double* ff, bool jac) {
+        csr_matvec<double>(g->X2F, x, fld2.p, len, s);                       // X x
+        lincomb(nfld, 1.0, ff, -1.0, fld2.p, fld2.p);                        // r = f - X x
+        const double rr = dot(fld2.p, fld2.p, nfld);
+        lincomb(nfld, 1.0, ff, -1.0, g->F2d.p, t8.p);
+        const double cc = dot(t8.p, t8.p, nfld);
+        const double eb = eval_barrier(ff, jac);
+        launches += 1;
+        return 1e8 * rr + cc + 1e-8 * eb;
+    }
+    bool injective_now() {
+        // locally_injectivity_check (integ.ipp:46-63) on fullx = UFull x
+        csr_matvec<double>(g->dUFull, g->x.p, g->tmp.p, 1.0, s);
+        if (!nfn.p) nfn.alloc((size_t)g->N * g->cut_nV);
+        csr_matvec<double>(g->F2N, g->tmp.p, nfn.p, 1.0, s);
+        k_orientation_count<<<stream_grid(nF), kThreads, 0, s>>>(nF, g->N, g->cutF.p, nfn.p, st(), ws());
+        MK_CHECK_LAUNCH();
+        launches += 3;
+        return aux0() == 0.0;
+    }
+    void lm_ni(bool use_iter_cb) {
+        const double ftol = 10e-10;
+        double lam = 0.01;
+        MK_CUDA(cudaMemcpyAsync(f.p, g->F2d.p, sizeof(double) * nfld, cudaMemcpyDeviceToDevice, s));
+        MK_CUDA(cudaMemcpyAsync(px.p, g->x.p, sizeof(double) * cols, cudaMemcpyDeviceToDevice, s));
+        double prevE2 = ni_energy(px.p, f.p, true);   // leaves r = f - X x in fld2 and the barrier Jacobian of f
+        int it = 0;
+        while (true) {
+            // gradient J^T E: gx = -1e8 X^T r ; gf = 1e8 r + (f - F2) + G^T fB (Jacobian weight wInteg, residual weight wBarrier: 1e4 * 1e-4)
+            csr_matvec<double>(g->Xt, fld2.p, grad.p, -1e8 * len, s);
+            lincomb(nfld, 1e8, fld2.p, 1.0, f.p, gf.p);
+            lincomb(nfld, 1.0, gf.p, -1.0, g->F2d.p, gf.p);
+            k_bar_Gt<<<stream_grid(nF), kThreads, 0, s>>>(nF, N, gco.p, fB.p, 1.0, gf.p, 1);
+            // rhs = -gx - 1e8 X^T K^{-1} gf
+            MK_CUDA(cudaMemcpyAsync(t8.p, gf.p, sizeof(double) * nfld, cudaMemcpyDeviceToDevice, s));
+            k_ni_face_solve<<<stream_grid(nF), kThreads, 0, s>>>(nF, N, gco.p, active.p, lam, 0, t8.p);
+            csr_matvec<double>(g->Xt, t8.p, x2.p, -1e8 * len, s);
+            lincomb(cols, -1.0, grad.p, 1.0, x2.p, grad.p);   // grad now holds the right-hand side
+            // damping diagonal of the x block: 1e8 diag(X^T X) + 1e8 sum c^2
+            lincomb(cols, 1e8, diagA0.p, 1e8, csq.p, D.p);
+            MK_CHECK_LAUNCH();
+            launches += 5;
+            ni_op.lambda = lam;
+            const double k0 = (1e8 + 1.0) * (1.0 + lam), r0 = 1.0 + lam * (1e8 + 1.0), w0 = 1e8 * r0 / k0;
+            Precond<double>* M;
+            lincomb(cols, w0, diagA0.p, lam, D.p, jac_diag.p);   // diag(S) up to the barrier blocks
+            if (lam * 1e8 >= 0.05 * w0) {   // damping dominates: S ~ diagonal
+                jacobi.d = jac_diag.p; jacobi.n = cols;
+                M = &jacobi;
+            } else {
+                scaled.inner = base_precond(); scaled.scale = 1.0 / w0; scaled.n = cols;
+                M = &scaled;
+            }
+            solve_direction(&ni_op, M, grad.p, jac_diag.p);
+            // df = K^{-1} (-gf + 1e8 X dx)
+            csr_matvec<double>(g->X2F, d.p, t8.p, 1e8 * len, s);
+            lincomb(nfld, 1.0, t8.p, -1.0, gf.p, t8.p);
+            k_ni_face_solve<<<stream_grid(nF), kThreads, 0, s>>>(nF, N, gco.p, active.p, lam, 0, t8.p);
+            MK_CHECK_LAUNCH();
+            launches += 2;
+            const double nd = std::sqrt(dot(d.p, d.p, cols) + dot(t8.p, t8.p, nfld));
+            if (getenv("MK_VERBOSE")) fprintf(stderr, "[mk] NI LM %d: lambda %.1e E %.10e |d| %.3e active faces %.0f\n", it, lam, prevE2, nd, n_active);
+            if (nd < ftol) break;   // x = prevx (lm.h:193-197)
+            lincomb(cols, 1.0, px.p, 1.0, d.p, x2.p);
+            lincomb(nfld, 1.0, f.p, 1.0, t8.p, f2.p);
+            DevBuf<double> keep_r(nfld);   // r of the current iterate (ni_energy overwrites fld2)
+            MK_CUDA(cudaMemcpyAsync(keep_r.p, fld2.p, sizeof(double) * nfld, cudaMemcpyDeviceToDevice, s));
+            const double newE2 = ni_energy(x2.p, f2.p, false);
+            const bool better = prevE2 > newE2;
+            bool stop = false;
+            if (better) {
+                MK_CUDA(cudaMemcpyAsync(px.p, x2.p, sizeof(double) * cols, cudaMemcpyDeviceToDevice, s));
+                MK_CUDA(cudaMemcpyAsync(f.p, f2.p, sizeof(double) * nfld, cudaMemcpyDeviceToDevice, s));
+                if (std::fabs(prevE2 - newE2) < ftol) stop = true;   // lm.h:208-211
+            }
+            // E, J at the (possibly unchanged) iterate; lambda update (lm.h:43-83)
+            prevE2 = ni_energy(px.p, f.p, true);
+            (void)keep_r;
+            if (stop) break;
+            if (better && std::isfinite(newE2)) lam /= 10.0; else lam *= 10.0;
+            MK_CUDA(cudaMemcpyAsync(g->x.p, px.p, sizeof(double) * cols, cudaMemcpyDeviceToDevice, s));
+            if (use_iter_cb && injective_now()) break;   // ir_init.h:28
+            it++;
+            if (!(it <= 100)) break;
+        }
+        MK_CUDA(cudaMemcpyAsync(g->x.p, px.p, sizeof(double) * cols, cudaMemcpyDeviceToDevice, s));
+        MK_CUDA(cudaStreamSynchronize(s));
+        run->st.outer_iterations += it;
+    }
+
+    // ---------------- rounding loop LM (ir.h:102-104; iter_rounding_loop.h:77-86): unknown x = g->x (feasible), xPrev = g->xprev, F2_ = f
+    double si_energy(const double* x, double* field_out, bool jac) {
+        csr_matvec<double>(g->X2F, x, field_out, len, s);
+        lincomb(nfld, 1.0, field_out, -1.0, f.p, t8.p);
+        const double rr = dot(t8.p, t8.p, nfld);
+        lincomb(cols, 1.0, x, -1.0, g->xprev.p, x2.p);
+        const double cc = dot(x2.p, x2.p, cols);
+        const double eb = eval_barrier(field_out, jac);
+        launches += 1;
+        return rr + 1e-4 * cc + 1e-8 * eb;
+    }
+    void lm_si() {
+        const double ftol = 1e-7;
+        double lam = 0.01;
+        launches = 0;
+        MK_CUDA(cudaMemcpyAsync(px.p, g->x.p, sizeof(double) * cols, cudaMemcpyDeviceToDevice, s));
+        double prevE2 = si_energy(px.p, fld.p, true);
+        int it = 0;
+        while (true) {
+            // gradient: X^T((X x - F2_) + 1e-8 G^T fB) + 1e-4 (x - xPrev)
+            lincomb(nfld, 1.0, fld.p, -1.0, f.p, t8.p);
+            k_bar_Gt<<<stream_grid(nF), kThreads, 0, s>>>(nF, N, gco.p, fB.p, 1e-8, t8.p, 1);
+            csr_matvec<double>(g->Xt, t8.p, grad.p, len, s);
+            lincomb(cols, 1.0, px.p, -1.0, g->xprev.p, x2.p);
+            lincomb(cols, -1.0, grad.p, -1e-4, x2.p, grad.p);   // right-hand side -J^T E
+            // damping diagonal: diag(X^T X) + 1e-4 + 1e10 sum c^2 + 1e-8 diag(Jb^T Jb)
+            lincomb(cols, 1.0, diagA0.p, 1e10, csq.p, D.p);
+            k_vec_add_const<<<stream_grid(cols), kThreads, 0, s>>>(cols, 1e-4, D.p);
+            if (n_active > 0)
+                k_bar_diag<<<stream_grid((int64_t)N * nF), kThreads, 0, s>>>(nF, N, gco.p, g->X2F.ptr.p, g->X2F.col.p, g->X2F.val.p, len, 1e-8, D.p);
+            MK_CHECK_LAUNCH();
+            launches += 4;
+            si_op.lambda = lam;
+            lincomb(cols, 1.0, diagA0.p, lam, D.p, jac_diag.p);
+            k_vec_add_const<<<stream_grid(cols), kThreads, 0, s>>>(cols, 1e-4, jac_diag.p);
+            solve_direction(&si_op, base_precond(), grad.p, jac_diag.p);
+            const double nd = std::sqrt(dot(d.p, d.p, cols));
+            if (getenv("MK_VERBOSE")) fprintf(stderr, "[mk] SI LM %d: lambda %.1e E %.10e |d| %.3e active faces %.0f\n", it, lam, prevE2, nd, n_active);
+            if (nd < ftol) break;
+            lincomb(cols, 1.0, px.p, 1.0, d.p, grad.p);   // trial iterate (grad is free again)
+            const double newE2 = si_energy(grad.p, fld2.p, false);
+            const bool better = prevE2 > newE2;
+            bool stop = false;
+            if (better) {
+                MK_CUDA(cudaMemcpyAsync(px.p, grad.p, sizeof(double) * cols, cudaMemcpyDeviceToDevice, s));
+                if (std::fabs(prevE2 - newE2) < ftol) stop = true;
+            }
+            prevE2 = si_energy(px.p, fld.p, true);
+            if (stop) break;
+            if (better && std::isfinite(newE2)) lam /= 10.0; else lam *= 10.0;
+            it++;
+            if (!(it <= 100)) break;
+        }
+        MK_CUDA(cudaMemcpyAsync(g->x.p, px.p, sizeof(double) * cols, cudaMemcpyDeviceToDevice, s));
+        MK_CUDA(cudaStreamSynchronize(s));
+    }
+};
+
 std::vector<int> concat_idcs(int n_fixed, const int* fixedIdcs, int n_sing, const int* sing, int n_int, const int* integ) {
     std::vector<int> v;
     if (fixedIdcs) v.insert(v.end(), fixedIdcs, fixedIdcs + n_fixed);
@@ -806,10 +1117,12 @@ extern "C" int mk_igm_poisson(mk_igm* g, int n_fixed, const int* fixedIdcs, cons
     MK_API_END_RC(g->ctx, rc)
 }
 
-extern "C" int mk_igm_round(mk_igm* g, int n_fixed, const int* fixedIdcs, const double* fixedVals, int n_sing, const int* singularIdcs,
-                            int n_int, const int* integerIdcs, int seamless, int roundSeams, double* fullx, int* fixed_idcs, int* fixed_vals,
-                            int* n_fixed_out, int* resolve_flags, int* tie_flags, mk_stats* stats) {
+static int igm_round_impl(mk_igm* g, int n_fixed, const int* fixedIdcs, const double* fixedVals, int n_sing, const int* singularIdcs,
+                          int n_int, const int* integerIdcs, int seamless, int roundSeams, int localInjectivity, int use_iter_cb, double* fullx,
+                          int* fixed_idcs, int* fixed_vals, int* n_fixed_out, int* resolve_flags, int* tie_flags, mk_stats* stats) {
     if (!g || !fullx || n_fixed < 0 || n_sing < 0 || n_int < 0) return MK_ERR_ARG;
+    if (localInjectivity && (!g->X2F.ptr.p || !g->Xt.ptr.p || !g->F2d.p)) return MK_ERR_ARG;  // host-mirror set-up keeps no device X2F
+    if (use_iter_cb && !g->F2N.ptr.p) return MK_ERR_ARG;  // the injectivity check needs fullx2Nfunc + the corner table (mk_igm_create_from_mesh)
     int rc = MK_OK;
     MK_API_BEGIN(g->ctx)
     MK_CUDA(cudaSetDevice(g->ctx->c.device));
@@ -822,6 +1135,14 @@ extern "C" int mk_igm_round(mk_igm* g, int n_fixed, const int* fixedIdcs, const 
     // ---- NI stage: Poisson solution, then the closed form of the linear LM
     run.poisson(n_fixed, fixedIdcs, fixedVals);
     bool ok = true;
+    std::unique_ptr<BarrierRun> bar;
+    if (localInjectivity) {
+        // ir.h:57-83: every LM carries the barrier and starts from lambda = 0.01; the NI stage is a real LM over [x; f] (no closed form)
+        bar = std::make_unique<BarrierRun>(g, s, &run);
+        bar->init(n_fixed, fixedIdcs);
+        bar->lm_ni(use_iter_cb != 0);
+        run.st.kernel_launches += bar->launches;
+    }
     // a Poisson solve that broke down (degenerate input: NaN / Inf in X2F or F2, or a non-SPD operator) must not enter the rounding loop
     const bool poisson_failed = run.st.status == MK_ERR_NOT_SPD || !(run.st.relres_max == run.st.relres_max);
     if (poisson_failed) {
@@ -832,11 +1153,13 @@ extern "C" int mk_igm_round(mk_igm* g, int n_fixed, const int* fixedIdcs, const 
     if (seamless && !poisson_failed) {
         // SI right-hand side base: X2F^T F2_ with F2_ = (1e8 length B x + F2) / (1e8 + 1)  ->  (1e8 A0 x + rhs0) / (1e8 + 1)
         DevBuf<double> base(g->cols);
-        g->opA0->apply(g->x.p, g->tmp.p, nullptr, run.g->pcg->ws(), s);
-        const double w = 1e8 / (1e8 + 1.0), w0 = 1.0 / (1e8 + 1.0);
-        k_axpby<<<stream_grid(g->cols), kThreads, 0, s>>>(g->cols, w, g->tmp.p, w0, g->rhs0.p, base.p);
-        MK_CHECK_LAUNCH();
-        run.st.kernel_launches += 2;
+        if (!bar) {
+            g->opA0->apply(g->x.p, g->tmp.p, nullptr, run.g->pcg->ws(), s);
+            const double w = 1e8 / (1e8 + 1.0), w0 = 1.0 / (1e8 + 1.0);
+            k_axpby<<<stream_grid(g->cols), kThreads, 0, s>>>(g->cols, w, g->tmp.p, w0, g->rhs0.p, base.p);
+            MK_CHECK_LAUNCH();
+            run.st.kernel_launches += 2;
+        }
         // ---- SI loop (ir.h:90-110, ir_loop.h:29-74)
         run.reset_constraints();
         std::vector<int> left = roundSeams ? std::vector<int>(integerIdcs, integerIdcs + n_int)
@@ -883,10 +1206,18 @@ extern "C" int mk_igm_round(mk_igm* g, int n_fixed, const int* fixedIdcs, const 
             rounded = true;
             MK_CUDA(cudaMemcpyAsync(g->xprev.p, g->x.p, sizeof(double) * g->cols, cudaMemcpyDeviceToDevice, s));
             run.eliminate_pending();
+            if (bar) {
+                // ir.h:102-104: lambda reset to 0.01, LM with the barrier on the field X2F x (iter_rounding_loop.h:77-86, ir_common.h:70-85)
+                bar->set_constraint_damping(fixed_local);
+                bar->lm_si();
+                run.st.outer_iterations++;
+                run.st.kernel_launches += bar->launches;
+            } else {
             k_axpby<<<stream_grid(g->cols), kThreads, 0, s>>>(g->cols, 1.0, base.p, 1e-4, g->xprev.p, g->b.p);
             MK_CHECK_LAUNCH();
             run.st.kernel_launches++;
             run.solve(g->opA.get());
+            }
             // post_checking (ir_loop.h:89-100): constraints are exact here, so this only guards the solver
             run.fetch_xS();
             double mx = 0;
@@ -905,4 +1236,18 @@ extern "C" int mk_igm_round(mk_igm* g, int n_fixed, const int* fixedIdcs, const 
     if (stats) *stats = run.st;
     if (!poisson_failed) rc = !ok ? MK_ERR_ROUNDING : run.st.status;
     MK_API_END_RC(g->ctx, rc)
+}
+
+extern "C" int mk_igm_round(mk_igm* g, int n_fixed, const int* fixedIdcs, const double* fixedVals, int n_sing, const int* singularIdcs,
+                            int n_int, const int* integerIdcs, int seamless, int roundSeams, double* fullx, int* fixed_idcs, int* fixed_vals,
+                            int* n_fixed_out, int* resolve_flags, int* tie_flags, mk_stats* stats) {
+    return igm_round_impl(g, n_fixed, fixedIdcs, fixedVals, n_sing, singularIdcs, n_int, integerIdcs, seamless, roundSeams, 0, 0, fullx, fixed_idcs,
+                          fixed_vals, n_fixed_out, resolve_flags, tie_flags, stats);
+}
+
+extern "C" int mk_igm_round_injective(mk_igm* g, int n_fixed, const int* fixedIdcs, const double* fixedVals, int n_sing, const int* singularIdcs,
+                                      int n_int, const int* integerIdcs, int seamless, int roundSeams, int use_iter_cb, double* fullx,
+                                      int* fixed_idcs, int* fixed_vals, int* n_fixed_out, int* resolve_flags, int* tie_flags, mk_stats* stats) {
+    return igm_round_impl(g, n_fixed, fixedIdcs, fixedVals, n_sing, singularIdcs, n_int, integerIdcs, seamless, roundSeams, 1, use_iter_cb, fullx,
+                          fixed_idcs, fixed_vals, n_fixed_out, resolve_flags, tie_flags, stats);
 }

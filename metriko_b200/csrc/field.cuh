@@ -567,13 +567,13 @@ inline EigStats inverse_iteration(Ctx& ctx, OpT& A, Precond<cdouble>* M, const d
             es.launches += rec->dots(b, grid, s);
             es.launches += rec->combine(x, 1.0, false, grid, s);
             A.apply(x, pcg.q(), nullptr, pcg.ws(), s);
-            pcg.launch_residual(b, tol * tol, maxit, 0);
+            pcg.launch_residual(b, Pcg<cdouble>::recurrence_tol2(tol), maxit, 0);
             if (add) MK_CUDA(cudaMemcpyAsync(slot, x, sizeof(cdouble) * n, cudaMemcpyDeviceToDevice, s));
             es.launches += 1 + A.launches_per_apply();
         } else {
             A.apply(u, pcg.q(), nullptr, pcg.ws(), s);
             k_dot_uq<<<grid, kThreads, 0, s>>>(n, u, pcg.q(), pcg.state(), pcg.ws());
-            k_warm_start<<<grid, kThreads, 0, s>>>(n, u, b, pcg.q(), x, pcg.r(), pcg.state(), pcg.ws(), tol * tol, maxit);
+            k_warm_start<<<grid, kThreads, 0, s>>>(n, u, b, pcg.q(), x, pcg.r(), pcg.state(), pcg.ws(), Pcg<cdouble>::recurrence_tol2(tol), maxit);
             if (add) MK_CUDA(cudaMemsetAsync(slot, 0, sizeof(cdouble) * n, s));  // first increment = the solution itself
             es.launches += 2 + A.launches_per_apply();
         }
