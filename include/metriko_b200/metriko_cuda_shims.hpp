@@ -7,8 +7,10 @@
 //   B2  metriko::cuda::CholeskyWrapper { bool factorize(const SprsD&); bool solve(const VecXd&, VecXd&) const; }   <- ir.h:14-20
 //   B4  metriko::cuda::iterative_rounding(...)  same argument list as ir.h:33-51 (localInjectivity must be false)
 //
-// Only Eigen's public accessors are used (rows(), outerIndexPtr(), innerIndexPtr(), valuePtr(), makeCompressed(), data(), resize()),
-// so the overlay compiles against any Eigen 3.3+/libigl the metriko build already fetches. Errors follow each seam's convention:
+// Only Eigen's public accessors are used (rows(), outerIndexPtr(), innerIndexPtr(), valuePtr(), makeCompressed(), data(), resize(); for B4 also
+// InnerIterator, setFromTriplets, operator*, pruned(), the RowMajor converting copy and FullPivLU::kernel()), so the overlay compiles against any
+// Eigen 3.3+/libigl the metriko build already fetches. All three seams are compiled and run in this repo against tests/cpp/mini_eigen.hpp
+// (tests/test_shim.py; the image has no Eigen). Errors follow each seam's convention:
 // B1 throws std::runtime_error like the CHOLMOD path (suitesparse/suitesparse_pdefinite.h:35-40), B2/B4 return false.
 #pragma once
 #include <complex>
@@ -60,7 +62,7 @@ inline VecXc solveSmallestEig(SprsC& L, SprsC& M, int nIter, const VecXc& u0, mk
                                              reinterpret_cast<const double*>(u0.data()), nIter, nullptr, reinterpret_cast<double*>(x.data()), stats);
     // MK_ERR_NOT_CONVERGED: the inner solves stopped at the fp64 floor above the requested residual (meshes beyond ~4M vertices); x is the
     // best iterate and the reference, which runs no convergence test at all (sls.h:44-51), would not have noticed -- warn, do not throw
-    if (rc == MK_ERR_NOT_CONVERGED) std::fprintf(stderr, "metriko_b200 solveSmallestEig: inner residual above tolerance (%s)\n", ctx.last_error());
+    if (rc == MK_ERR_NOT_CONVERGED) std::fprintf(stderr, "metriko_b200 solveSmallestEig: inner residual above tolerance (%s)\n", ctx.last_error().c_str());
     else if (rc != MK_OK) throw std::runtime_error("metriko_b200 solveSmallestEig failed (" + std::to_string(rc) + "): " + ctx.last_error());
     return x;
 }

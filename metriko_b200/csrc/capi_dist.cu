@@ -10,12 +10,14 @@
 using namespace mk;
 
 struct mk_dist {
+    CtxHold hold;
     mk_ctx* ctx = nullptr;
     DistComm c;
 };
 
 struct mk_dfield {
-    std::shared_ptr<Arena> arena;   // first member: destroyed last
+    CtxHold hold;                   // very first member: released last
+    std::shared_ptr<Arena> arena;   // destroyed after every buffer below
     mk_dist* d = nullptr;
     cudaStream_t stream = nullptr;
     int device = 0;
@@ -51,6 +53,7 @@ int mk_dist_create(mk_ctx* ctx, int rank, int world, const char* id, int id_byte
     MK_CUDA(cudaSetDevice(ctx->c.device));
     auto d = std::make_unique<mk_dist>();
     d->ctx = ctx;
+    d->hold.attach(ctx);
     d->c.rank = rank;
     d->c.world = world;
     MK_CUDA(cudaStreamCreateWithFlags(&d->c.comm_stream, cudaStreamNonBlocking));
@@ -78,6 +81,7 @@ int mk_dfield_create(mk_dist* d, int n_local, int n_interior, int n_halo, const 
     auto f = std::make_unique<mk_dfield>();
     f->arena = d->ctx->c.arena;
     f->d = d;
+    f->hold.attach(d->ctx);
     f->stream = s;
     f->device = d->ctx->c.device;
     DistFaceOp& op = f->op;

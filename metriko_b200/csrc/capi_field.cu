@@ -52,8 +52,11 @@ int mk_ctx_create(int device, void* stream, mk_ctx** out) {
 
 int mk_ctx_destroy(mk_ctx* ctx) {
     if (!ctx) return MK_OK;
-    if (ctx->c.owns_stream) cudaStreamDestroy(ctx->c.stream);
-    delete ctx;
+    if (ctx->c.handles > 0) {  // handles still refer to the stream and the error string: the last one to be destroyed finalizes the context
+        ctx->c.zombie = true;
+        return MK_OK;
+    }
+    mk_ctx_finalize(ctx);
     return MK_OK;
 }
 
@@ -74,6 +77,7 @@ int mk_field_create(mk_ctx* ctx, int nF, int nH, int N, const int* face2half, co
     auto f = std::make_unique<mk_field>();
     f->arena = ctx->c.arena;
     f->ctx = ctx;
+    f->hold.attach(ctx);
     f->stream = s;
     f->device = ctx->c.device;
     f->nF = nF; f->nH = nH; f->N = N;

@@ -10,7 +10,8 @@
 using namespace mk;  // internal header of the capi_*.cu units only
 
 struct mk_field {
-    std::shared_ptr<Arena> arena;   // first member: destroyed last, after every buffer below went back to it
+    CtxHold hold;                   // very first member: released last (may finish a deferred mk_ctx_destroy)
+    std::shared_ptr<Arena> arena;   // destroyed after every buffer below went back to it
     mk_ctx* ctx = nullptr;
     cudaStream_t stream = nullptr;  // copies, so that destruction does not depend on the context object
     int device = 0;

@@ -102,7 +102,8 @@ extern "C" int mk_solve_smallest_eig_csc(mk_ctx* ctx, int n, const int* L_outer,
 // real SPD solver handle (CholeskyWrapper, ir.h:14-20)
 // ------------------------------------------------------------------------------------------------
 struct mk_spd {
-    std::shared_ptr<Arena> arena;   // first member: destroyed last
+    CtxHold hold;                   // very first member: released last
+    std::shared_ptr<Arena> arena;   // destroyed after every buffer below
     mk_ctx* ctx = nullptr;
     cudaStream_t stream = nullptr;
     int device = 0;
@@ -126,6 +127,7 @@ extern "C" int mk_spd_factorize(mk_ctx* ctx, int n, const int* outer, const int*
     auto h = std::make_unique<mk_spd>();
     h->arena = ctx->c.arena;
     h->ctx = ctx;
+    h->hold.attach(ctx);
     h->stream = s;
     h->device = ctx->c.device;
     h->n = n;
@@ -217,7 +219,8 @@ extern "C" int mk_spd_spmv_bench(mk_spd* h, int reps, int fused_dot, double* ms_
 // IGM
 // ------------------------------------------------------------------------------------------------
 struct mk_igm {
-    std::shared_ptr<Arena> arena;   // first member: destroyed last
+    CtxHold hold;                   // very first member: released last
+    std::shared_ptr<Arena> arena;   // destroyed after every buffer below
     mk_ctx* ctx = nullptr;
     cudaStream_t stream = nullptr;
     int device = 0;
@@ -355,6 +358,7 @@ static int igm_create_impl(mk_ctx* ctx, int rows, int cols, const int64_t* x2f_p
     auto g = std::make_unique<mk_igm>();
     g->arena = ctx->c.arena;
     g->ctx = ctx;
+    g->hold.attach(ctx);
     g->stream = s;
     g->device = ctx->c.device;
     g->rows = rows; g->cols = cols; g->ufull_rows = ufull_rows;
@@ -471,6 +475,7 @@ extern "C" int mk_igm_create_from_mesh(mk_ctx* ctx, int N, int nF, int cut_nV, c
     auto g = std::make_unique<mk_igm>();
     g->arena = ctx->c.arena;
     g->ctx = ctx;
+    g->hold.attach(ctx);
     g->stream = s;
     g->device = ctx->c.device;
     g->rows = rows; g->cols = cols; g->ufull_rows = ufull_rows;
@@ -681,29 +686,128 @@ struct IgmRun {
     std::vector<double> xS;
     size_t applied = 0;  // constraints already eliminated from x
     mk_stats st{};
+    // ---- penalty slack of the reference (ir_loop.h:102-124: rounded dofs are pinned by rows of weight wConst^2 = 1e10, not eliminated).
+    // Its iterate satisfies C x = d only up to  C x_rho - d = mu / rho  (mu = Lagrange multipliers of the exactly constrained problem), so a
+    // candidate dof whose UFull row u lies in the row space of the rows already fixed sits  u . x_1 / rho  OFF its integer there,
+    //   u . x_1 = beta^T (T^T T)^-1 nu,   beta = Q u,  nu = Q (b - A x),  T = C Q^T   (first order in 1/rho; tests/tools/slack_mirror.py checks
+    // it against the oracle's penalty solves to 1e-13). `minDif > 10e-7` (ir.h:100) is evaluated on that value: every re-solve is a proximal
+    // step (wClose |x - xPrev|^2), so the decision changes fullx (7e-4 at 1M vertices for ONE re-solve), and the slack grows with the mesh
+    // (7e-10 at 642 vertices, 1.3e-6 at 1M: the reference re-solves there).
+    std::vector<double> slack_y;  // (T^T T)^-1 nu of the last re-solve; its length = the rank of the constraint set at that solve
+    std::vector<double> resS;
+    DevBuf<double> resS_dev;
+    static constexpr double kPenalty = 1e10;  // wConst^2, ir_loop.h:102
 
     void init(const std::vector<int>& idcs) {
         bank.build(g->UFull, idcs);
         const int m = (int)bank.S.size();
-        if (m > 5000) throw std::invalid_argument("igm: constraint support too large for the single-CTA projector");
         proj.m = m;
         proj.k = 0;
-        proj.kmax = (int)idcs.size() + 8;
+        proj.kmax = std::min((int)idcs.size() + 8, std::max(m, 1));   // the rank of the constraint set cannot exceed its support
         proj.S.alloc(std::max(m, 1));
         proj.S.upload(bank.S.data(), m, s);
         proj.Q.alloc((size_t)proj.kmax * std::max(m, 1));
+        proj.coef.alloc(std::max(proj.kmax, 1));
         qtmp.alloc(std::max(m, 1));
         xS_dev.alloc(std::max(m, 1));
         xS.assign(m, 0.0);
-        if ((size_t)(m + proj.kmax) * sizeof(double) > 48 * 1024)
-            MK_CUDA(cudaFuncSetAttribute(k_project, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((m + proj.kmax) * sizeof(double))));
         MK_CUDA(cudaStreamSynchronize(s));
-        use_cprec = constraint_precond_enabled() && g->precond() != nullptr && m > 0;
+        // the constraint preconditioner's coefficient kernel keeps the support in shared memory: beyond 200 KB the projector works alone
+        use_cprec = constraint_precond_enabled() && g->precond() != nullptr && m > 0 && (size_t)(m + kCprecMax) * sizeof(double) <= 200 * 1024;
         if (use_cprec) cprec.init(g->precond(), &proj, g->cols, s);
+    }
+    // after a re-solve of the SI loop with operator `op` and right-hand side g->b: nu, T, y of the constraint rows `fixed` (all of them,
+    // dependent ones included: each is a penalty row of the reference)
+    // PCG projects its right-hand side in place (solver.cuh), so the support entries of the UNPROJECTED b are put aside before the solve
+    void capture_rhs_on_support() {
+        const int m = proj.m;
+        if (m == 0) return;
+        if (!resS_dev.p) resS_dev.alloc((size_t)2 * m);
+        k_gather<<<(m + 127) / 128, 128, 0, s>>>(m, proj.S.p, g->b.p, resS_dev.p);
+        MK_CHECK_LAUNCH();
+        st.kernel_launches++;
+    }
+    void update_slack(CsrOp<double>* op, const std::vector<int>& fixed) {
+        const int m = proj.m, k = (int)cs.Q.size();
+        slack_y.clear();
+        if (m == 0 || k == 0) return;
+        op->apply(g->x.p, g->tmp.p, nullptr, g->pcg->ws(), s);
+        k_gather<<<(m + 127) / 128, 128, 0, s>>>(m, proj.S.p, g->tmp.p, resS_dev.p + m);
+        MK_CHECK_LAUNCH();
+        st.kernel_launches += 2;
+        resS.resize((size_t)2 * m);
+        resS_dev.download(resS.data(), (size_t)2 * m, s);
+        MK_CUDA(cudaStreamSynchronize(s));
+        std::vector<double> nu(k, 0.0), G((size_t)k * k, 0.0), t(k);
+        for (int j = 0; j < k; j++) {
+            double a = 0;
+            for (int p = 0; p < m; p++) a += cs.Q[j][p] * (resS[p] - resS[m + p]);
+            nu[j] = a;
+        }
+        for (int fi : fixed) {
+            const std::vector<double>& c = bank.rows.at(fi);
+            for (int j = 0; j < k; j++) {
+                double a = 0;
+                for (int p = 0; p < m; p++) a += cs.Q[j][p] * c[p];
+                t[j] = a;
+            }
+            for (int i = 0; i < k; i++)
+                for (int j = 0; j <= i; j++) G[(size_t)i * k + j] += t[i] * t[j];
+        }
+        // Cholesky of the k x k Gram matrix T^T T (full rank: Q spans exactly the rows of C), then y = G^-1 nu
+        for (int i = 0; i < k; i++) {
+            for (int j = 0; j <= i; j++) {
+                double a = G[(size_t)i * k + j];
+                for (int l = 0; l < j; l++) a -= G[(size_t)i * k + l] * G[(size_t)j * k + l];
+                if (i == j) {
+                    if (!(a > 0)) return;  // numerically rank deficient: no slack estimate (the exact values are used)
+                    G[(size_t)i * k + i] = std::sqrt(a);
+                } else G[(size_t)i * k + j] = a / G[(size_t)j * k + j];
+            }
+        }
+        for (int i = 0; i < k; i++) {
+            double a = nu[i];
+            for (int l = 0; l < i; l++) a -= G[(size_t)i * k + l] * nu[l];
+            nu[i] = a / G[(size_t)i * k + i];
+        }
+        for (int i = k - 1; i >= 0; i--) {
+            double a = nu[i];
+            for (int l = i + 1; l < k; l++) a -= G[(size_t)l * k + i] * nu[l];
+            nu[i] = a / G[(size_t)i * k + i];
+        }
+        slack_y = nu;
+        if (getenv("MK_VERBOSE")) {
+            double a = 0, b = 0;
+            for (int p = 0; p < m; p++) { a = std::max(a, std::fabs(resS[p] - resS[m + p])); b = std::max(b, std::fabs(resS[p])); }
+            double ymax = 0;
+            for (double v : slack_y) ymax = std::max(ymax, std::fabs(v));
+            fprintf(stderr, "[mk] slack update: k %d rows %zu, max |b - A x| on the support %.3e (max |b| %.3e), max |y| %.3e\n", k, fixed.size(), a, b, ymax);
+        }
+    }
+    // u . (x_rho - x) for the row of dof idx when it lies in the row space the last re-solve constrained; 0 otherwise
+    double slack_of(int idx) const {
+        const int k = (int)slack_y.size();
+        if (k == 0) return 0.0;
+        const std::vector<double>& u = bank.rows.at(idx);
+        const int m = (int)u.size();
+        std::vector<double> r = u;
+        double n0 = 0, acc = 0;
+        for (double v : u) n0 += v * v;
+        for (int j = 0; j < k; j++) {
+            double b = 0;
+            for (int p = 0; p < m; p++) b += cs.Q[j][p] * r[p];
+            for (int p = 0; p < m; p++) r[p] -= b * cs.Q[j][p];
+            acc += b * slack_y[j];
+        }
+        double n1 = 0;
+        for (double v : r) n1 += v * v;
+        if (n1 > 1e-18 * n0) return 0.0;  // an independent direction is left: the distance is not a slack effect
+        return acc / kPenalty;
     }
     void reset_constraints() {
         cs.Q.clear();
         cs.beta.clear();
+        slack_y.clear();
         proj.k = 0;
         applied = 0;
         cprec.reset();
@@ -1174,15 +1278,23 @@ static int igm_round_impl(mk_igm* g, int n_fixed, const int* fixedIdcs, const do
             run.fetch_xS();
             double minDif = 3276700.0, second = 1e300;
             int minIdx = -1;
+            double slackMin = 0.0;
             for (size_t i = 0; i < left.size(); i++) {
-                const double v = run.value_of(left[i]);
-                const double d = std::fabs(v - std::round(v));
-                if (d < minDif) { second = minDif; minIdx = (int)i; minDif = d; }
+                double v = run.value_of(left[i]);
+                double d = std::fabs(v - std::round(v));
+                double sl = 0.0;
+                if (d < 1e-5 && !bar) {  // possibly a dof the fixed rows already determine: the reference sees it through its penalty slack
+                    sl = run.slack_of(left[i]);
+                    if (getenv("MK_VERBOSE")) fprintf(stderr, "[mk] candidate %d: exact distance %.3e, emulated penalty slack %+.3e\n", left[i], d, sl);
+                    v += sl;
+                    d = std::fabs(v - std::round(v));
+                }
+                if (d < minDif) { second = minDif; minIdx = (int)i; minDif = d; slackMin = sl; }
                 else if (d < second) second = d;
             }
             if (minIdx < 0) { ok = false; break; }  // every candidate value is NaN / Inf: a diverged solve, not a rounding decision
             const int idx = left[minIdx];
-            const double X = run.value_of(idx);
+            const double X = run.value_of(idx) + slackMin;
             if (!std::isfinite(X) || std::fabs(X) > 2.0e9) { ok = false; break; }
             const int val = (int)std::round(X);
             left.erase(left.begin() + minIdx);
@@ -1193,6 +1305,10 @@ static int igm_round_impl(mk_igm* g, int n_fixed, const int* fixedIdcs, const do
             int flags = 0;
             if (std::fabs(std::fabs(X - std::floor(X)) - 0.5) < 1e-6) flags |= 1;
             if (minDif > 10e-7 && second - minDif < 1e-8) flags |= 2;
+            // the re-solve decision itself (ir.h:100: minDif > 10e-7) is a near-tie when the dof sits within a factor 2 of the threshold: the
+            // distance is then the reference's penalty slack (emulated to first order in 1/rho, see IgmRun::slack_of), whose own round-off
+            // (a kappa ~ 1e14 factorisation) is of that order
+            if (minDif > 0.5e-6 && minDif < 2e-6) flags |= 4;
             const bool consistent = run.add_constraint(idx, (double)val);
             const bool resolve = minDif > 10e-7;
             fixed_local.push_back(idx);
@@ -1216,7 +1332,9 @@ static int igm_round_impl(mk_igm* g, int n_fixed, const int* fixedIdcs, const do
             k_axpby<<<stream_grid(g->cols), kThreads, 0, s>>>(g->cols, 1.0, base.p, 1e-4, g->xprev.p, g->b.p);
             MK_CHECK_LAUNCH();
             run.st.kernel_launches++;
+            run.capture_rhs_on_support();
             run.solve(g->opA.get());
+            run.update_slack(g->opA.get(), fixed_local);
             }
             // post_checking (ir_loop.h:89-100): constraints are exact here, so this only guards the solver
             run.fetch_xS();

@@ -8,6 +8,23 @@ struct mk_ctx {
     mk::Ctx c;
 };
 
+// Handles keep a raw mk_ctx* (stream, error string). mk_ctx_destroy with live handles therefore only marks the context; the object and its
+// stream go when the last handle is destroyed (one host thread per context, so a plain counter is enough).
+inline void mk_ctx_finalize(mk_ctx* ctx) {
+    if (ctx->c.owns_stream) cudaStreamDestroy(ctx->c.stream);
+    delete ctx;
+}
+struct CtxHold {
+    mk_ctx* c = nullptr;
+    CtxHold() = default;
+    CtxHold(const CtxHold&) = delete;
+    CtxHold& operator=(const CtxHold&) = delete;
+    void attach(mk_ctx* x) { c = x; x->c.handles++; }
+    ~CtxHold() {
+        if (c && --c->c.handles == 0 && c->c.zombie) mk_ctx_finalize(c);
+    }
+};
+
 #define MK_API_BEGIN(ctxp) try { mk::AllocStreamScope _alloc_scope((ctxp)->c.stream, (ctxp)->c.arena.get());
 #define MK_API_END_RC(ctxp, rc)                                                     \
     return (rc);                                                                    \

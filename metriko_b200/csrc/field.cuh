@@ -16,6 +16,8 @@ struct Ctx {
     bool owns_stream = false;
     std::string err;
     std::shared_ptr<Arena> arena;  // device memory of everything created under this context (handles share ownership)
+    int handles = 0;               // live mk_field / mk_spd / mk_igm / mk_dist / mk_dfield objects created under this context
+    bool zombie = false;           // mk_ctx_destroy was called while handles were live: the last handle to go finishes the job
 };
 
 // Face stencil storage ("ELL-3", SoA): every face row of L has the constant diagonal 3 + 1e-9 (frf.h:65-75, closed

@@ -2,6 +2,7 @@
 // Set-up runs once per matrix; the per-iteration work is all on the device.
 #pragma once
 #include <omp.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
 #include <cmath>
@@ -14,13 +15,24 @@
 
 namespace mk {
 
-// MK_VERBOSE=1: set-up stage timers on stderr
+// NVTX ranges (header-only nvtx3: no-ops unless a profiler injected its library) around every stage a timeline should show: set-up stages,
+// each PCG solve, each inverse-iteration step, each rounding re-solve (SURVEY.md section 5 "tracing")
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+
+// MK_VERBOSE=1: set-up stage timers on stderr; always: one NVTX range per timer scope, one mark per lap
 struct StageTimer {
     bool on;
     double t0;
     const char* what;
-    explicit StageTimer(const char* w) : on(getenv("MK_VERBOSE") != nullptr), t0(omp_get_wtime()), what(w) {}
+    NvtxRange range;
+    explicit StageTimer(const char* w) : on(getenv("MK_VERBOSE") != nullptr), t0(omp_get_wtime()), what(w), range(w) {}
     void lap(const char* stage) {
+        nvtxMarkA(stage);
         if (!on) return;
         const double t = omp_get_wtime();
         fprintf(stderr, "[mk] %s: %-28s %8.1f ms\n", what, stage, (t - t0) * 1e3);

@@ -65,14 +65,46 @@ static __global__ void __launch_bounds__(kThreads) k_axpby(int n, double a, cons
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) y[i] = a * x[i] + b * z[i];
 }
 
+// The same projection for large constraint sets (hundreds of singularities / seam dofs: k m beyond what one CTA should do, or m + k beyond
+// its shared memory): c = Q v_S with one warp per constraint row, then v_S -= Q^T c with one thread per support column. Two launches, any size.
+static __global__ void __launch_bounds__(kThreads) k_project_dots(int k, int m, const int* __restrict__ S, const double* __restrict__ Q,
+                                                           const double* __restrict__ v, double* __restrict__ c, const PcgState* st) {
+    if (st && st->done) return;
+    const int lane = threadIdx.x & 31;
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (j >= k) return;
+    double a = 0.0;
+    for (int s = lane; s < m; s += 32) a += Q[(size_t)j * m + s] * v[S[s]];
+    a = warp_sum(a);
+    if (lane == 0) c[j] = a;
+}
+static __global__ void __launch_bounds__(kThreads) k_project_apply(int k, int m, const int* __restrict__ S, const double* __restrict__ Q,
+                                                            const double* __restrict__ c, double* __restrict__ v, const PcgState* st) {
+    if (st && st->done) return;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= m) return;
+    double a = 0.0;
+    for (int j = 0; j < k; j++) a += c[j] * Q[(size_t)j * m + s];
+    v[S[s]] -= a;
+}
+
+constexpr int kProjectOneCtaWork = 1 << 16;   // k * m up to which the single-CTA kernel is used (one launch, everything in shared memory)
+
 struct ConstraintProjector : Projector<double> {
     int k = 0, m = 0;
     DevBuf<int> S;
     DevBuf<double> Q;  // capacity kmax x m
+    DevBuf<double> coef;  // kmax
     int kmax = 0;
+    bool one_cta() const { return (long)k * m <= kProjectOneCtaWork && (size_t)(m + k) * sizeof(double) <= 48 * 1024; }
     void apply(double* v, const PcgState* st, cudaStream_t s) override {
         if (k == 0) return;
-        k_project<<<1, kThreads, (size_t)(m + k) * sizeof(double), s>>>(k, m, S.p, Q.p, v, st);
+        if (one_cta()) {
+            k_project<<<1, kThreads, (size_t)(m + k) * sizeof(double), s>>>(k, m, S.p, Q.p, v, st);
+        } else {
+            k_project_dots<<<(k * 32 + kThreads - 1) / kThreads, kThreads, 0, s>>>(k, m, S.p, Q.p, v, coef.p, st);
+            k_project_apply<<<(m + kThreads - 1) / kThreads, kThreads, 0, s>>>(k, m, S.p, Q.p, coef.p, v, st);
+        }
         MK_CHECK_LAUNCH();
     }
 };
@@ -153,6 +185,7 @@ struct ConstraintPrecond : Precond<double> {
         std::memset(&h, 0, sizeof(h));
         h.rr = 1.0; h.rho = 1.0; h.bnorm2 = 1.0;
         unit.upload(&h, 1, s);
+        if ((size_t)(proj->m + kCprecMax) * sizeof(double) > 200 * 1024) throw std::invalid_argument("constraint preconditioner: support too large (disable with MK_IGM_CPREC=0)");
         if ((size_t)(proj->m + kCprecMax) * sizeof(double) > 48 * 1024)
             MK_CUDA(cudaFuncSetAttribute(k_cprec_coef, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((proj->m + kCprecMax) * sizeof(double))));
         MK_CUDA(cudaStreamSynchronize(s));

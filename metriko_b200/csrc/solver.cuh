@@ -21,7 +21,15 @@ namespace mk {
 // Buffers created outside any context scope fall back to cudaMallocAsync on the scope's stream.
 struct Arena {
     static constexpr size_t kAlign = 512;
-    static constexpr size_t kSlabMin = (size_t)2 << 30;
+    // Slab sizes grow geometrically from 256 MiB to 2 GiB (a 2,562-vertex mesh should not pin 2 GiB; a 1M-vertex step ends up with a handful
+    // of 2 GiB slabs after its first pass); MK_ARENA_SLAB_MB fixes the size instead. A request larger than the current slab size gets a
+    // slab of its own.
+    static constexpr size_t kSlabFirst = (size_t)256 << 20, kSlabMax = (size_t)2 << 30;
+    size_t next_slab = slab_from_env() ? slab_from_env() : kSlabFirst;
+    static size_t slab_from_env() {
+        static const size_t v = [] { const char* e = getenv("MK_ARENA_SLAB_MB"); return e && atol(e) > 0 ? (size_t)atol(e) << 20 : (size_t)0; }();
+        return v;
+    }
     std::vector<void*> slabs;
     std::map<char*, size_t> free_by_addr;
     std::multimap<size_t, char*> free_by_size;
@@ -61,7 +69,8 @@ struct Arena {
         bytes = (bytes + kAlign - 1) / kAlign * kAlign;
         auto it = free_by_size.lower_bound(bytes);
         if (it == free_by_size.end()) {
-            const size_t slab = bytes > kSlabMin ? bytes : kSlabMin;
+            const size_t slab = bytes > next_slab ? bytes : next_slab;
+            if (!slab_from_env() && next_slab < kSlabMax) next_slab *= 2;
             void* base = nullptr;
             MK_CUDA(cudaMalloc(&base, slab));
             slabs.push_back(base);

@@ -131,7 +131,7 @@ def iterative_rounding(fixedIdcs, fixedVals, singularIdcs, integerIdcs, length, 
 
 
 def iterative_rounding_x2f(fixedIdcs, fixedVals, singularIdcs, integerIdcs, length, UFull, X2F, N, n, seamless, roundSeams, F2,
-                           ni_mode="lm", stats=None, localInjectivity=False, iter_cb=None, reuse_factor=False, progress=None):
+                           ni_mode="lm", stats=None, localInjectivity=False, iter_cb=None, reuse_factor=False, progress=None, trace=None):
     """The body of ir.h:33-113. G2 enters the algorithm only through X2F = (G2 UFull).pruned() (ir_init.h:173,
     ir_loop.h:123; gInteg * UExt = [-length X2F | I], ir_init.h:40-55), so X2F is the operator input here.
     Returns dict(success, fullx, x_small, fixedIdcs, fixedVals, n_solves, min_margin, ...).
@@ -253,6 +253,8 @@ def iterative_rounding_x2f(fixedIdcs, fixedVals, singularIdcs, integerIdcs, leng
         fixed_i.append(idx)
         fixed_v.append(val)
         del left[minIdx]
+        if trace is not None:  # every fixed dof, re-solved or not: (dof, value before rounding, distance, runner-up distance)
+            trace.append((idx, float(X[idx]), float(minDif), float(second)))
         if not left and not roundSeams and not roundedSingulars:
             left = list(integerIdcs)
             roundedSingulars = True

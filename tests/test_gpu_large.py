@@ -64,13 +64,17 @@ def test_large_golden(ctx, name):
     got = dict(zip([int(i) for i in out["fixedIdcs"]], [int(v) for v in out["fixedVals"]]))
     ref = dict(zip(g["out_fixedIdcs"].tolist(), g["out_fixedVals"].tolist()))
     assert got == ref, (name, {k: (got.get(k), ref.get(k)) for k in set(got) | set(ref) if got.get(k) != ref.get(k)})  # bit-exact integers
+    # the re-solve decision `minDif > 10e-7` (ir.h:100) of dofs the fixed rows already determine is taken on the reference's penalty slack,
+    # which the device emulates (IgmRun::slack_of): same number of re-solves, incl. the 13th of the 1M-vertex mesh whose slack is 1.31e-6
+    # (flag bit 2 marks decisions within a factor 2 of the threshold)
     assert out["n_solves"] == int(g["n_solves"])
+    sel = [tuple(r) for r in g["selection"]]
     resolved = [(i, t) for i, r, t in zip(out["fixedIdcs"], out["resolve_flags"], out["tie_flags"]) if r]
-    assert len(resolved) == len(g["selection"])
+    assert len(resolved) == len(sel)
     # same dof per re-solve, except at selection near-ties: symmetric twins of the mesh whose distances to an integer differ by ~1e-8 in
     # the oracle's run; the device run (whose inputs differ by ~1e-9: its own field went through the host stages) may order them the
     # other way, and must then have FLAGGED the step (bit 1: its own runner-up was within 1e-8)
-    for (i, t), (j, dmin, dsecond) in zip(resolved, g["selection"]):
+    for (i, t), (j, dmin, dsecond) in zip(resolved, sel):
         assert i == int(j) or ((t & 2) and dsecond - dmin < 1e-7), (i, j, t, dmin, dsecond)
     assert not any(t & 1 for t in out["tie_flags"])                      # no rounding near-tie at these sizes (min margin stored)
     assert np.abs(out["fullx"][g["fullx_idx"]] - g["fullx_val"]).max() < 1e-6

@@ -1,9 +1,15 @@
 """The C++ header overlay (include/metriko_b200/metriko_cuda_shims.hpp) compiles against the Eigen accessors it uses, links
-with the C-ABI library, fails loudly without a device (CPU test) and runs seams B1 + B2 on a B200 (GPU test)."""
+with the C-ABI library, fails loudly without a device (CPU test) and runs seams B1 + B2 on a B200 (GPU test). Seam B4
+(`cuda::iterative_rounding` with the reference's argument list, `detail::kernel_basis`, `detail::CsrCopy`) is compiled against
+tests/cpp/mini_eigen.hpp: its host part (UFull from Cfull, X2F = (G2 UFull).pruned()) is compared with the host glue on the CPU, the
+whole call with the oracle on a B200."""
 import os
+import struct
 import subprocess
 
+import numpy as np
 import pytest
+import scipy.sparse as sp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -36,3 +42,105 @@ def test_shim_runs_b1_b2_on_gpu(tmp_path):
     x = [float(t) for t in r.stdout.split("B2 ok x =")[1].split()]
     # [[4,-1,0],[-1,4,-1],[0,-1,4]] x = [1,2,3]
     assert max(abs(a - b) for a, b in zip(x, (0.4642857143, 0.8571428571, 0.9642857143))) < 1e-8
+
+
+# ---- seam B4 ----
+
+def _build_b4(tmp_path):
+    from metriko_b200 import build
+    build.build_cuda()
+    exe = str(tmp_path / "shim_b4_test")
+    libdir = os.path.join(ROOT, "metriko_b200")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Werror=format", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "tests", "cpp"),
+                    os.path.join(ROOT, "tests", "cpp", "shim_b4_test.cpp"), "-o", exe, "-L", libdir, "-lmetriko_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    return exe
+
+
+def _put_matrix(f, A):
+    A = sp.coo_matrix(A)
+    f.write(struct.pack("<iiq", A.shape[0], A.shape[1], A.nnz))
+    f.write(np.ascontiguousarray(A.row, np.int32).tobytes())
+    f.write(np.ascontiguousarray(A.col, np.int32).tobytes())
+    f.write(np.ascontiguousarray(A.data, np.float64).tobytes())
+
+
+def _put_vec(f, v, dt):
+    v = np.ascontiguousarray(v, dt)
+    f.write(struct.pack("<q", v.size))
+    f.write(v.tobytes())
+
+
+def _get_matrix(buf, off):
+    r, c, nnz = struct.unpack_from("<iiq", buf, off)
+    off += 16
+    row = np.frombuffer(buf, np.int32, nnz, off); off += 4 * nnz
+    col = np.frombuffer(buf, np.int32, nnz, off); off += 4 * nnz
+    val = np.frombuffer(buf, np.float64, nnz, off); off += 8 * nnz
+    return sp.csr_matrix((val, (row, col)), shape=(r, c)), off
+
+
+def _b4_case(tmp_path, localInjectivity=False):
+    from hostglue import Session
+    import oracle
+    s = Session().make_sphere(20, 3, bump=0.08)
+    fi = s.field_inputs()
+    nF = s.dims["nF"]
+    L = oracle.connection_laplacian(fi["twin"], fi["face"], fi["heArgOnFace"], nF, 4)
+    M = oracle.galerkin_mass_matrix(fi["faceArea"])
+    z = oracle.solve_smallest_eig(L, M, oracle.random_u0(nF, 0), 50)
+    s.field_post(z, 4, "curl")
+    s.igm_setup(0.02)
+    inp = s.igm_inputs()
+    path = str(tmp_path / "b4_in.bin")
+    with open(path, "wb") as f:
+        f.write(struct.pack("<6i", inp["N"], inp["n"], inp["nF"], 1, 0, int(localInjectivity)))
+        f.write(struct.pack("<d", inp["length"]))
+        _put_matrix(f, inp["Cfull"])
+        _put_matrix(f, inp["G2p"])
+        _put_vec(f, inp["fixedIdcs"], np.int32)
+        _put_vec(f, inp["fixedVals"], np.float64)
+        _put_vec(f, inp["singularIdcs"], np.int32)
+        _put_vec(f, inp["integerIdcs"], np.int32)
+        _put_vec(f, inp["F2"], np.float64)
+    return inp, path
+
+
+def _check_host_part(buf, inp):
+    U, off = _get_matrix(buf, 0)
+    X, off = _get_matrix(buf, off)
+    # the overlay's kernel basis against the host glue's restatement of ir_init.h:98-154 (an independent FullPivLU::kernel implementation)
+    assert U.shape == inp["UFull"].shape and abs(U - inp["UFull"]).max() < 1e-12
+    assert X.shape == inp["X2F"].shape and abs(X - inp["X2F"]).max() < 1e-12
+    assert abs(inp["Cfull"] @ U).max() < 1e-12          # it IS a kernel basis
+    return off
+
+
+def test_shim_b4_compiles_and_builds_ufull_x2f_on_cpu(tmp_path):
+    exe = _build_b4(tmp_path)
+    inp, path = _b4_case(tmp_path)
+    out = str(tmp_path / "b4_out.bin")
+    r = subprocess.run([exe, "host", path, out], capture_output=True, text=True)
+    assert r.returncode == 0 and "host ok" in r.stdout, r.stdout + r.stderr
+    _check_host_part(open(out, "rb").read(), inp)
+
+
+@pytest.mark.gpu
+def test_shim_b4_iterative_rounding_on_gpu(tmp_path):
+    """cuda::iterative_rounding(fixedIdcs, ..., Cfull, G2, ..., intrinsicField, fullx) -- the reference's own call (integ.ipp:66-86) --
+    against the oracle on the same inputs: fullx within 1e-6 (integers included: every rounded dof of fullx is the oracle's integer)."""
+    import oracle
+    exe = _build_b4(tmp_path)
+    inp, path = _b4_case(tmp_path)
+    out = str(tmp_path / "b4_out.bin")
+    r = subprocess.run([exe, "run", path, out], capture_output=True, text=True)
+    assert r.returncode == 0 and "B4 ok" in r.stdout, r.stdout + r.stderr
+    buf = open(out, "rb").read()
+    off = _check_host_part(buf, inp)
+    ok, n = struct.unpack_from("<iq", buf, off)
+    fullx = np.frombuffer(buf, np.float64, n, off + 12)
+    ref = oracle.iterative_rounding(inp["fixedIdcs"], inp["fixedVals"], inp["singularIdcs"], inp["integerIdcs"], inp["length"], inp["UFull"],
+                                    inp["G2p"], inp["N"], inp["n"], inp["nF"], True, False, inp["F2"], ni_mode="closed")
+    assert ok == 1 and ref["success"]
+    assert np.abs(fullx - ref["fullx"]).max() < 1e-6
+    for i, v in zip(ref["fixedIdcs"], ref["fixedVals"]):
+        assert abs(fullx[i] - v) < 1e-7
