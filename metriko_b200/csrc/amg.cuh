@@ -46,6 +46,12 @@ struct AmgParams {
                                // as singletons to the coarsest level (solved exactly there), l1-scaled in the smoother
     int agg = 1;               // 0 = sequential greedy (Vanek), 1 = MIS(2) roots (parallel; what the device set-up runs)
     int inject_dense = 1;      // prolongator rows of dense dofs are not smoothed (injection from their singleton aggregate)
+    int weighted = 1;          // transport mode: a coarse dof stands for an aggregate whose tentative column was normalised, so a field of
+                               // constant modulus has coarse coefficients proportional to the column norms (sqrt of the aggregate size on
+                               // level 1). The transported unit value is therefore scaled by that norm on every level below the finest --
+                               // what smoothed aggregation's local QR does with a one-column candidate. 0 = unit modulus on every level
+                               // (rounds 1-2a: the V-cycle lost against the two-grid method level by level: 66 against 19 iterations
+                               // at 1M vertices in the CPU mirror, tests/tools/field_cycle_study.py)
 };
 
 // real_op: the real symmetric IGM / LM operators use a strength threshold (drops weak and wrong-signed cotan couplings
@@ -62,6 +68,7 @@ inline AmgParams amg_params_from_env(bool real_op = false) {
     if (const char* e = getenv("MK_AMG_DENSE")) p.dense_row = atoi(e);
     if (const char* e = getenv("MK_AMG_AGG")) p.agg = atoi(e);
     if (const char* e = getenv("MK_AMG_INJECT")) p.inject_dense = atoi(e);
+    if (const char* e = getenv("MK_AMG_WEIGHTED")) p.weighted = atoi(e);
     return p;
 }
 
@@ -343,6 +350,8 @@ inline std::vector<AmgHostLevel<S>> build_hierarchy(HostCsr<S> A, std::vector<S>
                                                    : aggregate(L.A, prm.theta, use_cand ? &cand : nullptr, dense, agg, tv, dense_coarse);
         tm.lap("aggregate");
         if (nc >= n * 0.8 || nc == 0) { lv.push_back(std::move(L)); break; }  // stagnation: stop here
+        if (!use_cand && prm.weighted && !lv.empty())  // transport mode below the finest level: unit phase x the weight this dof stands for
+            for (int i = 0; i < n; i++) tv[i] *= cand[i];
         // normalise the tentative columns; the column norms are the coarse candidate
         std::vector<double> nrm(nc, 0.0);
         for (int i = 0; i < n; i++) nrm[agg[i]] += std::norm(tv[i]);

@@ -183,15 +183,18 @@ static __global__ void k_assign_singletons(int n, const int* __restrict__ flag, 
     if (flag[i]) { agg[i] = base + id[i]; st_rw(tv + i, dev_one<T>()); }
 }
 
-static __global__ void k_agg_sizes(int n, const int* __restrict__ agg, int* __restrict__ size) {
+// size[a] = sum of the members' weights^2. `cnt` (null on the finest level: every dof counts 1) = how many finest-level dofs a dof of this
+// level stands for = the SQUARE of its weight in the tentative prolongator (AmgParams::weighted), so the sums stay integers on every level:
+// exact in any order, the hierarchy stays bit-reproducible.
+static __global__ void k_agg_sizes(int n, const int* __restrict__ agg, const int* __restrict__ cnt, int* __restrict__ size) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) atomicAdd(size + agg[i], 1);  // integer counts: exact in any order
+    if (i < n) atomicAdd(size + agg[i], cnt ? cnt[i] : 1);
 }
 
-// T: one entry per row, (i, agg[i]) = tv[i] / sqrt(|aggregate|) (|tv| = 1, so the column norm is sqrt of the member count)
+// T: one entry per row, (i, agg[i]) = tv[i] * w_i / sqrt(sum of w^2 over the aggregate), |tv| = 1, w_i = sqrt(cnt[i]) (1 on the finest level)
 template <class T>
-static __global__ void k_build_tentative(int n, const int* __restrict__ agg, const T* __restrict__ tv, const int* __restrict__ size, int* __restrict__ tptr,
-                                         int* __restrict__ tcol, T* __restrict__ tval) {
+static __global__ void k_build_tentative(int n, const int* __restrict__ agg, const T* __restrict__ tv, const int* __restrict__ cnt, const int* __restrict__ size,
+                                         int* __restrict__ tptr, int* __restrict__ tcol, T* __restrict__ tval) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i > n) return;
     tptr[i] = i;
@@ -199,8 +202,9 @@ static __global__ void k_build_tentative(int n, const int* __restrict__ agg, con
     const int a = agg[i];
     tcol[i] = a;
     const double nrm = sqrt((double)size[a]);
+    const double w = cnt ? sqrt((double)cnt[i]) : 1.0;
     const T t = ld_ro(tv + i);
-    st_rw(tval + i, ST<T>::scale(1.0 / nrm, t));
+    st_rw(tval + i, ST<T>::scale(w / nrm, t));
 }
 
 // S = I - omega D^{-1} A on the pattern of A -- except the rows of dense dofs, which are the identity (one entry): dense dofs are
@@ -297,7 +301,7 @@ static __global__ void k_coarse_types(int n, const int* __restrict__ agg, const 
 // dense (may be null): dense dofs of this level; dense_next (size >= n): flags of the coarse level (its last n_dense ids).
 template <class T>
 inline int aggregate_dev(const DeviceCsr<T>& A, double theta, const char* dense, int n_dense, const double* dabs, DeviceCsr<T>& Tm, cudaStream_t s,
-                         const int* type = nullptr, DevBuf<int>* type_next = nullptr) {
+                         const int* type = nullptr, DevBuf<int>* type_next = nullptr, const int* cnt = nullptr, DevBuf<int>* cnt_next = nullptr) {
     const int n = A.rows;
     const int g = (n + 255) / 256;
     const double theta2 = theta * theta;
@@ -341,14 +345,14 @@ inline int aggregate_dev(const DeviceCsr<T>& A, double theta, const char* dense,
     MK_CHECK_LAUNCH();
     DevBuf<int> size((size_t)std::max(nagg, 1));
     size.zero(s);
-    k_agg_sizes<<<g, 256, 0, s>>>(n, agg.p, size.p);
+    k_agg_sizes<<<g, 256, 0, s>>>(n, agg.p, cnt, size.p);
     Tm.rows = n;
     Tm.cols = nagg;
     Tm.nnz = n;
     Tm.ptr.alloc((size_t)n + 1);
     Tm.col.alloc(n);
     Tm.val.alloc(n);
-    k_build_tentative<T><<<(n + 256) / 256, 256, 0, s>>>(n, agg.p, tv.p, size.p, Tm.ptr.p, Tm.col.p, Tm.val.p);
+    k_build_tentative<T><<<(n + 256) / 256, 256, 0, s>>>(n, agg.p, tv.p, cnt, size.p, Tm.ptr.p, Tm.col.p, Tm.val.p);
     if (type && type_next) {
         type_next->alloc((size_t)std::max(nagg, 1));
         type_next->zero(s);
@@ -356,6 +360,7 @@ inline int aggregate_dev(const DeviceCsr<T>& A, double theta, const char* dense,
     }
     MK_CHECK_LAUNCH();
     MK_CUDA(cudaStreamSynchronize(s));
+    if (cnt_next) *cnt_next = std::move(size);  // the coarse dofs' counts (weights^2)
     return nagg;
 }
 
@@ -379,6 +384,7 @@ inline std::unique_ptr<AmgPrecond<T>> build_amg_device(cudaStream_t s, DeviceCsr
     double nnz_sum = 0, n_sum = 0;
     DeviceCsr<T> A = std::move(A0);
     DevBuf<char> dense;
+    DevBuf<int> counts;  // finest-level dofs per dof of the current level (null on the finest level); AmgParams::weighted
     int n_dense = 0;
     if (prm.dense_row > 0 && A.rows > prm.coarse_max) {
         dense.alloc(A.rows);
@@ -407,10 +413,11 @@ inline std::unique_ptr<AmgPrecond<T>> build_amg_device(cudaStream_t s, DeviceCsr
         tm.lap("dinv + rho");
         bool last = (n - n_dense <= prm.coarse_max) || (l + 1 >= prm.max_levels);
         DeviceCsr<T> Tm;
-        DevBuf<int> types_next;
+        DevBuf<int> types_next, counts_next;
         int nc = 0;
         if (!last) {
-            nc = aggregate_dev<T>(A, prm.theta, n_dense ? dense.p : nullptr, n_dense, dabs.p, Tm, s, types.p, &types_next);
+            nc = aggregate_dev<T>(A, prm.theta, n_dense ? dense.p : nullptr, n_dense, dabs.p, Tm, s, types.p, &types_next,
+                                  prm.weighted ? counts.p : nullptr, prm.weighted ? &counts_next : nullptr);
             tm.lap("aggregate");
             if (nc >= n * 0.8 || nc == 0) last = true;
         }
@@ -463,6 +470,7 @@ inline std::unique_ptr<AmgPrecond<T>> build_amg_device(cudaStream_t s, DeviceCsr
         }
         A = std::move(Ac);
         if (types.p) types = std::move(types_next);
+        counts = std::move(counts_next);
     }
     // coarsest level: dense inverse on the host (<= 1500 rows) or Chebyshev
     AmgLevelDev<T>& C = amg->lv.back();

@@ -871,6 +871,7 @@ struct IgmRun {
     }
     // Poisson stage: min ||length X2F x - F2|| s.t. UFull[fixed] x = vals  (ir_init.h:173-212)
     void poisson(int n_fixed, const int* fixedIdcs, const double* fixedVals) {
+        NvtxRange nvtx_("igm_poisson");
         reset_constraints();
         g->x.zero(s);
         fetch_xS();
@@ -1275,6 +1276,7 @@ static int igm_round_impl(mk_igm* g, int n_fixed, const int* fixedIdcs, const do
         DevBuf<double> x_ni(g->cols);
         MK_CUDA(cudaMemcpyAsync(x_ni.p, g->x.p, sizeof(double) * g->cols, cudaMemcpyDeviceToDevice, s));
         while (!left.empty()) {
+            NvtxRange nvtx_("igm_rounding_step");
             run.fetch_xS();
             double minDif = 3276700.0, second = 1e300;
             int minIdx = -1;

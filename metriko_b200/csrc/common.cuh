@@ -1,6 +1,7 @@
 // Shared device/host helpers for libmetriko_b200 (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <cstdint>
 #include <cstdio>
@@ -8,6 +9,17 @@
 #include <string>
 
 namespace mk {
+
+#ifndef MK_NVTX_RANGE_DEFINED
+#define MK_NVTX_RANGE_DEFINED
+// NVTX range (header-only nvtx3: a no-op unless a profiler injected its library); see hostcsr.hpp
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+#endif
 
 struct CudaError : std::runtime_error {
     using std::runtime_error::runtime_error;

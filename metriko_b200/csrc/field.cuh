@@ -560,6 +560,7 @@ inline EigStats inverse_iteration(Ctx& ctx, OpT& A, Precond<cdouble>* M, const d
     const int grid = pcg.grid();
     int hint = 0;
     for (int it = 0; it < n_iter; it++) {
+        NvtxRange nvtx_("inverse_iteration_step");
         const bool recycle = rec && rec->cap > 0;
         const bool add = recycle && rec->count < rec->cap;  // once the space is full it is frozen (late increments are ~0 anyway)
         cdouble* slot = add ? rec->E.p + (size_t)rec->count * n : nullptr;

@@ -17,12 +17,15 @@ namespace mk {
 
 // NVTX ranges (header-only nvtx3: no-ops unless a profiler injected its library) around every stage a timeline should show: set-up stages,
 // each PCG solve, each inverse-iteration step, each rounding re-solve (SURVEY.md section 5 "tracing")
+#ifndef MK_NVTX_RANGE_DEFINED
+#define MK_NVTX_RANGE_DEFINED
 struct NvtxRange {
     explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
     ~NvtxRange() { nvtxRangePop(); }
     NvtxRange(const NvtxRange&) = delete;
     NvtxRange& operator=(const NvtxRange&) = delete;
 };
+#endif
 
 // MK_VERBOSE=1: set-up stage timers on stderr; always: one NVTX range per timer scope, one mark per lap
 struct StageTimer {

@@ -387,6 +387,7 @@ public:
     static constexpr double kRecurrenceMargin = 0.7;
     static double recurrence_tol2(double tol) { return tol * tol * kRecurrenceMargin * kRecurrenceMargin; }  // for callers that start the state themselves
     SolveStats solve(T* b, T* x, double tol, int maxit, bool residual_ready, int chunk = 16, bool use_graph = true, int hint = 0) {
+        NvtxRange nvtx_("pcg_solve");
         SolveStats out;
         long launches = 0;
         const double tol2 = tol * tol * kRecurrenceMargin * kRecurrenceMargin;
