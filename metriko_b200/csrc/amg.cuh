@@ -58,7 +58,11 @@ struct AmgParams {
 // from the aggregation graph); the complex face operator has unit-modulus off-diagonals and keeps theta = 0.
 inline AmgParams amg_params_from_env(bool real_op = false) {
     AmgParams p;
-    if (real_op) p.theta = 0.1;
+    // theta of the complex operator only acts below the finest level (its own off-diagonals all have unit modulus): dropping the weakest
+    // Galerkin couplings from the aggregation graph keeps the coarse aggregates compact (level 1 -> 2 coarsens 8:1 instead of 17:1).
+    // 1M vertices, B200: 480 / 359 / 336 / 330 / 343 / 838 inner iterations per 50-step solve at theta = 0 / 0.02 / 0.03 / 0.05 / 0.08 / 0.1
+    // (profiles/amg_tuning_r02_*): 0.03 sits in the flat part, far from the cliff at 0.1; torus and 16k ... 4M-vertex spheres agree.
+    p.theta = real_op ? 0.1 : 0.03;
     if (const char* e = getenv("MK_AMG_DEG")) p.cheb_degree = atoi(e);
     if (const char* e = getenv("MK_AMG_DEG_COARSE")) p.cheb_degree_coarse = atoi(e);
     if (const char* e = getenv("MK_AMG_RATIO")) p.cheb_ratio = atof(e);
@@ -69,6 +73,9 @@ inline AmgParams amg_params_from_env(bool real_op = false) {
     if (const char* e = getenv("MK_AMG_AGG")) p.agg = atoi(e);
     if (const char* e = getenv("MK_AMG_INJECT")) p.inject_dense = atoi(e);
     if (const char* e = getenv("MK_AMG_WEIGHTED")) p.weighted = atoi(e);
+    // per-operator overrides (the complex face operator and the real IGM / LM operators want different values)
+    if (const char* e = getenv(real_op ? "MK_AMG_THETA_REAL" : "MK_AMG_THETA_FIELD")) p.theta = atof(e);
+    if (const char* e = getenv(real_op ? "MK_AMG_COARSE_REAL" : "MK_AMG_COARSE_FIELD")) p.coarse_max = atoi(e);
     return p;
 }
 

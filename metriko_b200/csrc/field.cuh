@@ -514,7 +514,7 @@ struct RecycleSpace {
         n = n_; cap = cap_; count = 0;
         if (cap <= 0) return;
         if (E.n != (size_t)n * cap) E.alloc((size_t)n * cap);
-        if (!coef.p) coef.alloc(cap);
+        if (coef.n < (size_t)cap) coef.alloc(cap);  // (a handle may be solved again with more outer steps: the coefficients must follow)
         if (!partials.p) { partials.alloc((size_t)kMaxPartials * 2 * kRecycleChunk); ticket.alloc(1); ticket.zero(s); }
     }
     ReduceWs ws() { return ReduceWs{partials.p, ticket.p}; }
@@ -559,6 +559,7 @@ inline EigStats inverse_iteration(Ctx& ctx, OpT& A, Precond<cdouble>* M, const d
     pcg.bind(&A, M, nullptr);
     const int grid = pcg.grid();
     int hint = 0;
+    double tol_eff = tol;
     for (int it = 0; it < n_iter; it++) {
         NvtxRange nvtx_("inverse_iteration_step");
         const bool recycle = rec && rec->cap > 0;
@@ -570,19 +571,24 @@ inline EigStats inverse_iteration(Ctx& ctx, OpT& A, Precond<cdouble>* M, const d
             es.launches += rec->dots(b, grid, s);
             es.launches += rec->combine(x, 1.0, false, grid, s);
             A.apply(x, pcg.q(), nullptr, pcg.ws(), s);
-            pcg.launch_residual(b, Pcg<cdouble>::recurrence_tol2(tol), maxit, 0);
+            pcg.launch_residual(b, Pcg<cdouble>::recurrence_tol2(tol_eff), maxit, 0);
             if (add) MK_CUDA(cudaMemcpyAsync(slot, x, sizeof(cdouble) * n, cudaMemcpyDeviceToDevice, s));
             es.launches += 1 + A.launches_per_apply();
         } else {
             A.apply(u, pcg.q(), nullptr, pcg.ws(), s);
             k_dot_uq<<<grid, kThreads, 0, s>>>(n, u, pcg.q(), pcg.state(), pcg.ws());
-            k_warm_start<<<grid, kThreads, 0, s>>>(n, u, b, pcg.q(), x, pcg.r(), pcg.state(), pcg.ws(), Pcg<cdouble>::recurrence_tol2(tol), maxit);
+            k_warm_start<<<grid, kThreads, 0, s>>>(n, u, b, pcg.q(), x, pcg.r(), pcg.state(), pcg.ws(), Pcg<cdouble>::recurrence_tol2(tol_eff), maxit);
             if (add) MK_CUDA(cudaMemsetAsync(slot, 0, sizeof(cdouble) * n, s));  // first increment = the solution itself
             es.launches += 2 + A.launches_per_apply();
         }
         MK_CHECK_LAUNCH();
-        SolveStats ss = pcg.solve(b, x, tol, maxit, true, 16, use_graph, hint);
+        SolveStats ss = pcg.solve(b, x, tol_eff, maxit, true, 16, use_graph, hint);
         hint = ss.iterations + 1;
+        // fp64 floor (eps * cond(L) above the requested residual, meshes beyond ~4M vertices): the solve stalled after its restarts and says
+        // so (status 1). The following outer steps solve with the same operator and an ever more similar right-hand side, so they would
+        // stall at the same residual after the same wasted restarts: they are asked for what is attainable instead. The step is still
+        // reported as MK_ERR_NOT_CONVERGED with the achieved residual in relres_max.
+        if (ss.status == 1 && ss.relres > tol && ss.relres < 100 * tol) tol_eff = std::max(tol_eff, 1.05 * ss.relres);
         if (getenv("MK_VERBOSE")) fprintf(stderr, "[mk] inverse iteration %d: %d inner iterations (restarts %d), relres %.2e, iteration batches %.3f ms\n", it, ss.iterations, ss.restarts, ss.relres, ss.iter_ms);
         if (add) {
             // new basis vector: e = x - x0, L-orthogonalised against the others (it already is, up to the solve tolerance),
@@ -601,6 +607,10 @@ inline EigStats inverse_iteration(Ctx& ctx, OpT& A, Precond<cdouble>* M, const d
                 es.launches += A.launches_per_apply();
             }
             k_dot_uq<<<grid, kThreads, 0, s>>>(n, slot, pcg.q(), pcg.state(), pcg.ws());
+            if (getenv("MK_VERBOSE") && atoi(getenv("MK_VERBOSE")) >= 2) {
+                pcg.fetch_state();
+                fprintf(stderr, "[mk]   recycle slot %d: increment energy <e, L e> = %.3e\n", rec->count, pcg.host_state().pq);
+            }
             k_scale_energy<<<grid, kThreads, 0, s>>>(n, slot, pcg.state(), 0.0);
             es.launches += 2;
             rec->count++;

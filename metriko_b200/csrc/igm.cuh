@@ -116,7 +116,7 @@ struct ConstraintProjector : Projector<double> {
 //     z = M^{-1} r - W (Q W)^{-1} Q M^{-1} r,      W = M^{-1} Q^T  (n x k, one V-cycle per added constraint row),
 // so that Q z = 0 and the preconditioned operator on the feasible subspace is as well conditioned as M^{-1} A is on the whole space.
 // CPU mirror (tests/tools/mirror_rounding.py, 65k vertices, Poisson + 16 re-solves): 985 -> 693 iterations, with typed aggregation 1179 -> 580.
-constexpr int kCprecMax = 32;  // constraints beyond this many are left to the projector alone
+constexpr int kCprecMax = 64;  // constraints beyond this many are left to the projector alone (each column costs 4 n bytes per application)
 
 // y = (Q W)^{-1} Q z_S: one CTA (Q is k x m over the support S, Sinv is k x k with leading dimension ld)
 static __global__ void __launch_bounds__(kThreads) k_cprec_coef(int k, int m, const int* __restrict__ S, const double* __restrict__ Q,
@@ -143,8 +143,9 @@ static __global__ void __launch_bounds__(kThreads) k_cprec_coef(int k, int m, co
     }
 }
 
-// z -= sum_j y_j W_j (W column-major n x k)
-static __global__ void __launch_bounds__(kThreads) k_cprec_axpy(int n, int k, const double* __restrict__ W, const double* __restrict__ y,
+// z -= sum_j y_j W_j (W column-major n x k, stored in fp32: it is M^{-1} Q^T with the fp32 cycle's accuracy anyway, and (Q W)^{-1} is formed
+// from the STORED values, so Q z = 0 holds for what is subtracted; half the bytes of the one streaming kernel whose cost grows with k)
+static __global__ void __launch_bounds__(kThreads) k_cprec_axpy(int n, int k, const float* __restrict__ W, const double* __restrict__ y,
                                                         double* __restrict__ z, const PcgState* st) {
     __shared__ double c[kCprecMax];
     if (st && st->done) return;
@@ -153,9 +154,17 @@ static __global__ void __launch_bounds__(kThreads) k_cprec_axpy(int n, int k, co
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         double a = z[i];
 #pragma unroll 4
-        for (int j = 0; j < k; j++) a -= c[j] * ld_ro(W + (size_t)j * n + i);
+        for (int j = 0; j < k; j++) a -= c[j] * (double)__ldg(W + (size_t)j * n + i);
         z[i] = a;
     }
+}
+
+static __global__ void __launch_bounds__(kThreads) k_narrow_column(int n, const double* __restrict__ v, float* __restrict__ w) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) w[i] = (float)v[i];
+}
+static __global__ void k_gather_f32(int m, const int* __restrict__ S, const float* __restrict__ v, double* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) out[i] = (double)v[S[i]];
 }
 
 // v[S[i]] = q[i] (v zeroed before)
@@ -168,7 +177,8 @@ struct ConstraintPrecond : Precond<double> {
     Precond<double>* inner = nullptr;
     ConstraintProjector* proj = nullptr;
     int n = 0, k = 0;
-    DevBuf<double> W, Sinv, y, qfull, wS;
+    DevBuf<float> W;
+    DevBuf<double> Sinv, y, qfull, wcol, wS;
     DevBuf<PcgState> unit;                // rr = 1, done = 0: solver state for V-cycle applications outside a solve
     std::vector<std::vector<double>> WS;  // host copies of W_j restricted to the support
     long setup_launches = 0;
@@ -179,6 +189,7 @@ struct ConstraintPrecond : Precond<double> {
         Sinv.alloc((size_t)kCprecMax * kCprecMax);
         y.alloc(kCprecMax);
         qfull.alloc(n);
+        wcol.alloc(n);
         wS.alloc(std::max(proj->m, 1));
         unit.alloc(1);
         PcgState h;
@@ -197,13 +208,14 @@ struct ConstraintPrecond : Precond<double> {
         if (j != k || j >= kCprecMax) return;  // beyond the capacity: the projector alone handles the row
         qfull.zero(s);
         k_scatter<<<(m + 127) / 128, 128, 0, s>>>(m, proj->S.p, proj->Q.p + (size_t)j * m, qfull.p);
-        inner->apply(qfull.p, W.p + (size_t)j * n, unit.p, s);
-        k_gather<<<(m + 127) / 128, 128, 0, s>>>(m, proj->S.p, W.p + (size_t)j * n, wS.p);
+        inner->apply(qfull.p, wcol.p, unit.p, s);
+        k_narrow_column<<<stream_grid(n), kThreads, 0, s>>>(n, wcol.p, W.p + (size_t)j * n);
+        k_gather_f32<<<(m + 127) / 128, 128, 0, s>>>(m, proj->S.p, W.p + (size_t)j * n, wS.p);
         MK_CHECK_LAUNCH();
         WS.emplace_back(m);
         wS.download(WS.back().data(), m, s);
         MK_CUDA(cudaStreamSynchronize(s));
-        setup_launches += inner->launches_per_apply() + 2;
+        setup_launches += inner->launches_per_apply() + 3;
         const int kk = j + 1;
         std::vector<double> A((size_t)kk * kk), I((size_t)kk * kk, 0.0);
         for (int a = 0; a < kk; a++)

@@ -40,11 +40,14 @@ else:
     prob = api.IgmProblem(ctx, inp["X2F"], inp["UFull"], inp["F2"], inp["length"])
     prob.poisson(inp["fixedIdcs"], inp["fixedVals"])
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
-        prob.poisson(inp["fixedIdcs"], inp["fixedVals"])
+        if what == "igm_round":  # the whole rounding loop (Poisson + every re-solve)
+            prob.round(inp["fixedIdcs"], inp["fixedVals"], inp["singularIdcs"], inp["integerIdcs"], True, False)
+        else:
+            prob.poisson(inp["fixedIdcs"], inp["fixedVals"])
         torch.cuda.synchronize()
 path = os.path.join(ROOT, "gpurun_out", f"trace_{what}.json")
 prof.export_chrome_trace(path)
-ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") == "kernel"]
+ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
 ev.sort(key=lambda e: e["ts"])
 t0 = ev[0]["ts"] if ev else 0
 with open(os.path.join(ROOT, "gpurun_out", f"trace_{what}.csv"), "w", newline="") as fh:

@@ -165,3 +165,18 @@ def test_matching_and_singularities_on_device(ctx, ico4, matching):
     assert np.abs(eff - s.get("effort")).max() < 1e-9
     assert sing.sum() == 4 * s.dims["euler"]
     F.close()
+
+
+def test_second_solve_on_the_same_handle(ctx, ico4):
+    """A handle solved with ONE outer step and then with 50 must behave like a fresh handle solved with 50: the recycle space's coefficient
+    buffer once kept the size of the first call, and from the 33rd outer step on (the first coefficient beyond its 512-byte block) the
+    Galerkin start was garbage -- twice the inner iterations, found in a CUPTI trace of the 1M-vertex solve."""
+    nF = ico4.dims["nF"]
+    u0 = oracle.random_u0(nF, 3)
+    fresh = _mk(ctx, ico4)
+    z_ref = fresh.solveSmallestEig(u0, 50)
+    F = _mk(ctx, ico4)
+    F.solveSmallestEig(u0, 1)
+    z = F.solveSmallestEig(u0, 50)
+    assert F.stats["inner_iterations"] <= fresh.stats["inner_iterations"] + 5
+    assert field_angle_error(z, z_ref, 4).max() < 1e-7

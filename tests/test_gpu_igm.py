@@ -97,6 +97,36 @@ def test_cholesky_wrapper_seam(ctx):
     assert e.value.status in (-4, -3)
 
 
+def test_cholesky_wrapper_on_the_reference_penalty_system(ctx):
+    """B2 on the matrix LMSolver really factorises in the rounding loop (lm.h:184-189): dampJ^T dampJ with the 1e10 penalty rows of the fixed dofs
+    (ir_loop.h:102-124), cond ~ 1e14. PCG reaches the residual tolerance there, but a residual cannot bound the error at that conditioning
+    (5 % off the LU direction with multigrid, 70 % without): the solve must say so (MK_ERR_NOT_CONVERGED, x still written) instead of returning
+    a plausible-looking direction. The rounding loop itself goes through seam B4, which eliminates the fixed dofs exactly."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("b2probe", os.path.join(os.path.dirname(__file__), "tools", "b2_penalty_probe.py"))
+    probe = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(probe)
+    J, E = probe.si_system(load_golden("torus_24x16"), 6)
+    A = (J.T @ J).tocsc()
+    rhs = -(J.T @ E)
+    assert A.diagonal().max() / A.diagonal().min() > 1e9
+    w = api.CholeskyWrapper(ctx, precond=1)
+    assert w.factorize(A)
+    with pytest.raises(api.MkError) as e:
+        w.solve(rhs)
+    assert e.value.status == -3 and "penalty" in str(e.value)
+    assert w.stats["relres_max"] <= 1.001e-10          # the residual criterion itself was met: that is exactly the trap
+    # the same operator WITHOUT the penalty rows is what B2 is for
+    X = J[: J.shape[0] - 6 - A.shape[0]]
+    A2 = (X.T @ X + 1e-4 * sp.identity(A.shape[0])).tocsc()
+    w2 = api.CholeskyWrapper(ctx, precond=1)
+    assert w2.factorize(A2)
+    x2 = w2.solve(rhs)
+    x2_ref = spla.spsolve(A2, rhs)
+    assert np.abs(x2 - x2_ref).max() <= 1e-6 * np.abs(x2_ref).max()
+
+
 def test_full_size_rounding_properties(ctx):
     """Large case (octahedron x7, 131k faces): no oracle run; reference self-checks instead (post_checking,
     orientation, seamless integer transitions) plus solver-configuration independence of the integers."""
