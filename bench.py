@@ -51,7 +51,8 @@ FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only whe
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of k_spmv_face<false> from the committed `ncu --set full` capture
 # (profiles/ncu_full_spmv_kernels_r01b.csv: 159.5 MB read + 19.8 MB written), keyed by the face count it was taken at
 NCU_TRAFFIC_BYTES = {2097152: 179.3e6}
-NCU_TRAFFIC_SOURCE = "profiles/ncu_full_spmv_kernels_r01b.csv (ncu --set full, per launch)"
+NCU_TRAFFIC_SOURCE = ("profiles/ncu_full_spmv_kernels_r01b.csv (ncu --set full, per launch, k_spmv_face<false>: 159.5 MB read + 19.8 MB written); re-captured in round 2 on its "
+                      "fused-dot twin k_spmv_face<true> (same loads and stores): 159.5 + 19.2 MB, profiles/ncu_full_kernels_r02.csv")
 REFERENCE_BUDGET_S = 240.0   # the reference arm sizes its sample so that all K + W steps end within this
 # seconds per step of the reference arm (oracle, ni_mode="lm", every factorisation the reference performs) measured on this pool's
 # hosts, by octahedron subdivision level; only used to PICK the sample level, the run is timed live
@@ -438,11 +439,11 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         prob.poisson(inp["fixedIdcs"], inp["fixedVals"])   # one solve so that the hierarchy's work buffers exist
         ih = prob.hierarchy()
         npr = A.nnz / A.shape[0]
-        # per row (real): fp64 SELL SpMV + dot (nnz 12 + 4 + x 8 + y 8) | x, r update (p 8, q 8, x 16, r 16) | hand-over (r 8, dinv 4, b 4, d0 4) | fp32 SELL step
-        # (nnz 8 + 4 + v 4, b 4, r 4) | restrict 4 | prolong 8 | fp32 SELL residual + last (nnz 8 + 4 + x 4, b 4, dinv 4, xo 4) | hand-back (4 + 8) |
-        # constraint preconditioner z -= W y (z 16 + 8 k, k ~ 7 on average) | <r,z> (16) | p update (8 + 16)
-        ib = iteration_bytes(ih, {"spmv_dot": npr * 12 + 20, "update_xr": 48, "handover": 20, "cheb_step_first": npr * 8 + 16, "restrict": 4, "prolong": 8,
-                                  "resid_last": npr * 8 + 20, "handback": 12, "cprec_axpy": 16 + 8 * 7, "dot_rz": 16, "update_p": 24}, real=True)
+        # per row (real): fp64 SELL SpMV + dot (nnz 12 + 4 + x 8 + y 8) | x, r update fused with the hand-over (p 8, q 8, x 16, r 16, dinv 4, b 4, d0 4) |
+        # fp32 SELL step (nnz 8 + 4 + v 4, b 4, r 4) | restrict 4 | prolong 8 | fp32 SELL residual + last (nnz 8 + 4 + x 4, b 4, dinv 4, xo 4) |
+        # end of the constraint preconditioner fused with the hand-back and <r,z> (z_lo 4, W 4 k in fp32 with k ~ 7 on average, r 8, z 8) | p update (8 + 16)
+        ib = iteration_bytes(ih, {"spmv_dot": npr * 12 + 20, "update_xr_handover": 60, "cheb_step_first": npr * 8 + 16, "restrict": 4, "prolong": 8,
+                                  "resid_last": npr * 8 + 20, "cprec_finish": 20 + 4 * 7, "update_p": 24}, real=True)
         us_it = stage["igm_solve_ms"] * 1e3 / max(1, stage["igm_inner"])
         roofline["iteration"]["igm"] = {"hierarchy_rows_nnzA_nnzP": ih, **ib, "us_per_iteration_incl_rounding_loop": us_it,
                                         "achieved": ib["total_bytes"] / (us_it * 1e-6) / 1e9, "frac": ib["total_bytes"] / (us_it * 1e-6) / 1e9 / peak,

@@ -967,6 +967,8 @@ struct MixedPrecond : Precond<T> {
         k_update_p_lo<T, Tlo><<<stream_grid(n_), kThreads, 0, s>>>(n_, p, zo_lo.p, st);
     }
     int launches_fused() const override { return 2 + lo->launches_from_level(0); }
+    void cycle_only(PcgState* st, cudaStream_t s) override { cycle(nullptr, st, ReduceWs{nullptr, nullptr}, s); }
+    const void* lo_result() const override { return zo_lo.p; }
 };
 
 // ---- live timing of the cycle, level by level (bench.py / profiles: where an iteration's time goes, measured warm and back to back as

@@ -837,7 +837,8 @@ struct IgmRun {
         return acc / kPenalty;
     }
     // x_1 of the last re-solve (see xS1): particular part x_p = Q^T y on the support, homogeneous part w from the projected system
-    // P A P w = -P A x_p (same operator, projector and preconditioner as the re-solve; relative tolerance 1e-7: the term is divided by 1e10)
+    // P A P w = -P A x_p (same operator, projector and preconditioner as the re-solve; relative tolerance 1e-5: the term is divided by 1e10
+    // and decides gaps of ~1e-8 between values it shifts by ~1e-6)
     bool compute_x1(CsrOp<double>* op) {
         const int m = proj.m, k = (int)slack_y.size();
         if (k == 0 || m == 0 || k != (int)cs.Q.size() || applied != cs.Q.size()) return false;  // the constraint set moved on since the last re-solve
@@ -853,7 +854,7 @@ struct IgmRun {
         x1_dev.zero(s);
         MK_CHECK_LAUNCH();
         g->pcg->bind(op, use_cprec ? (Precond<double>*)&cprec : g->precond(), &proj);
-        SolveStats ss = g->pcg->solve(b1_dev.p, x1_dev.p, 1e-7, g->o.max_iter, false, 16, g->o.use_graph != 0);
+        SolveStats ss = g->pcg->solve(b1_dev.p, x1_dev.p, 1e-5, g->o.max_iter, false, 16, g->o.use_graph != 0);
         st.inner_iterations += ss.iterations;
         st.kernel_launches += ss.launches + 4;
         if (ss.status == 2) return false;

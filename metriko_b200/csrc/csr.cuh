@@ -149,7 +149,9 @@ inline void build_sell(DeviceCsr<T>& A, cudaStream_t s) {
     scan_lengths(kLongRow, tot, nl);
     A.padding = A.nnz ? (double)tot / (double)A.nnz : 1.0;  // long rows count as stored 0 / true len: only makes SELL look better
     const double mean = (double)A.nnz / rows;
-    if (mean > kRowModeMean || ((A.padding > kMaxSellPadding || rows <= kRowModeSmallRows) && mean >= kRowModeMinMean)) {
+    static const int row_mode_below = [] { const char* e = getenv("MK_ROWMODE_BELOW"); return e ? atoi(e) : 0; }();  // experiment knob
+    if (mean > kRowModeMean || ((A.padding > kMaxSellPadding || rows <= kRowModeSmallRows) && mean >= kRowModeMinMean) ||
+        (rows <= row_mode_below && mean >= kRowModeMinMean)) {
         A.row_mode = true;
         A.row_lanes = mean <= 6 ? 4 : (mean <= 12 ? 8 : (mean <= 24 ? 16 : 32));
         const double pad = A.padding;

@@ -490,6 +490,75 @@ static __global__ void __launch_bounds__(kThreads) k_multi_axpy(int n, int j0, i
     }
 }
 
+// The two projections an outer step needs, in ONE pass over the basis each (the basis is the traffic: 4 passes x up to 50 vectors per outer
+// step were 44 of the 183 ms of a 1M-vertex field solve):
+//   k_multi_dot2 : c1[j] = <E_j, v1>, c2[j] = <E_j, v2>          (re-orthogonalisation of the new increment; start of the NEXT solve)
+//   k_multi_axpy2: y1 -= sum_j c1[j] E_j ; y2 (+)= sum_j c2[j] E_j
+static __global__ void __launch_bounds__(kThreads) k_multi_dot2(int n, int j0, int cnt, const cdouble* __restrict__ E, const cdouble* __restrict__ v1,
+                                                         const cdouble* __restrict__ v2, cdouble* __restrict__ c1, cdouble* __restrict__ c2, ReduceWs ws) {
+    __shared__ double red[32];
+    double acc[4 * kRecycleChunk];
+#pragma unroll
+    for (int j = 0; j < 4 * kRecycleChunk; j++) acc[j] = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const cdouble a = ldc_nc(v1 + i), b = ldc_nc(v2 + i);
+#pragma unroll
+        for (int j = 0; j < kRecycleChunk; j++)
+            if (j < cnt) {
+                const cdouble e = ldc_nc(E + (size_t)(j0 + j) * n + i);
+                acc[4 * j] += e.x * a.x + e.y * a.y;
+                acc[4 * j + 1] += e.x * a.y - e.y * a.x;
+                acc[4 * j + 2] += e.x * b.x + e.y * b.y;
+                acc[4 * j + 3] += e.x * b.y - e.y * b.x;
+            }
+    }
+    grid_reduce<4 * kRecycleChunk>(acc, ws.partials, ws.ticket, red, [&](const double* s) {
+        for (int j = 0; j < cnt; j++) {
+            c1[j0 + j] = make_c(s[4 * j], s[4 * j + 1]);
+            c2[j0 + j] = make_c(s[4 * j + 2], s[4 * j + 3]);
+        }
+    });
+}
+
+static __global__ void __launch_bounds__(kThreads) k_multi_axpy2(int n, int j0, int cnt, const cdouble* __restrict__ E, const cdouble* __restrict__ c1,
+                                                          const cdouble* __restrict__ c2, cdouble* __restrict__ y1, cdouble* __restrict__ y2,
+                                                          int accumulate2) {
+    __shared__ cdouble a1[kRecycleChunk], a2[kRecycleChunk];
+    if (threadIdx.x < cnt) { a1[threadIdx.x] = c1[j0 + threadIdx.x]; a2[threadIdx.x] = c2[j0 + threadIdx.x]; }
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        cdouble u = ldc(y1 + i);
+        cdouble w = accumulate2 ? ldc(y2 + i) : make_c(0.0, 0.0);
+#pragma unroll
+        for (int j = 0; j < kRecycleChunk; j++)
+            if (j < cnt) {
+                const cdouble e = ldc_nc(E + (size_t)(j0 + j) * n + i);
+                u = ST<cdouble>::fma_(make_c(-a1[j].x, -a1[j].y), e, u);
+                w = ST<cdouble>::fma_(a2[j], e, w);
+            }
+        stc(y1 + i, u);
+        stc(y2 + i, w);
+    }
+}
+
+// c = <e, v> (complex, conj on e) into coef[slot]; then (second kernel) x += coef[slot] e
+static __global__ void __launch_bounds__(kThreads) k_cdot_slot(int n, const cdouble* __restrict__ e, const cdouble* __restrict__ v, cdouble* __restrict__ coef,
+                                                        int slot, ReduceWs ws) {
+    __shared__ double red[32];
+    double acc[2] = {0.0, 0.0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const cdouble a = ldc_nc(e + i), b = ldc_nc(v + i);
+        acc[0] += a.x * b.x + a.y * b.y;
+        acc[1] += a.x * b.y - a.y * b.x;
+    }
+    grid_reduce<2>(acc, ws.partials, ws.ticket, red, [&](const double* s) { coef[slot] = make_c(s[0], s[1]); });
+}
+static __global__ void __launch_bounds__(kThreads) k_caxpy_slot(int n, const cdouble* __restrict__ e, const cdouble* __restrict__ coef, int slot,
+                                                         cdouble* __restrict__ x) {
+    const cdouble c = coef[slot];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) stc(x + i, ST<cdouble>::fma_(c, ldc_nc(e + i), ldc(x + i)));
+}
+
 // e = x - e (the slot holds the start vector x0 on entry)
 static __global__ void __launch_bounds__(kThreads) k_increment(int n, const cdouble* __restrict__ x, cdouble* __restrict__ e) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) stc(e + i, ldc_nc(x + i) - ldc(e + i));
@@ -507,15 +576,15 @@ static __global__ void __launch_bounds__(kThreads) k_scale_energy(int n, cdouble
 
 struct RecycleSpace {
     int n = 0, cap = 0, count = 0;  // `count` of `cap` slots filled
-    DevBuf<cdouble> E, coef;
+    DevBuf<cdouble> E, coef, coef2;
     DevBuf<double> partials;
     DevBuf<unsigned int> ticket;
     void init(int n_, int cap_, cudaStream_t s) {
         n = n_; cap = cap_; count = 0;
         if (cap <= 0) return;
         if (E.n != (size_t)n * cap) E.alloc((size_t)n * cap);
-        if (coef.n < (size_t)cap) coef.alloc(cap);  // (a handle may be solved again with more outer steps: the coefficients must follow)
-        if (!partials.p) { partials.alloc((size_t)kMaxPartials * 2 * kRecycleChunk); ticket.alloc(1); ticket.zero(s); }
+        if (coef.n < (size_t)cap) { coef.alloc(cap); coef2.alloc(cap); }  // (a handle may be solved again with more outer steps: the coefficients must follow)
+        if (!partials.p) { partials.alloc((size_t)kMaxPartials * 4 * kRecycleChunk); ticket.alloc(1); ticket.zero(s); }
     }
     ReduceWs ws() { return ReduceWs{partials.p, ticket.p}; }
     int valid() const { return count < cap ? count : cap; }
@@ -524,6 +593,20 @@ struct RecycleSpace {
         int l = 0;
         for (int j0 = 0; j0 < valid(); j0 += kRecycleChunk, l++)
             k_multi_dot<<<grid, kThreads, 0, s>>>(n, j0, std::min(kRecycleChunk, valid() - j0), E.p, v, coef.p, ws());
+        return l;
+    }
+    // coef = E^H v1, coef2 = E^H v2 over the filled slots, one pass
+    int dots2(const cdouble* v1, const cdouble* v2, int grid, cudaStream_t s) {
+        int l = 0;
+        for (int j0 = 0; j0 < valid(); j0 += kRecycleChunk, l++)
+            k_multi_dot2<<<grid, kThreads, 0, s>>>(n, j0, std::min(kRecycleChunk, valid() - j0), E.p, v1, v2, coef.p, coef2.p, ws());
+        return l;
+    }
+    // y1 -= E coef ; y2 = E coef2 (y2 overwritten), one pass
+    int combine2(cdouble* y1, cdouble* y2, int grid, cudaStream_t s) {
+        int l = 0;
+        for (int j0 = 0; j0 < valid(); j0 += kRecycleChunk, l++)
+            k_multi_axpy2<<<grid, kThreads, 0, s>>>(n, j0, std::min(kRecycleChunk, valid() - j0), E.p, coef.p, coef2.p, y1, y2, j0 > 0 ? 1 : 0);
         return l;
     }
     int combine(cdouble* x, double sign, bool accumulate, int grid, cudaStream_t s) {
@@ -560,16 +643,24 @@ inline EigStats inverse_iteration(Ctx& ctx, OpT& A, Precond<cdouble>* M, const d
     const int grid = pcg.grid();
     int hint = 0;
     double tol_eff = tol;
+    // the multi-vector reductions end with 16 / 32 CTA-wide sums per CTA: few, long CTAs (each thread ~25 elements at 1M vertices)
+    const int gdot = std::min(grid, 4 * kSMs);
+    const bool fuse_passes = !(getenv("MK_RECYCLE_FUSED") && std::strcmp(getenv("MK_RECYCLE_FUSED"), "0") == 0);
+    bool x0_ready = false;  // b and x already hold the next right-hand side and its Galerkin start (prepared at the end of the previous step)
     for (int it = 0; it < n_iter; it++) {
         NvtxRange nvtx_("inverse_iteration_step");
         const bool recycle = rec && rec->cap > 0;
-        const bool add = recycle && rec->count < rec->cap;  // once the space is full it is frozen (late increments are ~0 anyway)
+        // once the space is full it is frozen (late increments are ~0 anyway); the last step's increment would never be used
+        const bool add = recycle && rec->count < rec->cap && it + 1 < n_iter;
         cdouble* slot = add ? rec->E.p + (size_t)rec->count * n : nullptr;
-        k_mass_rhs<<<grid, kThreads, 0, s>>>(n, mass, u, b, pcg.state(), pcg.ws());
-        if (recycle && rec->valid() > 0) {
-            // x0 = sum_j (e_j^H b) e_j ; r = b - L x0
-            es.launches += rec->dots(b, grid, s);
-            es.launches += rec->combine(x, 1.0, false, grid, s);
+        if (!x0_ready) k_mass_rhs<<<grid, kThreads, 0, s>>>(n, mass, u, b, pcg.state(), pcg.ws());
+        if (x0_ready || (recycle && rec->valid() > 0)) {
+            if (!x0_ready) {
+                // x0 = sum_j (e_j^H b) e_j
+                es.launches += rec->dots(b, gdot, s);
+                es.launches += rec->combine(x, 1.0, false, grid, s);
+            }
+            // r = b - L x0
             A.apply(x, pcg.q(), nullptr, pcg.ws(), s);
             pcg.launch_residual(b, Pcg<cdouble>::recurrence_tol2(tol_eff), maxit, 0);
             if (add) MK_CUDA(cudaMemcpyAsync(slot, x, sizeof(cdouble) * n, cudaMemcpyDeviceToDevice, s));
@@ -581,6 +672,7 @@ inline EigStats inverse_iteration(Ctx& ctx, OpT& A, Precond<cdouble>* M, const d
             if (add) MK_CUDA(cudaMemsetAsync(slot, 0, sizeof(cdouble) * n, s));  // first increment = the solution itself
             es.launches += 2 + A.launches_per_apply();
         }
+        x0_ready = false;
         MK_CHECK_LAUNCH();
         SolveStats ss = pcg.solve(b, x, tol_eff, maxit, true, 16, use_graph, hint);
         hint = ss.iterations + 1;
@@ -590,6 +682,7 @@ inline EigStats inverse_iteration(Ctx& ctx, OpT& A, Precond<cdouble>* M, const d
         // reported as MK_ERR_NOT_CONVERGED with the achieved residual in relres_max.
         if (ss.status == 1 && ss.relres > tol && ss.relres < 100 * tol) tol_eff = std::max(tol_eff, 1.05 * ss.relres);
         if (getenv("MK_VERBOSE")) fprintf(stderr, "[mk] inverse iteration %d: %d inner iterations (restarts %d), relres %.2e, iteration batches %.3f ms\n", it, ss.iterations, ss.restarts, ss.relres, ss.iter_ms);
+        bool normalised = false;
         if (add) {
             // new basis vector: e = x - x0, L-orthogonalised against the others (it already is, up to the solve tolerance),
             // normalised in the energy norm with an explicit L e so that the Galerkin relation stays exact to round-off
@@ -600,8 +693,20 @@ inline EigStats inverse_iteration(Ctx& ctx, OpT& A, Precond<cdouble>* M, const d
             // <e_j, L e> = <e_j, L x - b> is the residual of the solve just finished), but that residual is 1e-10 |b| while the late
             // increments are themselves tiny, so RELATIVE to |e|_L the new vector is far from orthogonal: without this pass the 1M-vertex
             // field solve needs 3,783 inner iterations instead of 1,017 (measured, round 2; MK_RECYCLE_REORTH=0 reproduces it).
-            if (recycle_reorthogonalise() && rec->valid() > 0) {
-                es.launches += rec->dots(pcg.q(), grid, s);
+            const bool reorth = recycle_reorthogonalise() && rec->valid() > 0;
+            if (reorth && fuse_passes) {
+                // The next solve's Galerkin start needs the same basis against the next right-hand side: both projections share ONE pass
+                // for the coefficients and ONE for the combinations. The next right-hand side first: u = x / |x|_M (sls.h:48-50), b = M u.
+                k_mnorm2<<<grid, kThreads, 0, s>>>(n, mass, x, pcg.state(), pcg.ws());
+                k_normalize_copy<<<grid, kThreads, 0, s>>>(n, x, u, pcg.state());
+                k_mass_rhs<<<grid, kThreads, 0, s>>>(n, mass, u, b, pcg.state(), pcg.ws());
+                normalised = true;
+                es.launches += rec->dots2(pcg.q(), b, gdot, s);      // coef = E^H (L e), coef2 = E^H b
+                es.launches += rec->combine2(slot, x, grid, s);      // e -= E coef ; x = E coef2 (u keeps the iterate)
+                A.apply(slot, pcg.q(), nullptr, pcg.ws(), s);
+                es.launches += 3 + A.launches_per_apply();
+            } else if (reorth) {
+                es.launches += rec->dots(pcg.q(), gdot, s);
                 es.launches += rec->combine(slot, -1.0, true, grid, s);
                 A.apply(slot, pcg.q(), nullptr, pcg.ws(), s);
                 es.launches += A.launches_per_apply();
@@ -613,10 +718,19 @@ inline EigStats inverse_iteration(Ctx& ctx, OpT& A, Precond<cdouble>* M, const d
             }
             k_scale_energy<<<grid, kThreads, 0, s>>>(n, slot, pcg.state(), 0.0);
             es.launches += 2;
+            if (normalised) {
+                // the new vector's own share of the start: x += <e, b> e
+                k_cdot_slot<<<gdot, kThreads, 0, s>>>(n, slot, b, rec->coef2.p, rec->count, rec->ws());
+                k_caxpy_slot<<<grid, kThreads, 0, s>>>(n, slot, rec->coef2.p, rec->count, x);
+                es.launches += 2;
+                x0_ready = true;
+            }
             rec->count++;
         }
-        k_mnorm2<<<grid, kThreads, 0, s>>>(n, mass, x, pcg.state(), pcg.ws());
-        k_normalize_copy<<<grid, kThreads, 0, s>>>(n, x, u, pcg.state());
+        if (!normalised) {
+            k_mnorm2<<<grid, kThreads, 0, s>>>(n, mass, x, pcg.state(), pcg.ws());
+            k_normalize_copy<<<grid, kThreads, 0, s>>>(n, x, u, pcg.state());
+        }
         MK_CHECK_LAUNCH();
         es.outer++;
         es.inner_total += ss.iterations;

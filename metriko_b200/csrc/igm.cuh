@@ -159,6 +159,80 @@ static __global__ void __launch_bounds__(kThreads) k_cprec_axpy(int n, int k, co
     }
 }
 
+// The same coefficients from the fp32 cycle output (z = zscale * z_lo is not formed yet): y = (Q W)^{-1} Q (zscale z_lo)_S
+static __global__ void __launch_bounds__(kThreads) k_cprec_coef_lo(int k, int m, const int* __restrict__ S, const double* __restrict__ Q,
+                                                           const double* __restrict__ Sinv, int ld, const float* __restrict__ zl,
+                                                           double* __restrict__ y, const PcgState* st) {
+    extern __shared__ double sm[];
+    if (st->done) return;
+    double* vS = sm;     // m
+    double* t = sm + m;  // k
+    const double zs = st->zscale;
+    for (int s = threadIdx.x; s < m; s += blockDim.x) vS[s] = zs * (double)zl[S[s]];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int j = wid; j < k; j += nw) {
+        double a = 0.0;
+        for (int s = lane; s < m; s += 32) a += Q[(size_t)j * m + s] * vS[s];
+        a = warp_sum(a);
+        if (lane == 0) t[j] = a;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        double a = 0.0;
+        for (int j = 0; j < k; j++) a += Sinv[(size_t)i * ld + j] * t[j];
+        y[i] = a;
+    }
+}
+
+// The end of the preconditioner fused with the PCG reduction: z = zscale z_lo - W y (fp64, written once), rho_new = <r, z>, beta = rho_new / rho.
+// Replaces the hand-back kernel, the streaming correction and k_dot_rz (6 + 32 + 10 us at 1M vertices) by one pass.
+static __global__ void __launch_bounds__(kThreads) k_cprec_finish(int n, int k, const float* __restrict__ W, const double* __restrict__ y,
+                                                          const float* __restrict__ zl, const double* __restrict__ r, double* __restrict__ z,
+                                                          PcgState* st, ReduceWs ws) {
+    __shared__ double c[kCprecMax];
+    __shared__ double red[32];
+    if (st->done) return;
+    if ((int)threadIdx.x < k) c[threadIdx.x] = y[threadIdx.x];
+    __syncthreads();
+    const double zs = st->zscale;
+    double acc = 0.0;
+    // two rows per thread: 8-byte loads from every column of W (n is even or the tail row is handled alone; the columns start n * 4 bytes apart,
+    // so pairs stay 8-byte aligned exactly when n is even), 8 columns in flight
+    const int n2 = (n & 1) ? 0 : n / 2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x) {
+        const float2 zz = __ldg(reinterpret_cast<const float2*>(zl) + i);
+        double a0 = zs * (double)zz.x, a1 = zs * (double)zz.y;
+        int j = 0;
+        for (; j + 8 <= k; j += 8) {
+            float2 w[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) w[u] = __ldg(reinterpret_cast<const float2*>(W + (size_t)(j + u) * n) + i);
+#pragma unroll
+            for (int u = 0; u < 8; u++) { a0 -= c[j + u] * (double)w[u].x; a1 -= c[j + u] * (double)w[u].y; }
+        }
+        for (; j < k; j++) {
+            const float2 w = __ldg(reinterpret_cast<const float2*>(W + (size_t)j * n) + i);
+            a0 -= c[j] * (double)w.x;
+            a1 -= c[j] * (double)w.y;
+        }
+        const double2 rr = __ldg(reinterpret_cast<const double2*>(r) + i);
+        reinterpret_cast<double2*>(z)[i] = make_double2(a0, a1);
+        acc += rr.x * a0 + rr.y * a1;
+    }
+    for (int i = 2 * n2 + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double a = zs * (double)__ldg(zl + i);
+        for (int j = 0; j < k; j++) a -= c[j] * (double)__ldg(W + (size_t)j * n + i);
+        z[i] = a;
+        acc += ld_ro(r + i) * a;
+    }
+    double v[1] = {acc};
+    grid_reduce<1>(v, ws.partials, ws.ticket, red, [&](const double* s) {
+        st->beta = s[0] / st->rho;
+        st->rho = s[0];
+    });
+}
+
 static __global__ void __launch_bounds__(kThreads) k_narrow_column(int n, const double* __restrict__ v, float* __restrict__ w) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) w[i] = (float)v[i];
 }
@@ -197,8 +271,10 @@ struct ConstraintPrecond : Precond<double> {
         h.rr = 1.0; h.rho = 1.0; h.bnorm2 = 1.0;
         unit.upload(&h, 1, s);
         if ((size_t)(proj->m + kCprecMax) * sizeof(double) > 200 * 1024) throw std::invalid_argument("constraint preconditioner: support too large (disable with MK_IGM_CPREC=0)");
-        if ((size_t)(proj->m + kCprecMax) * sizeof(double) > 48 * 1024)
+        if ((size_t)(proj->m + kCprecMax) * sizeof(double) > 48 * 1024) {
             MK_CUDA(cudaFuncSetAttribute(k_cprec_coef, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((proj->m + kCprecMax) * sizeof(double))));
+            MK_CUDA(cudaFuncSetAttribute(k_cprec_coef_lo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((proj->m + kCprecMax) * sizeof(double))));
+        }
         MK_CUDA(cudaStreamSynchronize(s));
     }
     void reset() { k = 0; WS.clear(); }
@@ -257,6 +333,20 @@ struct ConstraintPrecond : Precond<double> {
         MK_CHECK_LAUNCH();
     }
     int launches_per_apply() const override { return inner->launches_per_apply() + (k ? 2 : 0); }
+    // fused PCG body with a projector (solver.cuh): the inner mixed-precision cycle hands its fp32 output over to k_cprec_finish
+    bool fused_projected() const override { return inner->fused_pcg() && inner->lo_result() != nullptr; }
+    void update_xr_handover(int n_, double* x, double* r, const double* p, const double* q, PcgState* st, ReduceWs ws, cudaStream_t s) override {
+        inner->update_xr_handover(n_, x, r, p, q, st, ws, s);
+    }
+    void cycle_to_z(const double* r, double* z, PcgState* st, ReduceWs ws, cudaStream_t s) override {
+        inner->cycle_only(st, s);
+        const float* zl = static_cast<const float*>(inner->lo_result());
+        if (k > 0)
+            k_cprec_coef_lo<<<1, kThreads, (size_t)(proj->m + k) * sizeof(double), s>>>(k, proj->m, proj->S.p, proj->Q.p, Sinv.p, kCprecMax, zl, y.p, st);
+        k_cprec_finish<<<stream_grid(n), kThreads, 0, s>>>(n, k, W.p, y.p, zl, r, z, st, ws);
+        MK_CHECK_LAUNCH();
+    }
+    int launches_fused_projected() const override { return inner->launches_fused() - 1 + (k ? 2 : 1); }
 };
 
 // On by default (1M vertices, B200: IGM solve 594 -> 412 ms, 1347 -> 841 inner iterations, same integers, fullx within 1.5e-9;

@@ -328,6 +328,14 @@ struct Precond {
     //   p = z + beta p, z read from the cycle's own output
     virtual void update_p(int, T*, const PcgState*, cudaStream_t) {}
     virtual int launches_fused() const { return 0; }  // kernels of the three calls above
+    // Fused body for solves WITH a projector (the IGM re-solves): update_xr_handover as above, then cycle_to_z = the cycle on the handed-over
+    // residual with z written in fp64 and rho_new = <r, z>, beta finished in its last kernel (no stand-alone hand-back / dot kernel); the
+    // projector and p = z + beta p follow. The two hooks below let a wrapping preconditioner (igm.cuh ConstraintPrecond) finish the cycle itself.
+    virtual bool fused_projected() const { return false; }
+    virtual void cycle_to_z(const T*, T*, PcgState*, ReduceWs, cudaStream_t) {}
+    virtual int launches_fused_projected() const { return 0; }  // kernels of update_xr_handover + cycle_to_z
+    virtual void cycle_only(PcgState*, cudaStream_t) {}          // the cycle alone; result (fp32, scaled by 1 / zscale) at lo_result()
+    virtual const void* lo_result() const { return nullptr; }
 };
 
 // In-place projection onto the feasible subspace (IGM constraint elimination); null for unconstrained solves.
@@ -449,8 +457,10 @@ public:
     }
 
     bool fused() const { return M_ && !P_ && M_->fused_pcg(); }
+    bool fused_projected() const { return M_ && P_ && M_->fused_projected(); }
     int launches_per_iteration() const {
         if (fused()) return A_->launches_per_apply() + M_->launches_fused();
+        if (fused_projected()) return A_->launches_per_apply() + 2 + M_->launches_fused_projected() + 1;
         return A_->launches_per_apply() + (P_ ? (M_ ? 2 : 1) : 0) + 1 + (M_ ? M_->launches_per_apply() + 1 : 0) + 1;
     }
 
@@ -485,6 +495,14 @@ private:
             return;
         }
         if (P_) P_->apply(q_.p, st_.p, stream_);
+        if (fused_projected()) {
+            M_->update_xr_handover(n_, x, r_.p, p_.p, q_.p, st_.p, ws(), stream_);
+            M_->cycle_to_z(r_.p, z_.p, st_.p, ws(), stream_);
+            P_->apply(z_.p, st_.p, stream_);  // <r, P z> = <P r, z> = <r, z>: rho is not touched by cleaning z
+            k_update_p<T><<<grid_, kThreads, 0, stream_>>>(n_, p_.p, z_.p, st_.p);
+            MK_CHECK_LAUNCH();
+            return;
+        }
         if (M_) {
             k_update_xr<T, true><<<grid_, kThreads, 0, stream_>>>(n_, x, r_.p, p_.p, q_.p, st_.p, ws());
             // without a projector the preconditioner may finish <r, z> in its own last kernel

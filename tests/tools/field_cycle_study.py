@@ -48,7 +48,7 @@ M = oracle.galerkin_mass_matrix(fi["faceArea"])
 b = M @ oracle.random_u0(nF, 0)
 H = capi.amg_host_hierarchy(L)
 print("faces", nF, "levels", describe(H), flush=True)
-variants = [("V deg 1/2 (device default)", dict()), ("V deg 1/3", dict(degc=3)), ("V deg 2/2", dict(deg0=2)), ("W from level 1", dict(gamma_from=1)),
+variants = [("V deg 1/2 (device default)", dict()), ("V deg 1/1", dict(degc=1)), ("V deg 1/3", dict(degc=3)), ("V deg 2/2", dict(deg0=2)), ("W from level 1", dict(gamma_from=1)),
             ("W from level 2", dict(gamma_from=2)), ("W from 1, deg 1/1", dict(gamma_from=1, degc=1)), ("two-grid (exact level 1)", dict(exact_from=1)),
             ("three-grid (exact level 2)", dict(exact_from=2))]
 for name, kw in variants:
