@@ -271,7 +271,7 @@ static __global__ void __launch_bounds__(kThreads) k_rho_scale(int n, const T* _
 }
 
 template <class T>
-inline double estimate_rho_dev(const DeviceCsr<T>& A, const T* dinv, cudaStream_t s, int iters = 12) {
+inline double estimate_rho_dev(const DeviceCsr<T>& A, const T* dinv, cudaStream_t s, LinOp<T>* fast_op = nullptr, int iters = 12) {
     const int n = A.rows;
     DevBuf<T> v(n), w(n);
     DevBuf<double> out(2), partials((size_t)kMaxPartials * 4);
@@ -280,7 +280,9 @@ inline double estimate_rho_dev(const DeviceCsr<T>& A, const T* dinv, cudaStream_
     const int grid = stream_grid(n);
     k_rho_init<T><<<grid, kThreads, 0, s>>>(n, v.p);
     for (int it = 0; it < iters; it++) {
-        csr_matvec<T>(A, v.p, w.p, 1.0, s);
+        // level 0 behind the solver's own operator (face stencil / SELL): 32-45 us per product instead of ~350 for the set-up's plain CSR kernel
+        if (fast_op) fast_op->apply(v.p, w.p, nullptr, ReduceWs{partials.p, ticket.p}, s, false);
+        else csr_matvec<T>(A, v.p, w.p, 1.0, s);
         k_rho_norms<T><<<grid, kThreads, 0, s>>>(n, dinv, w.p, v.p, out.p, ReduceWs{partials.p, ticket.p});
         k_rho_scale<T><<<grid, kThreads, 0, s>>>(n, w.p, v.p, out.p);
     }
@@ -463,7 +465,7 @@ inline std::unique_ptr<AmgPrecond<T>> build_amg_device(cudaStream_t s, DeviceCsr
         DevBuf<double> dabs(n);
         k_diag_dinv<T><<<stream_grid((int64_t)n * 32), kThreads, 0, s>>>(n, A.ptr.p, A.col.p, A.val.p, n_dense ? dense.p : nullptr, dabs.p, L.dinv.p);
         MK_CHECK_LAUNCH();
-        const double rho = estimate_rho_dev<T>(A, L.dinv.p, s);
+        const double rho = estimate_rho_dev<T>(A, L.dinv.p, s, (l == 0 && fine_op && fine_op->applies()) ? fine_op : nullptr);
         L.lmax = 1.1 * rho;
         L.r.alloc(n); L.d.alloc(n); L.q.alloc(n);
         if (l > 0) { L.x.alloc(n); L.b.alloc(n); }

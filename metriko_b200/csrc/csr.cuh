@@ -149,9 +149,10 @@ inline void build_sell(DeviceCsr<T>& A, cudaStream_t s) {
     scan_lengths(kLongRow, tot, nl);
     A.padding = A.nnz ? (double)tot / (double)A.nnz : 1.0;  // long rows count as stored 0 / true len: only makes SELL look better
     const double mean = (double)A.nnz / rows;
-    static const int row_mode_below = [] { const char* e = getenv("MK_ROWMODE_BELOW"); return e ? atoi(e) : 0; }();  // experiment knob
-    if (mean > kRowModeMean || ((A.padding > kMaxSellPadding || rows <= kRowModeSmallRows) && mean >= kRowModeMinMean) ||
-        (rows <= row_mode_below && mean >= kRowModeMinMean)) {
+    // (lanes-per-row on the 387k-row level 1 of the field hierarchy, 10.8 entries per row, was measured and loses: the cycle from level 1
+    // downwards takes 197 instead of 129 us, profiles/cycle_probe_r02_z_*.json; so does batching the last 1-3 columns of a SELL row into one
+    // load group, 255 against 248 us per field cycle -- SELL with the 4-wide unrolled loop stays the layout of every regular operator)
+    if (mean > kRowModeMean || ((A.padding > kMaxSellPadding || rows <= kRowModeSmallRows) && mean >= kRowModeMinMean)) {
         A.row_mode = true;
         A.row_lanes = mean <= 6 ? 4 : (mean <= 12 ? 8 : (mean <= 24 ? 16 : 32));
         const double pad = A.padding;

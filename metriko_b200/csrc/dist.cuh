@@ -254,6 +254,7 @@ struct DistFaceOp {
 // ~20% of a V-cycle's work, which bounds the speed-up (Amdahl) -- distributing level 1 as well is the next step.
 struct NullOp : LinOp<cdouble> {
     void apply(const cdouble*, cdouble*, PcgState*, ReduceWs, cudaStream_t, bool) override { throw std::logic_error("NullOp applied"); }
+    bool applies() const override { return false; }
 };
 
 struct DistAmgPrecond : Precond<cdouble> {

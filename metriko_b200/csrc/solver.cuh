@@ -297,6 +297,7 @@ struct LinOp {
     // kernel finishes the fused reduction pq = <x, y>, alpha = rho / pq (the PCG step).
     virtual void apply(const T* x, T* y, PcgState* st, ReduceWs ws, cudaStream_t s, bool dot = true) = 0;
     virtual int launches_per_apply() const { return 1; }
+    virtual bool applies() const { return true; }  // false: a placeholder that only marks "level 0 lives elsewhere" (dist.cuh NullOp)
     // Chebyshev smoothing fused into the operator kernel (the multigrid V-cycle, amg.cuh; the epilogues are documented at SpmvMode, csr.cuh):
     //   cheb_step      : q = A d_in ; x (+)= d_in ; r -= q ; d_out = c1 d_in + c2 dinv .* r   (`first`: x = d_in, r = b - q; d_out may be null)
     //   cheb_resid     : r = b - A x ; d_out = inv_theta dinv .* r
