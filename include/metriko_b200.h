@@ -217,6 +217,8 @@ int mk_dfield_spmv_bench(mk_dfield* f, int reps, int overlap, double* ms_per_lau
  * across ranks). Collective: every rank calls with its rows. */
 int mk_dfield_pcg(mk_dfield* f, const double* b_local, const double* x0_local, const mk_solve_opts* opts, double* x_local, mk_stats* stats);
 int mk_dfield_solve(mk_dfield* f, const double* u0_local, int n_iter, const mk_solve_opts* opts, double* x_local, mk_stats* stats);
+/* mk_dfield_pcg with the owned rows of b and x already in device memory (x_dev: start vector in, solution out): no host <-> device copies. */
+int mk_dfield_pcg_dev(mk_dfield* f, const double* b_dev, double* x_dev, const mk_solve_opts* opts, mk_stats* stats);
 
 /* ---- multigrid set-up, exposed for tests. mk_amg_host_build is the host mirror (no device needed) of the device set-up the solvers
  * run: it builds the same smoothed-aggregation hierarchy for a Hermitian (is_complex = 1, interleaved values) or symmetric CSR

@@ -107,6 +107,7 @@ def lib() -> C.CDLL:
         L.mk_dfield_spmv.argtypes = [vp, vp, vp]
         L.mk_dfield_spmv_bench.argtypes = [vp, C.c_int, C.c_int, dp]
         L.mk_dfield_pcg.argtypes = [vp, vp, vp, C.POINTER(SolveOpts), vp, C.POINTER(Stats)]
+        L.mk_dfield_pcg_dev.argtypes = [vp, vp, vp, C.POINTER(SolveOpts), C.POINTER(Stats)]
         L.mk_dfield_solve.argtypes = [vp, vp, C.c_int, C.POINTER(SolveOpts), vp, C.POINTER(Stats)]
         L.mk_amg_host_build.argtypes = [C.c_int, vp, vp, vp, C.c_int, vp, C.POINTER(vp)]
         L.mk_amg_dev_build.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, C.POINTER(vp)]

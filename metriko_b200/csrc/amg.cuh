@@ -1109,6 +1109,45 @@ inline std::unique_ptr<MixedPrecond<T>> lower_precision(cudaStream_t s, std::uni
     return mp;
 }
 
+// fp32 copy of the levels >= `from` of an fp64 hierarchy as a hierarchy of its own (its level 0 = level `from`, a materialised CSR operator):
+// the replicated coarse part of the partitioned preconditioner (dist.cuh) runs the same fp32 cycle as the single-GPU solver.
+template <class T>
+inline std::unique_ptr<AmgPrecond<typename LowOf<T>::type>> lower_tail(cudaStream_t s, AmgPrecond<T>& hi, int from) {
+    using Tlo = typename LowOf<T>::type;
+    auto lo = std::make_unique<AmgPrecond<Tlo>>();
+    lo->prm = hi.prm;
+    lo->prm.cheb_degree = hi.prm.cheb_degree_coarse > 0 ? hi.prm.cheb_degree_coarse : hi.prm.cheb_degree;  // its level 0 is a coarse level
+    const int nl = (int)hi.lv.size();
+    lo->lv.resize(nl - from);
+    for (int l = from; l < nl; l++) {
+        AmgLevelDev<T>& H = hi.lv[l];
+        AmgLevelDev<Tlo>& L = lo->lv[l - from];
+        const int n = H.n;
+        L.n = n;
+        L.lmax = H.lmax;
+        L.x.alloc(n); L.b.alloc(n); L.xo.alloc(n);
+        lower_csr<T, Tlo>(H.A, L.A, s);
+        if (l + 1 < nl) {
+            lower_csr<T, Tlo>(H.P, L.P, s);
+            lower_csr<T, Tlo>(H.R, L.R, s);
+        }
+        L.dinv.alloc(n);
+        k_narrow_vector<T, Tlo><<<stream_grid(n), kThreads, 0, s>>>(n, H.dinv.p, L.dinv.p);
+        L.r.alloc(n); L.d.alloc(n); L.q.alloc(n);
+        MK_CHECK_LAUNCH();
+    }
+    lo->coarse_n = hi.coarse_n;
+    lo->coarse_dense = hi.coarse_dense;
+    if (hi.coarse_dense) {
+        const size_t m = hi.coarse_inv.n;
+        lo->coarse_inv.alloc(m);
+        k_narrow_vector<T, Tlo><<<stream_grid((int64_t)m), kThreads, 0, s>>>((int)m, hi.coarse_inv.p, lo->coarse_inv.p);
+        MK_CHECK_LAUNCH();
+    }
+    MK_CUDA(cudaStreamSynchronize(s));
+    return lo;
+}
+
 // Typed aggregation of the IGM hierarchy (u- and v-type dofs never share an aggregate). It resolves the two near-kernel vectors better
 // (Poisson solve 116 -> 100 iterations at 1M vertices), which only pays together with the constraint preconditioner (igm.cuh): under the
 // plain projected preconditioner every added rounding constraint then costs 10-20 extra iterations (2215 against 1537 in total), with

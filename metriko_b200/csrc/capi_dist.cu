@@ -183,6 +183,22 @@ int mk_dfield_set_global(mk_dfield* f, int nF, const int* nbr, const double* val
         L0.r.release(); L0.d.release(); L0.q.release(); L0.dinv.release();
         g->G->first_level = 1;   // level 0 runs distributed (DistAmgPrecond): no replicated work vectors of global length
         g->G->prepare(s);
+        if (precond_fp32()) {
+            // the replicated levels >= 1 in fp32 storage and arithmetic, like the single-GPU cycle (MK_PRECOND_FP32=0: the fp64 levels)
+            g->Glo = lower_tail<cdouble>(s, *g->G, 1);
+            g->Glo->prepare(s);
+            const int W = f->d->c.world;
+            const size_t padded = (size_t)((g->n1 + W - 1) / W) * W;   // reduce-scatter / all-gather want equal blocks
+            g->b1_lo.alloc(padded);
+            g->x1_lo.alloc(padded);
+            g->b1_lo.zero(s);
+            g->x1_lo.zero(s);
+            const char* e = getenv("MK_DIST_L1");
+            if (W > 1 && g->Glo->lv.size() >= 3 && !(e && std::strcmp(e, "0") == 0)) {
+                g->L1 = std::make_unique<DistLevel1>();
+                g->L1->build(&f->d->c, g->Glo->lv[0], g->Glo->lv[1].n, s);
+            }
+        }
         f->gamg = std::move(g);
     }
     MK_CUDA(cudaStreamSynchronize(s));
@@ -363,6 +379,40 @@ int mk_dfield_pcg(mk_dfield* f, const double* b_local, const double* x0_local, c
     else f->x_ext.zero(s);
     SolveStats ss = f->pcg->solve(f->op, M, f->b.p, f->x_ext.p, o.tol, o.max_iter, 8, 0);
     f->x_ext.download((cdouble*)x_local, n, s);
+    MK_CUDA(cudaStreamSynchronize(s));
+    auto t2 = std::chrono::steady_clock::now();
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        stats->outer_iterations = 1;
+        stats->inner_iterations = ss.iterations;
+        stats->inner_max = ss.iterations;
+        stats->relres_max = ss.relres;
+        stats->kernel_launches = ss.launches;
+        stats->setup_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+        stats->solve_ms = std::chrono::duration<double, std::milli>(t2 - t1).count();
+        stats->status = ss.status == 0 ? MK_OK : (ss.status == 2 ? MK_ERR_NOT_SPD : MK_ERR_NOT_CONVERGED);
+    }
+    rc = ss.status == 0 ? MK_OK : (ss.status == 2 ? MK_ERR_NOT_SPD : MK_ERR_NOT_CONVERGED);
+    MK_API_END_RC(f->d->ctx, rc)
+}
+
+int mk_dfield_pcg_dev(mk_dfield* f, const double* b_dev, double* x_dev, const mk_solve_opts* opts, mk_stats* stats) {
+    if (!f || !b_dev || !x_dev) return MK_ERR_ARG;
+    int rc = MK_OK;
+    MK_API_BEGIN(f->d->ctx)
+    MK_CUDA(cudaSetDevice(f->d->ctx->c.device));
+    cudaStream_t s = f->d->ctx->c.stream;
+    mk_solve_opts o;
+    if (opts) o = *opts; else mk_default_opts(&o);
+    auto t0 = std::chrono::steady_clock::now();
+    Precond<cdouble>* M = dfield_precond(f, o);
+    MK_CUDA(cudaStreamSynchronize(s));
+    auto t1 = std::chrono::steady_clock::now();
+    const int n = f->op.nloc;
+    MK_CUDA(cudaMemcpyAsync(f->b.p, b_dev, sizeof(cdouble) * n, cudaMemcpyDeviceToDevice, s));
+    MK_CUDA(cudaMemcpyAsync(f->x_ext.p, x_dev, sizeof(cdouble) * n, cudaMemcpyDeviceToDevice, s));
+    SolveStats ss = f->pcg->solve(f->op, M, f->b.p, f->x_ext.p, o.tol, o.max_iter, 8, 0);
+    MK_CUDA(cudaMemcpyAsync(x_dev, f->x_ext.p, sizeof(cdouble) * n, cudaMemcpyDeviceToDevice, s));
     MK_CUDA(cudaStreamSynchronize(s));
     auto t2 = std::chrono::steady_clock::now();
     if (stats) {

@@ -22,6 +22,8 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*ReduceScatter)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
@@ -44,6 +46,8 @@ struct NcclApi {
             api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
             api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
             api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+            api.ReduceScatter = (decltype(api.ReduceScatter))sym("ncclReduceScatter");
+            api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
             api.Send = (decltype(api.Send))sym("ncclSend");
             api.Recv = (decltype(api.Recv))sym("ncclRecv");
             api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
@@ -72,6 +76,9 @@ struct DistComm {
     }
     void allreduce_sum(double* buf, int n, cudaStream_t s) {
         if (world > 1) MK_NCCL(NcclApi::get().AllReduce(buf, buf, (size_t)n, ncclDouble, ncclSum, comm, s));
+    }
+    void allreduce_sum_f32(float* buf, int n, cudaStream_t s) {
+        if (world > 1) MK_NCCL(NcclApi::get().AllReduce(buf, buf, (size_t)n, ncclFloat, ncclSum, comm, s));
     }
 };
 
@@ -257,11 +264,224 @@ struct NullOp : LinOp<cdouble> {
     bool applies() const override { return false; }
 };
 
+// ---- level 1 of the global hierarchy, distributed (round 2) ----------------------------------------------------------------------------
+// The replicated coarse levels were the Amdahl limit of the partitioned solve (level 1 of the 8M-vertex hierarchy: 3.1 M rows, 33 M entries,
+// four fused smoother SpMVs per cycle on EVERY rank). Level 1 is now row-partitioned as well: rank r owns the contiguous index block
+// [r c, (r+1) c), c = ceil(n1 / W) (level-1 dofs are numbered in root-face order, so blocks are spatially compact), keeps its rows of A_1
+// with LOCAL column numbers [owned | halo] -- the same x_ext layout as level 0, so every fused smoother kernel of csr.cuh runs unchanged --
+// and exchanges the few thousand halo entries before each of the four SpMVs (NCCL send/recv, plan derived locally from the replicated
+// operator: every rank sees all rows, no set-up communication). The restricted residual arrives by reduce-scatter instead of all-reduce, the
+// correction leaves by all-gather (together the bytes of the all-reduce they replace); level 2 (1/13 of level 1) and below stay replicated.
+static __global__ void k_l1_mark_halo(int nown, int lo, int hi, const int* __restrict__ ptr, const int* __restrict__ col, int* __restrict__ flag) {
+    const int lane = threadIdx.x & 31;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= nown) return;
+    for (int k = ptr[i] + lane; k < ptr[i + 1]; k += 32) {
+        const int c = col[k];
+        if (c < lo || c >= hi) flag[c] = 1;  // racing writes of the same value
+    }
+}
+static __global__ void k_l1_renumber(int nown, int lo, int hi, const int* __restrict__ ptr, int* __restrict__ col, const int* __restrict__ pos) {
+    const int lane = threadIdx.x & 31;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= nown) return;
+    for (int k = ptr[i] + lane; k < ptr[i + 1]; k += 32) {
+        const int c = col[k];
+        col[k] = (c >= lo && c < hi) ? c - lo : nown + pos[c];
+    }
+}
+static __global__ void k_l1_compact(int n, const int* __restrict__ flag, const int* __restrict__ pos, int* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flag[i]) out[pos[i]] = i;
+}
+// need[(owner of row) * nown + (c - lo)] = 1 for every entry (row, c) of the GLOBAL operator with c in my block and the row in another
+static __global__ void k_l1_mark_needed(int n1, int chunk, int me, int lo, int nown, const int* __restrict__ ptr, const int* __restrict__ col,
+                                        unsigned char* __restrict__ need) {
+    const int lane = threadIdx.x & 31;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n1) return;
+    const int ro = i / chunk;
+    if (ro == me) return;
+    for (int k = ptr[i] + lane; k < ptr[i + 1]; k += 32) {
+        const int c = col[k];
+        if (c >= lo && c < lo + nown) need[(size_t)ro * nown + (c - lo)] = 1;
+    }
+}
+static __global__ void __launch_bounds__(kThreads) k_l1_pack(int m, const int* __restrict__ idx, const cfloat* __restrict__ x, cfloat* __restrict__ out,
+                                                      const PcgState* st) {
+    if (st && st->done) return;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < m; k += gridDim.x * blockDim.x) out[k] = x[__ldg(idx + k)];
+}
+static __global__ void __launch_bounds__(kThreads) k_l1_copy(int n, const cfloat* __restrict__ in, cfloat* __restrict__ out, const PcgState* st) {
+    if (st && st->done) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = in[i];
+}
+
+struct DistLevel1 {
+    DistComm* dc = nullptr;
+    int n1 = 0, n2 = 0, chunk = 0, lo = 0, hi = 0, nown = 0, nhalo = 0, nsend = 0;
+    DeviceCsr<cfloat> A, P, R;   // own rows of A_1 (local columns), own rows of P_1 (n_own x n2), its conjugate transpose (n2 x n_own)
+    DevBuf<cfloat> dinv, b, r, x_ext, d_ext, q_ext, xo, b2, x2, sendbuf;
+    DevBuf<int> send_idx;
+    std::vector<int> send_counts, recv_counts, send_off, recv_off;
+    double lmax = 2.0;
+
+    // builds the slice of rank dc->rank from the replicated fp32 level (its A, P, dinv, lmax); `lv` is level 0 of the fp32 tail hierarchy
+    void build(DistComm* dc_, AmgLevelDev<cfloat>& lv, int n2_, cudaStream_t s) {
+        dc = dc_;
+        const int W = dc->world, me = dc->rank;
+        n1 = lv.n; n2 = n2_;
+        chunk = (n1 + W - 1) / W;
+        lo = std::min(me * chunk, n1);
+        hi = std::min(lo + chunk, n1);
+        nown = hi - lo;
+        lmax = lv.lmax;
+        DevBuf<int> rows(std::max(nown, 1));
+        {
+            std::vector<int> h(std::max(nown, 1));
+            for (int i = 0; i < nown; i++) h[i] = lo + i;
+            rows.upload(h.data(), nown, s);
+        }
+        csr_gather_rows<cfloat>(lv.A, rows.p, nown, A, s);
+        csr_gather_rows<cfloat>(lv.P, rows.p, nown, P, s);
+        transpose_dev<cfloat>(P, R, true, s);
+        // halo columns of my rows, local numbering
+        DevBuf<int> flag((size_t)n1 + 1), pos((size_t)n1 + 1);
+        flag.zero(s);
+        const int gw = std::max(1, (nown * 32 + 255) / 256);
+        k_l1_mark_halo<<<gw, 256, 0, s>>>(nown, lo, hi, A.ptr.p, A.col.p, flag.p);
+        dev_exclusive_scan(flag.p, pos.p, n1, s);
+        nhalo = dev_read_int(pos.p + n1, s);
+        DevBuf<int> halo_glob(std::max(nhalo, 1));
+        k_l1_compact<<<(n1 + 255) / 256, 256, 0, s>>>(n1, flag.p, pos.p, halo_glob.p);
+        k_l1_renumber<<<gw, 256, 0, s>>>(nown, lo, hi, A.ptr.p, A.col.p, pos.p);
+        MK_CHECK_LAUNCH();
+        A.cols = nown + nhalo;
+        std::vector<int> hg(std::max(nhalo, 1));
+        halo_glob.download(hg.data(), nhalo, s);
+        // what the peers need of my block: the same rule applied to THEIR rows of the replicated operator
+        DevBuf<unsigned char> need((size_t)W * std::max(nown, 1));
+        MK_CUDA(cudaMemsetAsync(need.p, 0, (size_t)W * std::max(nown, 1), s));
+        k_l1_mark_needed<<<(int)(((int64_t)n1 * 32 + 255) / 256), 256, 0, s>>>(n1, chunk, me, lo, nown, lv.A.ptr.p, lv.A.col.p, need.p);
+        MK_CHECK_LAUNCH();
+        std::vector<unsigned char> hn((size_t)W * std::max(nown, 1));
+        need.download(hn.data(), hn.size(), s);
+        MK_CUDA(cudaStreamSynchronize(s));
+        send_counts.assign(W, 0); recv_counts.assign(W, 0); send_off.assign(W, 0); recv_off.assign(W, 0);
+        for (int k = 0; k < nhalo; k++) recv_counts[std::min(hg[k] / chunk, W - 1)]++;   // sorted by global index: contiguous per owner
+        std::vector<int> sidx;
+        for (int p = 0; p < W; p++) {
+            send_off[p] = (int)sidx.size();
+            if (p != me)
+                for (int j = 0; j < nown; j++)
+                    if (hn[(size_t)p * nown + j]) sidx.push_back(j);   // ascending local index = ascending global index = the peer's halo order
+            send_counts[p] = (int)sidx.size() - send_off[p];
+        }
+        for (int p = 1; p < W; p++) recv_off[p] = recv_off[p - 1] + recv_counts[p - 1];
+        nsend = (int)sidx.size();
+        send_idx.alloc(std::max(nsend, 1));
+        send_idx.upload(sidx.data(), nsend, s);
+        sendbuf.alloc(std::max(nsend, 1));
+        build_sell(A, s);
+        build_sell(P, s);
+        build_sell(R, s);
+        dinv.alloc(std::max(nown, 1));
+        if (nown) MK_CUDA(cudaMemcpyAsync(dinv.p, lv.dinv.p + lo, sizeof(cfloat) * nown, cudaMemcpyDeviceToDevice, s));
+        const size_t ne = (size_t)std::max(nown + nhalo, 1);
+        b.alloc(std::max(chunk, 1)); r.alloc(std::max(nown, 1)); xo.alloc(std::max(chunk, 1));
+        x_ext.alloc(ne); d_ext.alloc(ne); q_ext.alloc(ne);
+        x_ext.zero(s); d_ext.zero(s); q_ext.zero(s); xo.zero(s); b.zero(s);
+        b2.alloc(std::max(n2, 1)); x2.alloc(std::max(n2, 1));
+        MK_CUDA(cudaStreamSynchronize(s));
+        if (getenv("MK_VERBOSE"))
+            fprintf(stderr, "[mk] distributed level 1: rank %d owns %d of %d rows, halo %d, sends %d\n", me, nown, n1, nhalo, nsend);
+    }
+    // refresh the halo part of v_ext = [owned | halo] from the owners
+    void exchange(cfloat* v_ext, const PcgState* st, cudaStream_t s) {
+        NcclApi& nc = NcclApi::get();
+        if (nsend) k_l1_pack<<<stream_grid(nsend), kThreads, 0, s>>>(nsend, send_idx.p, v_ext, sendbuf.p, st);
+        MK_NCCL(nc.GroupStart());
+        for (int p = 0; p < dc->world; p++) {
+            if (p == dc->rank) continue;
+            if (send_counts[p]) MK_NCCL(nc.Send(sendbuf.p + send_off[p], 2 * (size_t)send_counts[p], ncclFloat, p, dc->comm, s));
+            if (recv_counts[p]) MK_NCCL(nc.Recv(v_ext + nown + recv_off[p], 2 * (size_t)recv_counts[p], ncclFloat, p, dc->comm, s));
+        }
+        MK_NCCL(nc.GroupEnd());
+    }
+    // b1_pad: every rank's partial sums of the restricted residual, W * chunk entries (zero padded); x1_pad: the correction, same length.
+    // `tail` = the replicated fp32 hierarchy whose level 0 is this level (its levels >= 1 are used as they are).
+    void cycle(const cfloat* b1_pad, cfloat* x1_pad, AmgPrecond<cfloat>& tail, int deg, double ratio, const PcgState* st, cudaStream_t s) {
+        NcclApi& nc = NcclApi::get();
+        MK_NCCL(nc.ReduceScatter(b1_pad, b.p, 2 * (size_t)chunk, ncclFloat, ncclSum, dc->comm, s));
+        const double lmin = lmax / ratio, theta = 0.5 * (lmax + lmin), de = 0.5 * (lmax - lmin), sigma = theta / de;
+        const int g = stream_grid(std::max(nown, 1));
+        cfloat* d_cur = deg == 1 ? x_ext.p : d_ext.p;
+        if (nown) k_start_dir<cfloat><<<g, kThreads, 0, s>>>(nown, b.p, dinv.p, d_cur, 1.0 / theta, st);
+        {
+            double rho = 1.0 / sigma;
+            for (int k = 0; k < deg; k++) {
+                const double rho1 = 1.0 / (2.0 * sigma - rho);
+                cfloat* d_next = (k == deg - 1) ? nullptr : (d_cur == d_ext.p ? q_ext.p : d_ext.p);
+                exchange(d_cur, st, s);
+                if (nown) spmv_cheb_step<cfloat>(A, 0.0, d_cur, d_next, r.p, x_ext.p, b.p, dinv.p, rho1 * rho, 2.0 * rho1 / de, k == 0 ? 1 : 0, st, s);
+                d_cur = d_next;
+                rho = rho1;
+            }
+        }
+        // restriction: partial sums over my columns of R_1, summed over the ranks; levels >= 2 replicated
+        if (nown) spmv_plain(R, r.p, b2.p, false, st, s);
+        else MK_CUDA(cudaMemsetAsync(b2.p, 0, sizeof(cfloat) * n2, s));
+        dc->allreduce_sum_f32(reinterpret_cast<float*>(b2.p), 2 * n2, s);
+        tail.vcycle(1, b2.p, x2.p, st, s);
+        if (nown) spmv_plain(P, x2.p, x_ext.p, true, st, s);
+        // post-smoothing
+        exchange(x_ext.p, st, s);
+        if (deg == 1) {
+            if (nown) spmv_cheb_resid_last<cfloat>(A, 0.0, x_ext.p, b.p, xo.p, dinv.p, 1.0 / theta, nullptr, const_cast<PcgState*>(st), ReduceWs{nullptr, nullptr}, s);
+        } else {
+            if (nown) spmv_cheb_resid<cfloat>(A, 0.0, x_ext.p, b.p, r.p, d_ext.p, dinv.p, 1.0 / theta, st, s);
+            cfloat* dc_ = d_ext.p;
+            double rho = 1.0 / sigma;
+            for (int k = 0; k + 1 < deg; k++) {
+                const double rho1 = 1.0 / (2.0 * sigma - rho);
+                exchange(dc_, st, s);
+                if (k + 2 == deg) {
+                    if (nown) spmv_cheb_step_last<cfloat>(A, 0.0, dc_, r.p, x_ext.p, xo.p, dinv.p, rho1 * rho, 2.0 * rho1 / de, nullptr, const_cast<PcgState*>(st),
+                                                          ReduceWs{nullptr, nullptr}, s);
+                } else {
+                    cfloat* dn = dc_ == d_ext.p ? q_ext.p : d_ext.p;
+                    if (nown) spmv_cheb_step<cfloat>(A, 0.0, dc_, dn, r.p, x_ext.p, nullptr, dinv.p, rho1 * rho, 2.0 * rho1 / de, 0, st, s);
+                    dc_ = dn;
+                }
+                rho = rho1;
+            }
+        }
+        MK_CHECK_LAUNCH();
+        MK_NCCL(nc.AllGather(xo.p, x1_pad, 2 * (size_t)chunk, ncclFloat, dc->comm, s));
+    }
+};
+
+// hand-over of the restricted residual to the fp32 replicated tail: b_lo = b / |r| (|r| = the PCG residual norm in the state: any factor of the
+// right magnitude serves, the cycle is linear), and back: xo = |r| xo_lo. st == null (the start of a solve): no scaling.
+static __global__ void __launch_bounds__(kThreads) k_tail_narrow(int n, const cdouble* __restrict__ b, cfloat* __restrict__ b_lo, const PcgState* st) {
+    if (st && st->done) return;
+    const double sc = (st && st->rr > 0.0) ? rsqrt(st->rr) : 1.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) b_lo[i] = to_low<cfloat, cdouble>(ldc_nc(b + i), sc);
+}
+static __global__ void __launch_bounds__(kThreads) k_tail_widen(int n, const cfloat* __restrict__ x_lo, cdouble* __restrict__ x, const PcgState* st) {
+    if (st && st->done) return;
+    const double sc = (st && st->rr > 0.0) ? sqrt(st->rr) : 1.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) stc(x + i, to_high<cdouble, cfloat>(x_lo[i], sc));
+}
+
 struct DistAmgPrecond : Precond<cdouble> {
     DistFaceOp* A = nullptr;
     DistComm* dc = nullptr;
     NullOp null_op;
     std::unique_ptr<AmgPrecond<cdouble>> G;  // global hierarchy; level 0 only contributes lmax / dinv / P_0
+    std::unique_ptr<AmgPrecond<cfloat>> Glo;  // fp32 copy of its levels >= 1 (MK_PRECOND_FP32, default): the replicated part of every rank
+    DevBuf<cfloat> b1_lo, x1_lo;              // level-1 right-hand side (summed over the ranks in fp32: half the all-reduce bytes) and result
+    std::unique_ptr<DistLevel1> L1;           // world > 1: level 1 row-partitioned as well (MK_DIST_L1=0: replicated like the levels below it)
     DeviceCsr<cdouble> P0, R0;               // this rank's rows of P_0 (local row order) and their conjugate transpose (n1 x n_local)
     DevBuf<cdouble> dinv, r, d_ext, q;
     double lmax = 2.0;
@@ -296,14 +516,26 @@ struct DistAmgPrecond : Precond<cdouble> {
         smooth(rin, z, true, st, s);
         AmgLevelDev<cdouble>& C = G->lv[1];
         spmv_plain(R0, r.p, C.b.p, false, st, s);
-        dc->allreduce_sum(reinterpret_cast<double*>(C.b.p), 2 * n1, s);
-        G->vcycle(1, C.b.p, C.xo.p, st, s);
+        if (Glo) {
+            k_tail_narrow<<<stream_grid(n1), kThreads, 0, s>>>(n1, C.b.p, b1_lo.p, st);
+            if (L1) {
+                L1->cycle(b1_lo.p, x1_lo.p, *Glo, Glo->degree(0), Glo->prm.cheb_ratio, st, s);
+            } else {
+                dc->allreduce_sum_f32(reinterpret_cast<float*>(b1_lo.p), 2 * n1, s);
+                Glo->vcycle(0, b1_lo.p, x1_lo.p, st, s);
+            }
+            k_tail_widen<<<stream_grid(n1), kThreads, 0, s>>>(n1, x1_lo.p, C.xo.p, st);
+            MK_CHECK_LAUNCH();
+        } else {
+            dc->allreduce_sum(reinterpret_cast<double*>(C.b.p), 2 * n1, s);
+            G->vcycle(1, C.b.p, C.xo.p, st, s);
+        }
         spmv_plain(P0, C.xo.p, z, true, st, s);
         smooth(rin, z, false, st, s);
     }
     int launches_per_apply() const override {
         const int per_spmv = A->launches_per_apply();
-        return (2 * prm.cheb_degree + 1) * (per_spmv + 1) + 1 + 2 + (G ? 1 + G->launches_from_level(1) : 0);
+        return (2 * prm.cheb_degree + 1) * (per_spmv + 1) + 1 + 2 + (Glo ? 3 + Glo->launches_from_level(0) : (G ? 1 + G->launches_from_level(1) : 0));
     }
 };
 

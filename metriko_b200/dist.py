@@ -127,6 +127,14 @@ class DistFaceField:
         self.ctx.check(rc, allow=(-3,))
         return x
 
+    def pcg_dev(self, b_dev_ptr: int, x_dev_ptr: int, **opts):
+        """The same solve with the owned rows of b and x (start vector in, solution out) resident in device memory (raw pointers)."""
+        st = Stats()
+        o = default_opts(**opts)
+        rc = self.ctx.L.mk_dfield_pcg_dev(self.h, C.c_void_p(b_dev_ptr), C.c_void_p(x_dev_ptr), C.byref(o), C.byref(st))
+        self.stats = st.as_dict()
+        self.ctx.check(rc, allow=(-3,))
+
     def solveSmallestEig(self, u0_local, nIter: int = 50, **opts):
         u0 = as_c128(u0_local)
         x = np.empty_like(u0)

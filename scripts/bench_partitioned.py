@@ -57,11 +57,50 @@ def run_partitioned(ctx, rank, world, kind=4, levels=11, reps=100, outer=0, both
         torch.cuda.synchronize()
         t = time.time()
         try:
-            F.pcg(b, precond=precond)
+            if os.environ.get("PART_TRACE") and rank == 0:   # CUPTI timeline of the timed solve (then NOT a timing run): kernel time by name
+                from torch.profiler import ProfilerActivity, profile
+                with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                    F.pcg(b, precond=precond)
+                    torch.cuda.synchronize()
+                import collections
+                path = os.environ["PART_TRACE"]
+                prof.export_chrome_trace(path + ".json")
+                ev = [e for e in json.load(open(path + ".json"))["traceEvents"] if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
+                os.remove(path + ".json")
+                by = collections.defaultdict(lambda: [0, 0.0])
+                for e in ev:
+                    k = e["name"].split("(")[0].replace("void ", "").replace("mk::", "")
+                    by[k][0] += 1
+                    by[k][1] += e["dur"]
+                tot = sum(v[1] for v in by.values())
+                span = (max(e["ts"] + e["dur"] for e in ev) - min(e["ts"] for e in ev)) if ev else 0.0
+                with open(path, "w") as fh:
+                    fh.write(f"{len(ev)} device activities, span {span / 1e3:.2f} ms, busy {tot / 1e3:.2f} ms\n")
+                    for k, (c, tt) in sorted(by.items(), key=lambda kv: -kv[1][1])[:40]:
+                        fh.write(f"{tt / 1e3:9.2f} ms {100 * tt / max(tot, 1e-9):5.1f} %  {c:6d} x {tt / c:8.2f} us  {k}\n")
+            else:
+                F.pcg(b, precond=precond)
         except Exception as e:  # noqa: BLE001
             res[f"pcg_precond{precond}_error"] = repr(e)
         res[f"pcg_precond{precond}"] = dict(iterations=int(F.stats["inner_iterations"]), relres=F.stats["relres_max"], setup_ms=F.stats["setup_ms"],
                                             solve_ms=maxr(F.stats["solve_ms"]), wall_s=maxr(time.time() - t))
+    # the same solve with b and x resident in HBM (what `value` means in bench.py): the host-buffer call above moves 2 x 16 B per owned row
+    # through pageable memory inside its solve_ms
+    try:
+        bd = torch.from_numpy(np.ascontiguousarray(b).view(np.float64)).cuda()
+        xd = torch.zeros_like(bd)
+        torch.cuda.synchronize()
+        F.pcg_dev(bd.data_ptr(), xd.data_ptr(), precond=1)
+        xd.zero_()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = time.time()
+        F.pcg_dev(bd.data_ptr(), xd.data_ptr(), precond=1)
+        res["pcg_precond1_resident"] = dict(iterations=int(F.stats["inner_iterations"]), relres=F.stats["relres_max"], solve_ms=maxr(F.stats["solve_ms"]),
+                                            wall_s=maxr(time.time() - t))
+    except Exception as e:  # noqa: BLE001
+        res["pcg_precond1_resident_error"] = repr(e)
     if outer:
         t = time.time()
         try:
