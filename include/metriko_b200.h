@@ -168,8 +168,9 @@ int mk_igm_poisson(mk_igm* g, int n_fixed, const int* fixedIdcs, const double* f
  * Outputs: fullx[ufull_rows]; fixed_idcs/fixed_vals[n_sing + n_int] in the order dofs were fixed, n_fixed_out their
  * count; resolve_flags[i] = 1 if fixing entry i triggered a re-solve; tie_flags[i] bit0 = rounding near-tie
  * (|frac - 0.5| < 1e-6), bit1 = selection near-tie (runner-up distance within 1e-8 and above the 10e-7 skip threshold), bit2 = re-solve
- * near-tie (the dof was already within 1e-7 .. 1e-5 of an integer: whether "minDif > 10e-7", iter_rounding.h:100, triggers a re-solve then depends
- * on how exactly earlier constraints hold -- to ~1e-6 under the reference's penalty rows, to round-off under the elimination used here).
+ * near-tie ("minDif > 10e-7", iter_rounding.h:100, met within a factor 2). Values that close to a decision are evaluated on the REFERENCE's
+ * iterate: its 1e10 penalty rows hold the fixed dofs only up to mu / rho, and that slack (up to 1.3e-6 at 1M vertices) is what decides whether
+ * a dof the fixed rows already determine triggers a re-solve; the library emulates it to first order in 1 / rho.
  * Returns MK_ERR_ROUNDING when post_checking (iter_rounding_loop.h:89-100) fails. */
 int mk_igm_round(mk_igm* g, int n_fixed, const int* fixedIdcs, const double* fixedVals, int n_sing, const int* singularIdcs,
                  int n_int, const int* integerIdcs, int seamless, int roundSeams, double* fullx, int* fixed_idcs, int* fixed_vals,

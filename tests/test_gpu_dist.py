@@ -36,6 +36,12 @@ def _check_rank(rank, world, g, seed=3):
         xs = F.pcg(b[rows], precond=precond)
         assert F.stats["relres_max"] <= 1.001e-10 and F.stats["status"] == 0
         out[f"pcg{precond}"] = (xs, F.stats["inner_iterations"])
+        if precond == 1:   # the same solve with b and x resident in device memory (mk_dfield_pcg_dev)
+            bd = torch.from_numpy(np.ascontiguousarray(b[rows]).view(np.float64)).cuda(ctx.device)
+            xd = torch.zeros_like(bd)
+            F.pcg_dev(bd.data_ptr(), xd.data_ptr(), precond=1)
+            assert F.stats["inner_iterations"] == out["pcg1"][1]
+            assert np.abs(xd.cpu().numpy().view(np.complex128) - xs).max() <= 1e-12 * np.abs(xs).max()
     z = F.solveSmallestEig(g["u0"][rows], 50)
     assert F.stats["relres_max"] <= 1.001e-10 and F.stats["status"] == 0
     F.close()
@@ -110,3 +116,75 @@ def test_partitioned_world2_matches_oracle(name):
     assert field_angle_error(z, g["z50"], 4).max() < 1e-5                   # same field as the oracle's direct-solver recurrence
     assert res[0][4] == res[1][4]                                           # ranks agree on the iteration count (device-side state)
     assert res[0][4] <= res[0][7] and res[0][4] <= 32                       # global hierarchy: one-GPU iteration counts, not block-Jacobi's
+
+
+def _worker_l1(rank, world, port, dist_l1, q):
+    """world-2 solve on a 32,768-face sphere (4 multigrid levels, so that level 1 is itself coarsened and DistLevel1 is built)"""
+    try:
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        os.environ["MK_DIST_L1"] = str(dist_l1)
+        import torch.distributed as dist
+        from hostglue import Session
+        from metriko_b200 import capi
+        from metriko_b200.dist import DistContext, DistFaceField
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        torch.cuda.set_device(rank)
+        g = Session().make_sphere(8, 6, bump=0.08).field_inputs()
+        nF = len(g["faceArea"])
+        ctx = capi.Context(rank)
+        d = DistContext(ctx, rank, world)
+        F = DistFaceField.from_mesh(d, g["face2half"], g["next"], g["twin"], g["face"], g["heArgOnFace"], g["faceArea"], 4)
+        rows = F.plan.owned_global()
+        b = g["faceArea"] * oracle.random_u0(nF, 2)
+        xs = F.pcg(b[rows], precond=1)
+        q.put((rank, "ok", rows, xs, F.stats["inner_iterations"], F.stats["relres_max"]))
+        F.close()
+        d.close()
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:  # noqa: BLE001
+        import traceback
+        q.put((rank, "fail", traceback.format_exc()))
+
+
+def test_partitioned_world2_distributed_level1():
+    """Level 1 of the global hierarchy row-partitioned (DistLevel1: level-1 halo exchange, reduce-scatter / all-gather) against the same solve
+    with level 1 replicated (MK_DIST_L1=0) and against a direct solve: same iteration count (+-1: the level-1 residual is summed in another
+    order), residual bar met, solutions equal."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    from hostglue import Session
+    world = 2
+    runs = {}
+    for dist_l1 in (1, 0):
+        s = socket.socket()
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+        s.close()
+        mpctx = mp.get_context("spawn")
+        q = mpctx.Queue()
+        procs = [mpctx.Process(target=_worker_l1, args=(r, world, port, dist_l1, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        res = [q.get(timeout=300) for _ in range(world)]
+        for p in procs:
+            p.join(timeout=60)
+        for r in res:
+            assert r[1] == "ok", r[2]
+        runs[dist_l1] = res
+    g = Session().make_sphere(8, 6, bump=0.08).field_inputs()
+    nF = len(g["faceArea"])
+    L = oracle.connection_laplacian(g["twin"], g["face"], g["heArgOnFace"], nF, 4).tocsr()
+    b = g["faceArea"] * oracle.random_u0(nF, 2)
+    xs = {}
+    for k, res in runs.items():
+        x = np.empty(nF, np.complex128)
+        for r in res:
+            x[r[2]] = r[3]
+            assert r[5] <= 1.001e-10
+        assert np.linalg.norm(L @ x - b) <= 1.01e-10 * np.linalg.norm(b)
+        xs[k] = x
+    assert abs(runs[1][0][4] - runs[0][0][4]) <= 1 and runs[1][0][4] == runs[1][1][4]
+    assert np.abs(xs[1] - xs[0]).max() <= 1e-7 * np.abs(xs[0]).max()
