@@ -200,4 +200,47 @@ __device__ __forceinline__ void grid_reduce(const double (&v)[K], double* partia
     }
 }
 
+// The same for many values (the multi-vector dot products of the recycle space): ONE barrier pair per CTA instead of one per value --
+// every warp reduces all K values by shuffles and parks them in shared memory, the first K threads add the warps' partials.
+// `smem` = double[K * 32] (K values x up to 32 warps).
+template <int K, class Fin>
+__device__ __forceinline__ void grid_reduce_many(double (&v)[K], double* partials, unsigned int* ticket, double* smem, Fin fin) {
+    __shared__ bool is_last_many;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const double w = warp_sum(v[k]);
+        if (lane == 0) smem[k * 32 + wid] = w;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < K) {
+        double a = 0.0;
+        for (int w = 0; w < nw; w++) a += smem[threadIdx.x * 32 + w];
+        partials[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = a;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int t = atomicAdd(ticket, 1u);
+        is_last_many = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last_many) {
+        __threadfence();
+        // warp w sums value w, w + nw, ... over the CTAs in index order (deterministic)
+        for (int k = wid; k < K; k += nw) {
+            double a = 0.0;
+            for (int i = lane; i < (int)gridDim.x; i += 32) a += ((volatile double*)partials)[(size_t)k * gridDim.x + i];
+            a = warp_sum(a);
+            if (lane == 0) smem[k] = a;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            *ticket = 0u;
+            fin(smem);
+        }
+    }
+}
+
 }  // namespace mk

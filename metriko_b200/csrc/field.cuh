@@ -494,16 +494,18 @@ static __global__ void __launch_bounds__(kThreads) k_multi_axpy(int n, int j0, i
 // step were 44 of the 183 ms of a 1M-vertex field solve):
 //   k_multi_dot2 : c1[j] = <E_j, v1>, c2[j] = <E_j, v2>          (re-orthogonalisation of the new increment; start of the NEXT solve)
 //   k_multi_axpy2: y1 -= sum_j c1[j] E_j ; y2 (+)= sum_j c2[j] E_j
+constexpr int kDot2Chunk = 4;  // basis vectors per launch of the two-vector dot: 16 fp64 accumulators per thread (8 vectors x 2 right-hand sides
+                               // = 32 accumulators compiled to 102 registers + a stack frame and ran at 2 TB/s: 171 us per launch at 1M vertices)
 static __global__ void __launch_bounds__(kThreads) k_multi_dot2(int n, int j0, int cnt, const cdouble* __restrict__ E, const cdouble* __restrict__ v1,
                                                          const cdouble* __restrict__ v2, cdouble* __restrict__ c1, cdouble* __restrict__ c2, ReduceWs ws) {
-    __shared__ double red[32];
-    double acc[4 * kRecycleChunk];
+    __shared__ double red[4 * kDot2Chunk * 32];
+    double acc[4 * kDot2Chunk];
 #pragma unroll
-    for (int j = 0; j < 4 * kRecycleChunk; j++) acc[j] = 0.0;
+    for (int j = 0; j < 4 * kDot2Chunk; j++) acc[j] = 0.0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const cdouble a = ldc_nc(v1 + i), b = ldc_nc(v2 + i);
 #pragma unroll
-        for (int j = 0; j < kRecycleChunk; j++)
+        for (int j = 0; j < kDot2Chunk; j++)
             if (j < cnt) {
                 const cdouble e = ldc_nc(E + (size_t)(j0 + j) * n + i);
                 acc[4 * j] += e.x * a.x + e.y * a.y;
@@ -512,7 +514,7 @@ static __global__ void __launch_bounds__(kThreads) k_multi_dot2(int n, int j0, i
                 acc[4 * j + 3] += e.x * b.y - e.y * b.x;
             }
     }
-    grid_reduce<4 * kRecycleChunk>(acc, ws.partials, ws.ticket, red, [&](const double* s) {
+    grid_reduce_many<4 * kDot2Chunk>(acc, ws.partials, ws.ticket, red, [&](const double* s) {
         for (int j = 0; j < cnt; j++) {
             c1[j0 + j] = make_c(s[4 * j], s[4 * j + 1]);
             c2[j0 + j] = make_c(s[4 * j + 2], s[4 * j + 3]);
@@ -598,8 +600,8 @@ struct RecycleSpace {
     // coef = E^H v1, coef2 = E^H v2 over the filled slots, one pass
     int dots2(const cdouble* v1, const cdouble* v2, int grid, cudaStream_t s) {
         int l = 0;
-        for (int j0 = 0; j0 < valid(); j0 += kRecycleChunk, l++)
-            k_multi_dot2<<<grid, kThreads, 0, s>>>(n, j0, std::min(kRecycleChunk, valid() - j0), E.p, v1, v2, coef.p, coef2.p, ws());
+        for (int j0 = 0; j0 < valid(); j0 += kDot2Chunk, l++)
+            k_multi_dot2<<<grid, kThreads, 0, s>>>(n, j0, std::min(kDot2Chunk, valid() - j0), E.p, v1, v2, coef.p, coef2.p, ws());
         return l;
     }
     // y1 -= E coef ; y2 = E coef2 (y2 overwritten), one pass
