@@ -718,6 +718,10 @@ struct IgmRun {
     // step (wClose |x - xPrev|^2), so the decision changes fullx (7e-4 at 1M vertices for ONE re-solve), and the slack grows with the mesh
     // (7e-10 at 642 vertices, 1.3e-6 at 1M: the reference re-solves there).
     std::vector<double> slack_y;  // (T^T T)^-1 nu of the last re-solve; its length = the rank of the constraint set at that solve
+    std::vector<std::vector<double>> slack_T;  // the fixed rows in the Q basis, in the order they were fixed (grown incrementally)
+    std::vector<int> slack_T_idx;
+    std::vector<double> slack_G;  // lower triangle of T^T T, slack_k_done x slack_k_done
+    int slack_k_done = 0;
     // The same first-order term for EVERY dof: x_rho = x + x_1 / rho with  H x_1 + C^T mu_1 = 0,  C x_1 = mu  <=>  Q x_1 = y. It shifts all
     // candidate values by O(1e-6) at 1M vertices, enough to turn a selection near-tie of the reference (twins of the mesh whose distances
     // to an integer differ by 8e-8 in the 1M-vertex golden) the other way -- and the twin chosen decides which dof later meets the re-solve
@@ -770,22 +774,47 @@ struct IgmRun {
         resS.resize((size_t)2 * m);
         resS_dev.download(resS.data(), (size_t)2 * m, s);
         MK_CUDA(cudaStreamSynchronize(s));
-        std::vector<double> nu(k, 0.0), G((size_t)k * k, 0.0), t(k);
+        std::vector<double> nu(k, 0.0);
         for (int j = 0; j < k; j++) {
             double a = 0;
             for (int p = 0; p < m; p++) a += cs.Q[j][p] * (resS[p] - resS[m + p]);
             nu[j] = a;
         }
-        for (int fi : fixed) {
-            const std::vector<double>& c = bank.rows.at(fi);
-            for (int j = 0; j < k; j++) {
-                double a = 0;
-                for (int p = 0; p < m; p++) a += cs.Q[j][p] * c[p];
-                t[j] = a;
-            }
-            for (int i = 0; i < k; i++)
-                for (int j = 0; j <= i; j++) G[(size_t)i * k + j] += t[i] * t[j];
+        // T (rows = the fixed rows in the Q basis) and G = T^T T are kept between re-solves: a re-solve adds a few fixed rows and at most a
+        // few rows of Q, so only the new row / column blocks are computed (O(new * k * m) instead of O(all * k * m) per re-solve: with
+        // hundreds of singularities the full rebuild was the dominant host cost of the rounding loop)
+        auto qdot = [&](int j, const std::vector<double>& c) {
+            double a = 0;
+            for (int p = 0; p < m; p++) a += cs.Q[j][p] * c[p];
+            return a;
+        };
+        const int k0 = slack_k_done;
+        const size_t r0 = slack_T.size();
+        for (size_t r = 0; r < r0; r++) {
+            const std::vector<double>& c = bank.rows.at(slack_T_idx[r]);
+            for (int j = k0; j < k; j++) slack_T[r].push_back(qdot(j, c));
         }
+        for (size_t r = r0; r < fixed.size(); r++) {
+            const std::vector<double>& c = bank.rows.at(fixed[r]);
+            std::vector<double> t(k);
+            for (int j = 0; j < k; j++) t[j] = qdot(j, c);
+            slack_T.push_back(std::move(t));
+            slack_T_idx.push_back(fixed[r]);
+        }
+        {
+            std::vector<double> Gn((size_t)k * k, 0.0);
+            for (int i = 0; i < k0; i++)
+                for (int j = 0; j < k0; j++) Gn[(size_t)i * k + j] = slack_G[(size_t)i * k0 + j];
+            for (size_t r = r0; r < slack_T.size(); r++)   // new fixed rows into the old block
+                for (int i = 0; i < k0; i++)
+                    for (int j = 0; j <= i; j++) Gn[(size_t)i * k + j] += slack_T[r][i] * slack_T[r][j];
+            for (size_t r = 0; r < slack_T.size(); r++)    // every row into the new rows of G
+                for (int i = k0; i < k; i++)
+                    for (int j = 0; j <= i; j++) Gn[(size_t)i * k + j] += slack_T[r][i] * slack_T[r][j];
+            slack_G = std::move(Gn);
+            slack_k_done = k;
+        }
+        std::vector<double> G = slack_G;  // lower triangle valid
         // Cholesky of the k x k Gram matrix T^T T (full rank: Q spans exactly the rows of C), then y = G^-1 nu
         for (int i = 0; i < k; i++) {
             for (int j = 0; j <= i; j++) {
@@ -878,6 +907,10 @@ struct IgmRun {
         cs.Q.clear();
         cs.beta.clear();
         slack_y.clear();
+        slack_T.clear();
+        slack_T_idx.clear();
+        slack_G.clear();
+        slack_k_done = 0;
         x1_valid = false;
         proj.k = 0;
         applied = 0;
