@@ -194,7 +194,8 @@ int mk_dfield_set_global(mk_dfield* f, int nF, const int* nbr, const double* val
             g->b1_lo.zero(s);
             g->x1_lo.zero(s);
             const char* e = getenv("MK_DIST_L1");
-            if (W > 1 && g->Glo->lv.size() >= 3 && !(e && std::strcmp(e, "0") == 0)) {
+            // (tiny hierarchies stay replicated: every rank must own a non-trivial block of level 1)
+            if (W > 1 && g->Glo->lv.size() >= 3 && g->n1 >= 256 * W && !(e && std::strcmp(e, "0") == 0)) {
                 g->L1 = std::make_unique<DistLevel1>();
                 g->L1->build(&f->d->c, g->Glo->lv[0], g->Glo->lv[1].n, s);
             }
