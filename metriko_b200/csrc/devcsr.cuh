@@ -167,15 +167,17 @@ __device__ __forceinline__ int find_col(const int* __restrict__ col, int b, int 
 // ---------------------------------------------------------------------------------------------------------------
 // row binning
 // ---------------------------------------------------------------------------------------------------------------
+constexpr int kBinThread = 24;       // <= : one THREAD per row, candidates insertion-sorted in local memory (P = S T and A P of the multigrid set-up:
+                                     // 7 and ~18 candidates per row on 2 M rows -- a warp per row with a shared-memory bitonic sort was 4x the time)
 constexpr int kBinWarpSmall = 128;   // <= : one warp, 128-int shared buffer
 constexpr int kBinWarp = 1024;       // <= : one warp, 1024-int shared buffer
 constexpr int kBinCta = 8192;        // <= : one CTA, 8192-int shared buffer; above: "huge" rows
 constexpr int kLongARow = 512;       // rows of A longer than this also go to the huge path (the gather costs row length x outputs)
 
 struct RowBins {
-    DevBuf<int> list;   // 4 x n row ids
-    DevBuf<int> count;  // 4
-    int h_count[4] = {0, 0, 0, 0};
+    DevBuf<int> list;   // 5 x n row ids (bin 4 = the thread-per-row bin)
+    DevBuf<int> count;  // 5
+    int h_count[5] = {0, 0, 0, 0, 0};
     int n = 0;
     const int* rows(int b) const { return list.p + (size_t)b * n; }
 };
@@ -184,18 +186,18 @@ static __global__ void k_bin_rows(int n, const int* __restrict__ size, int* __re
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int u = size[i];
-    const int b = u <= kBinWarpSmall ? 0 : (u <= kBinWarp ? 1 : (u <= kBinCta ? 2 : 3));
+    const int b = u <= kBinThread ? 4 : (u <= kBinWarpSmall ? 0 : (u <= kBinWarp ? 1 : (u <= kBinCta ? 2 : 3)));
     list[(size_t)b * n + atomicAdd(count + b, 1)] = i;  // list order does not influence any result
 }
 
 inline void bin_rows(RowBins& B, int n, const int* size, cudaStream_t s) {
     B.n = n;
-    B.list.alloc((size_t)4 * std::max(n, 1));
-    B.count.alloc(4);
+    B.list.alloc((size_t)5 * std::max(n, 1));
+    B.count.alloc(5);
     B.count.zero(s);
     if (n > 0) k_bin_rows<<<(n + 255) / 256, 256, 0, s>>>(n, size, B.list.p, B.count.p);
     MK_CHECK_LAUNCH();
-    MK_CUDA(cudaMemcpyAsync(B.h_count, B.count.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    MK_CUDA(cudaMemcpyAsync(B.h_count, B.count.p, 5 * sizeof(int), cudaMemcpyDeviceToHost, s));
     MK_CUDA(cudaStreamSynchronize(s));
 }
 
@@ -282,6 +284,49 @@ static __global__ void __launch_bounds__(128) k_spgemm_warp(int n_list, const in
             }
         }
         __syncwarp();
+    }
+}
+
+// One thread per listed row (<= kBinThread candidates): the candidates (column, position in A, position in B) are insertion-sorted by
+// column as they are generated -- stable, so equal columns stay in the order of row i of A, which is the summation order of gather_product:
+// the values are bit-identical to the other bins'.
+template <class T, bool NUMERIC>
+static __global__ void __launch_bounds__(128) k_spgemm_thread(int n_list, const int* __restrict__ list, const int* __restrict__ aptr,
+                                                              const int* __restrict__ acol, const T* __restrict__ aval, const int* __restrict__ bptr,
+                                                              const int* __restrict__ bcol, const T* __restrict__ bval, int* __restrict__ rownnz,
+                                                              const int* __restrict__ cptr, int* __restrict__ ccol, T* __restrict__ cval) {
+    int cc[kBinThread], ka_[kBinThread], kb_[kBinThread];
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n_list; w += gridDim.x * blockDim.x) {
+        const int i = list[w];
+        int cnt = 0;
+        for (int ka = aptr[i]; ka < aptr[i + 1]; ka++) {
+            const int j = __ldg(acol + ka);
+            for (int kb = __ldg(bptr + j); kb < __ldg(bptr + j + 1); kb++) {
+                const int c = __ldg(bcol + kb);
+                int p = cnt;
+                while (p > 0 && cc[p - 1] > c) { cc[p] = cc[p - 1]; ka_[p] = ka_[p - 1]; kb_[p] = kb_[p - 1]; p--; }
+                cc[p] = c; ka_[p] = ka; kb_[p] = kb;
+                cnt++;
+            }
+        }
+        if (!NUMERIC) {
+            int u = 0;
+            for (int k = 0; k < cnt; k++) u += (k == 0 || cc[k] != cc[k - 1]) ? 1 : 0;
+            rownnz[i] = u;
+        } else {
+            int o = cptr[i] - 1;
+            T acc = ST<T>::zero();
+            for (int k = 0; k < cnt; k++) {
+                if (k == 0 || cc[k] != cc[k - 1]) {
+                    if (k > 0) st_rw(cval + o, acc);
+                    o++;
+                    ccol[o] = cc[k];
+                    acc = ST<T>::zero();
+                }
+                acc = ST<T>::fma_(ld_ro(aval + ka_[k]), ld_ro(bval + kb_[k]), acc);
+            }
+            if (cnt > 0) st_rw(cval + o, acc);
+        }
     }
 }
 
@@ -451,7 +496,7 @@ inline void spgemm(const DeviceCsr<T>& A, const DeviceCsr<T>& B, DeviceCsr<T>& C
     static const bool dbg = getenv("MK_VERBOSE") && atoi(getenv("MK_VERBOSE")) >= 2;
     StageTimer tm("spgemm");
     tm.on = dbg;
-    if (dbg) fprintf(stderr, "[mk] spgemm: %d x %d x %d, bins %d %d %d %d\n", n, A.cols, B.cols, bins.h_count[0], bins.h_count[1], bins.h_count[2], bins.h_count[3]);
+    if (dbg) fprintf(stderr, "[mk] spgemm: %d x %d x %d, bins %d | %d %d %d %d\n", n, A.cols, B.cols, bins.h_count[4], bins.h_count[0], bins.h_count[1], bins.h_count[2], bins.h_count[3]);
     DevBuf<int> rownnz((size_t)n + 1);
     rownnz.zero(s);
     const int nh = bins.h_count[3];
@@ -468,7 +513,11 @@ inline void spgemm(const DeviceCsr<T>& A, const DeviceCsr<T>& B, DeviceCsr<T>& C
     }
     auto warp_grid = [](int cnt) { return std::max(1, std::min((cnt + 3) / 4, kSMs * 16)); };
     auto cta_grid = [](int cnt) { return std::max(1, std::min(cnt, kSMs * 4)); };
+    auto thread_grid = [](int cnt) { return std::max(1, std::min((cnt + 127) / 128, kSMs * 32)); };
     // symbolic
+    if (bins.h_count[4])
+        k_spgemm_thread<T, false><<<thread_grid(bins.h_count[4]), 128, 0, s>>>(bins.h_count[4], bins.rows(4), A.ptr.p, A.col.p, A.val.p, B.ptr.p, B.col.p,
+                                                                                B.val.p, rownnz.p, nullptr, nullptr, nullptr);
     if (bins.h_count[0])
         k_spgemm_warp<T, kBinWarpSmall, false><<<warp_grid(bins.h_count[0]), 128, 0, s>>>(bins.h_count[0], bins.rows(0), A.ptr.p, A.col.p, A.val.p, B.ptr.p,
                                                                                            B.col.p, B.val.p, rownnz.p, nullptr, nullptr, nullptr);
@@ -491,6 +540,9 @@ inline void spgemm(const DeviceCsr<T>& A, const DeviceCsr<T>& B, DeviceCsr<T>& C
     C.col.alloc((size_t)std::max(nnz, 1));
     C.val.alloc((size_t)std::max(nnz, 1));
     // numeric
+    if (bins.h_count[4])
+        k_spgemm_thread<T, true><<<thread_grid(bins.h_count[4]), 128, 0, s>>>(bins.h_count[4], bins.rows(4), A.ptr.p, A.col.p, A.val.p, B.ptr.p, B.col.p,
+                                                                               B.val.p, nullptr, C.ptr.p, C.col.p, C.val.p);
     if (bins.h_count[0])
         k_spgemm_warp<T, kBinWarpSmall, true><<<warp_grid(bins.h_count[0]), 128, 0, s>>>(bins.h_count[0], bins.rows(0), A.ptr.p, A.col.p, A.val.p, B.ptr.p,
                                                                                           B.col.p, B.val.p, nullptr, C.ptr.p, C.col.p, C.val.p);
@@ -562,6 +614,22 @@ static __global__ void __launch_bounds__(256) k_sort_rows_cta(int n_list, const 
     }
 }
 
+// short rows (<= kBinThread): one thread per row, insertion sort in local memory
+static __global__ void __launch_bounds__(128) k_sort_rows_thread(int n_list, const int* __restrict__ list, const int* __restrict__ ptr, int* __restrict__ col) {
+    int buf[kBinThread];
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n_list; w += gridDim.x * blockDim.x) {
+        const int i = list[w];
+        const int b = ptr[i], cnt = ptr[i + 1] - b;
+        for (int k = 0; k < cnt; k++) {
+            const int c = col[b + k];
+            int p = k;
+            while (p > 0 && buf[p - 1] > c) { buf[p] = buf[p - 1]; p--; }
+            buf[p] = c;
+        }
+        for (int k = 0; k < cnt; k++) col[b + k] = buf[k];
+    }
+}
+
 // huge rows: the same sort in a global scratch buffer (scratch_ptr[w] = offset of row w's power-of-two sized segment)
 static __global__ void __launch_bounds__(1024) k_sort_rows_global(int n_list, const int* __restrict__ list, const int* __restrict__ ptr, int* __restrict__ col,
                                                                   const int64_t* __restrict__ scratch_ptr, int* __restrict__ scratch) {
@@ -611,6 +679,8 @@ inline void transpose_dev(const DeviceCsr<T>& A, DeviceCsr<T>& B, bool conjugate
     RowBins bins;
     bin_rows(bins, m, cnt.p, s);
     auto warp_grid = [](int c) { return std::max(1, std::min((c + 3) / 4, kSMs * 16)); };
+    if (bins.h_count[4])
+        k_sort_rows_thread<<<std::max(1, std::min((bins.h_count[4] + 127) / 128, kSMs * 32)), 128, 0, s>>>(bins.h_count[4], bins.rows(4), B.ptr.p, B.col.p);
     if (bins.h_count[0]) k_sort_rows_warp<kBinWarpSmall><<<warp_grid(bins.h_count[0]), 128, 0, s>>>(bins.h_count[0], bins.rows(0), B.ptr.p, B.col.p);
     if (bins.h_count[1]) k_sort_rows_warp<kBinWarp><<<warp_grid(bins.h_count[1]), 128, 0, s>>>(bins.h_count[1], bins.rows(1), B.ptr.p, B.col.p);
     if (bins.h_count[2]) k_sort_rows_cta<<<std::min(bins.h_count[2], kSMs * 4), 256, 0, s>>>(bins.h_count[2], bins.rows(2), B.ptr.p, B.col.p);
