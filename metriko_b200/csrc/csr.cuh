@@ -449,8 +449,11 @@ inline int extra_blocks(int n_huge, int n_long) { return n_huge + (n_long + kThr
 // SELL-32 SpMV: the CTAs after the `extra` ones run one thread per row, one warp per slice; rows longer than kLongRow are empty in the
 // slices and served by the extra CTAs of the SAME launch (extra_rows) -- no second kernel, no dependency, and no slice is serialised by
 // one wide row.
+// Occupancy: the real fp32 kernels (every SpMV of the IGM V-cycle) fit 32 registers without spilling and run 8 CTAs per SM -- the cycle on the
+// 7-entries-per-row operator is gather-latency bound and gains 12 % (285 -> 253 us per application at 1M vertices); cfloat / double / cdouble
+// spill at 32 registers and measure slower (field cycle 247 -> 251 us), so they stay at 6 CTAs per SM (40 registers).
 template <class T, int MODE>
-__global__ void __launch_bounds__(kThreads, 6) k_spmv_sell(int n, int n_slices, const int* __restrict__ sl_ptr, const int* __restrict__ sl_col,
+__global__ void __launch_bounds__(kThreads, sizeof(T) <= 4 ? 8 : 6) k_spmv_sell(int n, int n_slices, const int* __restrict__ sl_ptr, const int* __restrict__ sl_col,
                                                         const T* __restrict__ sl_val, const unsigned int* __restrict__ long_bits, int extra,
                                                         int n_huge, const int* __restrict__ huge_rows, int n_long, const int* __restrict__ long_rows,
                                                         const int* __restrict__ ptr, const int* __restrict__ col, const T* __restrict__ val,
