@@ -1,8 +1,8 @@
 """Oracle: the per-face injectivity barrier of the localInjectivity LM path. Restates
 include/metriko/core/igm/iterative_rounding/injective_barrier.h:19-109 and the localInjectivity branch of
-Integration::compute_jacobian (iter_rounding_common.h:70-85) in numpy. Test infrastructure only (oracle/__init__.py); the CUDA
-path of this round does not implement the barrier -- this file is the checker the next round builds against.
-Parity unpinned: the reference ships no fixtures for it."""
+Integration::compute_jacobian (iter_rounding_common.h:70-85) in numpy. Test infrastructure only (oracle/__init__.py): the checker of
+mk_igm_round_injective (csrc/barrier.cuh). Pinned against the reference's own injective_barrier.h compiled in place (oracle/_ref,
+tests/test_oracle_ref.py::test_live_barrier_update and the barrier fixtures tests/golden/ref_*.npz)."""
 from __future__ import annotations
 
 import numpy as np

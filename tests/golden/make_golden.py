@@ -4,7 +4,8 @@ The reference (komietty/metriko) ships no golden vectors and cannot be built or 
 (C++ with Eigen/libigl absent), so these fixtures are NOT outputs of the reference: they are outputs of the CPU
 oracle (oracle/, a line-by-line restatement with SuperLU direct solves) on inputs produced by the host-glue
 stage. They pin (1) the oracle against regressions and (2) the CUDA path on the GPU box, where neither
-/root/reference nor a long oracle run is available. Parity with the reference itself stays "unpinned".
+/root/reference nor a long oracle run is available. tests/golden/make_golden_ref.py / tests/test_oracle_ref.py tie them to the
+reference's own rounding-loop / LM / inverse-iteration code compiled against Eigen stand-ins (ref_<name>.npz).
 
 Run from the repo root:  python tests/golden/make_golden.py
 """
