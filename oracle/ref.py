@@ -151,6 +151,44 @@ class Ref:
         return x
 
 
+    _INT = ("twin", "next", "prev", "face", "tail", "head", "edge", "crnr", "face2half", "vert2half", "edge2face", "edge2vert", "face2edge", "matching",
+            "singular", "cmatching", "dims", "L_rows", "L_cols", "M_rows")
+    _CPLX = ("L_vals", "M_vals", "compressed", "field", "connection", "cfield")
+
+    def face_rosy_field(self, V, F, N, u0, matching="curl", seam=None, names=None):
+        """Hmesh(V, F) (hmesh.h:313-569) + FaceRosyField(mesh, N, Smoothest) (frf.h:17-44) + computeMatching (frf.h:100-202) [+ the combed field
+        (frf.h:207-249) when a seam is given] run by the reference's own code; returns the requested arrays (default: all)."""
+        V = np.ascontiguousarray(V, np.float64).reshape(-1, 3)
+        F = np.ascontiguousarray(F, np.int32).reshape(-1, 3)
+        u0 = np.ascontiguousarray(u0, np.complex128)
+        assert u0.size == F.shape[0]
+        self.L.ref_field_create.restype = C.c_void_p
+        self.L.ref_field_get.restype = C.c_long
+        sm = None if seam is None else np.ascontiguousarray(seam, np.int32)
+        h = C.c_void_p(self.L.ref_field_create(int(V.shape[0]), _dp(V.reshape(-1)), int(F.shape[0]), _ip(F.reshape(-1)), int(N),
+                                               _dp(u0.view(np.float64)), 1 if matching == "curl" else 0,
+                                               _ip(sm) if sm is not None else C.POINTER(C.c_int)()))
+        all_names = ("dims", "twin", "next", "prev", "face", "tail", "head", "edge", "crnr", "face2half", "vert2half", "heArgOnFace", "faceArea",
+                     "angleDefect", "dihedralArg", "heLen", "faceBasisX", "faceBasisY", "faceNormal", "edge2face", "edge2vert", "face2edge", "L_rows",
+                     "L_cols", "L_vals", "M_rows", "M_vals", "compressed", "field", "connection", "matching", "singular", "ext") + \
+                    (("cfield", "cmatching") if seam is not None else ())
+        out = {}
+        try:
+            for k in (names or all_names):
+                n = self.L.ref_field_get(h, k.encode(), C.c_long(0), C.POINTER(C.c_double)())
+                assert n >= 0, k
+                buf = np.zeros(n)
+                self.L.ref_field_get(h, k.encode(), C.c_long(n), _dp(buf))
+                if k in self._INT:
+                    buf = buf.astype(np.int64)
+                elif k in self._CPLX:
+                    buf = buf.view(np.complex128)
+                out[k] = buf
+        finally:
+            self.L.ref_field_destroy(h)
+        return out
+
+
 _keep: list = []
 
 

@@ -9,10 +9,15 @@
 //   ref_naive_integration    the NaiveIntegration constructor alone: UFull (ir_init.h:98-154), x0 (ir_init.h:173-212), X2F
 //   ref_barrier_update       InjectiveBarrier::update + gen_image_filed (injective_barrier.h:37-109)
 //   ref_solve_smallest_eig   solver/sparse_linear_solver.h:29-54 (the no-SuiteSparse branch) on given L, M with an explicit u0
+//   ref_field_create / get   Hmesh(V, F) (hmesh/hmesh.h:313-569; igl::edge_topology is the stand-in of ref_shim/igl/edge_topology.h) and
+//                            FaceRosyField(mesh, N, FieldType::Smoothest) (vectorfield/face_rosy_field.h:17-44: connectionLaplacian frf.h:46-76,
+//                            galerkinMassMatrix frf.h:78-84, solveSmallestEig, decode frf.h:37-43), computeMatching (frf.h:100-202),
+//                            compute_combbed_field (frf.h:207-249, seam given), compute_extrinsic_field (frf.h:251-264)
 #include <cstring>
 
 #include "metriko/core/igm/iterative_rounding/iter_rounding.h"
 #include "metriko/core/solver/sparse_linear_solver.h"
+#include "metriko/core/vectorfield/face_rosy_field.h"
 
 using namespace metriko;
 
@@ -141,6 +146,102 @@ int ref_solve_smallest_eig(int n, long l_nnz, const int* l_r, const int* l_c, co
     refshim::random_source = nullptr;
     for (long i = 0; i < r.size(); i++) { x[2 * i] = r(i).real(); x[2 * i + 1] = r(i).imag(); }
     return 1;
+}
+
+
+struct RefField {
+    std::unique_ptr<Hmesh> mesh;
+    std::unique_ptr<FaceRosyField> field, combed;
+    SprsC L, M;
+    MatXd ext;
+};
+
+// V[3 nV] and F[3 nF] row-major. u0: 2 nF doubles for VecXc::Random. matching_type 0 = Principal, 1 = Curl. seam[nE] (0 / 1) or null: with a
+// seam the combed field (compute_combbed_field) is computed as well.
+void* ref_field_create(int nV, const double* V, int nF, const int* F, int N, const double* u0, int matching_type, const int* seam) {
+    MatXd Vm(nV, 3);
+    MatXi Fm(nF, 3);
+    for (int i = 0; i < nV; i++) for (int j = 0; j < 3; j++) Vm(i, j) = V[3 * i + j];
+    for (int i = 0; i < nF; i++) for (int j = 0; j < 3; j++) Fm(i, j) = F[3 * i + j];
+    auto* r = new RefField;
+    r->mesh = std::make_unique<Hmesh>(Vm, Fm);
+    refshim::random_source = u0;
+    refshim::random_pos = 0;
+    r->field = std::make_unique<FaceRosyField>(*r->mesh, N, FieldType::Smoothest);
+    refshim::random_source = nullptr;
+    r->L = r->field->connectionLaplacian();
+    r->M = r->field->galerkinMassMatrix();
+    r->field->computeMatching(matching_type ? MatchingType::Curl : MatchingType::Principal);
+    if (N == 4) r->ext = compute_extrinsic_field(*r->mesh, *r->field, N);
+    if (seam) {
+        std::vector<bool> sm(r->mesh->nE);
+        for (int e = 0; e < r->mesh->nE; e++) sm[e] = seam[e] != 0;
+        r->combed = compute_combbed_field(*r->field, sm);
+    }
+    return r;
+}
+
+void ref_field_destroy(void* h) { delete static_cast<RefField*>(h); }
+
+// every array as doubles (integers converted; complex interleaved; matrices row-major); returns the length, fills up to cap
+long ref_field_get(void* h, const char* name, long cap, double* out) {
+    const RefField& r = *static_cast<RefField*>(h);
+    const Hmesh& m = *r.mesh;
+    std::vector<double> v;
+    const std::string k(name);
+    auto ints = [&](const std::vector<int>& a) { v.assign(a.begin(), a.end()); };
+    auto vecd = [&](const VecXd& a) { for (long i = 0; i < a.size(); i++) v.push_back(a(i)); };
+    auto veci = [&](const VecXi& a) { for (long i = 0; i < a.size(); i++) v.push_back(a(i)); };
+    auto vecc = [&](const VecXc& a) { for (long i = 0; i < a.size(); i++) { v.push_back(a(i).real()); v.push_back(a(i).imag()); } };
+    auto matd = [&](const MatXd& a) { for (long i = 0; i < a.rows(); i++) for (long j = 0; j < a.cols(); j++) v.push_back(a(i, j)); };
+    auto mati = [&](const MatXi& a) { for (long i = 0; i < a.rows(); i++) for (long j = 0; j < a.cols(); j++) v.push_back(a(i, j)); };
+    auto matc = [&](const MatXc& a) { for (long i = 0; i < a.rows(); i++) for (long j = 0; j < a.cols(); j++) { v.push_back(a(i, j).real()); v.push_back(a(i, j).imag()); } };
+    auto coo = [&](const SprsC& a, int what) {
+        for (long j = 0; j < a.outerSize(); j++)
+            for (SprsC::InnerIterator it(a, j); it; ++it) {
+                if (what == 0) v.push_back(it.row());
+                else if (what == 1) v.push_back(it.col());
+                else { v.push_back(it.value().real()); v.push_back(it.value().imag()); }
+            }
+    };
+    if (k == "dims") v = {(double)m.nV, (double)m.nF, (double)m.nE, (double)m.nH, (double)m.nEularChars};
+    else if (k == "twin") ints(m.twin);
+    else if (k == "next") ints(m.next);
+    else if (k == "prev") ints(m.prev);
+    else if (k == "face") ints(m.face);
+    else if (k == "tail") ints(m.tail);
+    else if (k == "head") ints(m.head);
+    else if (k == "edge") ints(m.edge);
+    else if (k == "crnr") ints(m.crnr);
+    else if (k == "face2half") ints(m.face2half);
+    else if (k == "vert2half") ints(m.vert2half);
+    else if (k == "heArgOnFace") vecd(m.heArgOnFace);
+    else if (k == "faceArea") vecd(m.faceArea);
+    else if (k == "angleDefect") vecd(m.angleDefect);
+    else if (k == "dihedralArg") vecd(m.dihedralArg);
+    else if (k == "heLen") { for (const Half& hh : m.halfs) v.push_back(hh.len()); }
+    else if (k == "faceBasisX") matd(m.faceBasisX);
+    else if (k == "faceBasisY") matd(m.faceBasisY);
+    else if (k == "faceNormal") matd(m.faceNormal);
+    else if (k == "edge2face") mati(m.edge2face);
+    else if (k == "edge2vert") mati(m.edge2vert);
+    else if (k == "face2edge") mati(m.face2edge);
+    else if (k == "L_rows") coo(r.L, 0);
+    else if (k == "L_cols") coo(r.L, 1);
+    else if (k == "L_vals") coo(r.L, 2);
+    else if (k == "M_rows") coo(r.M, 0);
+    else if (k == "M_vals") coo(r.M, 2);
+    else if (k == "compressed") vecc(r.field->compressed);
+    else if (k == "field") matc(r.field->field);
+    else if (k == "connection") vecc(r.field->connection);
+    else if (k == "matching") veci(r.field->matching);
+    else if (k == "singular") veci(r.field->singular);
+    else if (k == "ext") matd(r.ext);
+    else if (k == "cfield" && r.combed) matc(r.combed->field);
+    else if (k == "cmatching" && r.combed) veci(r.combed->matching);
+    else return -1;
+    for (long i = 0; i < (long)v.size() && i < cap; i++) out[i] = v[i];
+    return (long)v.size();
 }
 
 }  // extern "C"

@@ -17,7 +17,14 @@
 //   * Matrix::Random() reads from refshim::random_source when the harness sets it (the reference's VecXc::Random is unseeded: u0 is an
 //     explicit input everywhere in this repository).
 #pragma once
+// frf.h:150 calls an unqualified abs() on doubles. With only <cmath> / <cstdlib>, libstdc++ leaves just the C `int abs(int)` in the global
+// namespace and the call silently truncates (seen: a principal matching of -1 instead of 3 on one edge); the reference's own toolchain (libc++,
+// typedef.h:10) and real Eigen put the floating-point overloads there. The C++ wrappers of these two headers do the same.
+#include <math.h>
+#include <stdlib.h>
+
 #include <algorithm>
+#include <cassert>
 #include <cmath>
 #include <complex>
 #include <cstdio>
@@ -28,6 +35,7 @@
 #include <limits>
 #include <memory>
 #include <numeric>
+#include <queue>
 #include <set>
 #include <type_traits>
 #include <vector>
@@ -80,6 +88,8 @@ struct ArrayX {
     std::vector<T> v;
     long r = 0, c = 0;
     ArrayX array() const { return *this; }
+    ArrayX square() const { ArrayX o = *this; for (auto& x : o.v) x = x * x; return o; }
+    friend ArrayX operator*(const ArrayX& a, const T& s) { ArrayX o = a; for (auto& x : o.v) x = x * s; return o; }
     ArrayX operator-() const { ArrayX o = *this; for (auto& x : o.v) x = -x; return o; }
     friend ArrayX operator*(const ArrayX& a, const ArrayX& b) { ArrayX o = a; for (size_t i = 0; i < o.v.size(); i++) o.v[i] = a.v[i] * b.v[i]; return o; }
     friend ArrayX operator/(const ArrayX& a, const ArrayX& b) { ArrayX o = a; for (size_t i = 0; i < o.v.size(); i++) o.v[i] = a.v[i] / b.v[i]; return o; }
@@ -123,6 +133,9 @@ public:
     Matrix(const Matrix<T, R2, C2>& o) { assign(o); }
     template <int R2, int C2>
     Matrix& operator=(const Matrix<T, R2, C2>& o) { assign(o); return *this; }
+    // real -> complex (VecXc connection = VecXd::Zero(n), frf.h:109): Eigen 3.3+ assigns across scalar types that convert
+    template <class T2, int R2, int C2, class = std::enable_if_t<!std::is_same<T2, T>::value && std::is_convertible<T2, T>::value>>
+    Matrix(const Matrix<T2, R2, C2>& o) { init_like(o.rows(), o.cols()); for (long i = 0; i < o.size(); i++) v_[i] = T(o(i)); }
     Matrix(const ArrayX<T>& a) { init_like(a.r, a.c); v_ = a.v; }
     Matrix(const Map<Matrix>& m);
 
@@ -133,6 +146,8 @@ public:
     const T* data() const { return v_.data(); }
     void resize(long n) { if (R == 1) init(1, n); else init(n, 1); }
     void resize(long r, long c) { init(r, c); }
+    void conservativeResize(long n) { if (R == 1) { r_ = 1; c_ = n; } else { r_ = n; c_ = 1; } v_.resize((size_t)n, T{}); }
+    Matrix eval() const { return *this; }
 
     T& operator()(long i) { return v_[i]; }
     const T& operator()(long i) const { return v_[i]; }
@@ -141,6 +156,8 @@ public:
     T& operator()(long i, long j) { return v_[(size_t)j * r_ + i]; }
     const T& operator()(long i, long j) const { return v_[(size_t)j * r_ + i]; }
 
+    static Matrix Zero() { Matrix m; std::fill(m.v_.begin(), m.v_.end(), T{}); return m; }
+    static Matrix Ones(long n) { Matrix m(n); std::fill(m.v_.begin(), m.v_.end(), T(1)); return m; }
     static Matrix Zero(long n) { Matrix m(n); std::fill(m.v_.begin(), m.v_.end(), T{}); return m; }
     static Matrix Zero(long r, long c) { Matrix m(r, c); std::fill(m.v_.begin(), m.v_.end(), T{}); return m; }
     static Matrix Constant(long n, const T& x) { Matrix m(n); std::fill(m.v_.begin(), m.v_.end(), x); return m; }
@@ -161,6 +178,32 @@ public:
         return m;
     }
     T maxCoeff() const { return *std::max_element(v_.begin(), v_.end()); }
+    Matrix normalized() const { const double n = norm(); Matrix o = *this; if (n > 0) for (auto& x : o.v_) x = x / n; return o; }
+    void normalize() { *this = normalized(); }
+    template <int R2, int C2>
+    Matrix cross(const Matrix<T, R2, C2>& b) const {
+        Matrix o = *this;
+        o.v_[0] = v_[1] * b(2) - v_[2] * b(1);
+        o.v_[1] = v_[2] * b(0) - v_[0] * b(2);
+        o.v_[2] = v_[0] * b(1) - v_[1] * b(0);
+        return o;
+    }
+    Matrix<T, C, R> adjoint() const {
+        Matrix<T, C, R> o(c_, r_);
+        for (long i = 0; i < r_; i++) for (long j = 0; j < c_; j++) o(j, i) = conj_((*this)(i, j));
+        return o;
+    }
+    // dense product (only small ones occur: row vector times column vector)
+    template <int R2, int C2>
+    Matrix<T, R, C2> operator*(const Matrix<T, R2, C2>& b) const {
+        Matrix<T, R, C2> o(r_, b.cols());
+        for (long i = 0; i < r_; i++) for (long j = 0; j < b.cols(); j++) { T acc{}; for (long k = 0; k < c_; k++) acc += (*this)(i, k) * b(k, j); o(i, j) = acc; }
+        return o;
+    }
+    template <int R2, int C2>
+    Matrix& operator+=(const Matrix<T, R2, C2>& b) { for (long i = 0; i < size(); i++) v_[i] += b(i); return *this; }
+    template <int R2, int C2>
+    Matrix& operator-=(const Matrix<T, R2, C2>& b) { for (long i = 0; i < size(); i++) v_[i] -= b(i); return *this; }
     // x.dot(y) = sum conj(x_i) y_i
     template <int R2, int C2>
     T dot(const Matrix<T, R2, C2>& o) const {
@@ -174,11 +217,26 @@ public:
     DynVec head(long n) const { return segment(0, n); }
     DynVec tail(long n) const { return segment(size() - n, n); }
 
+    using RowVec = Matrix<T, 1, Dynamic>;
+    struct RowRef;
+    struct RowArr {  // m.row(i).array()
+        Matrix* m;
+        long i;
+        RowArr& operator+=(const ArrayX<T>& a) { for (long j = 0; j < m->c_; j++) (*m)(i, j) += a.v[j]; return *this; }
+        ArrayX<T> operator*(const T& s) const { ArrayX<T> a; a.r = 1; a.c = m->c_; for (long j = 0; j < m->c_; j++) a.v.push_back((*m)(i, j) * s); return a; }
+    };
     struct RowRef {
         Matrix* m;
         long i;
         template <int R2, int C2>
         RowRef& operator=(const Matrix<T, R2, C2>& o) { for (long j = 0; j < m->c_; j++) (*m)(i, j) = o(j); return *this; }
+        RowVec vec() const { RowVec v(m->c_); for (long j = 0; j < m->c_; j++) v(j) = (*m)(i, j); return v; }
+        template <int R2, int C2>
+        operator Matrix<T, R2, C2>() const { return Matrix<T, R2, C2>(vec()); }
+        T& operator[](long j) { return (*m)(i, j); }
+        RowArr array() { return RowArr{m, i}; }
+        friend RowVec operator-(const RowRef& a, const RowRef& b) { return a.vec() - b.vec(); }
+        friend RowVec operator+(const RowRef& a, const RowRef& b) { return a.vec() + b.vec(); }
         CommaInit<T> operator<<(const T& s) {
             Matrix* mm = m; long ii = i;
             CommaInit<T> ci([mm, ii](long k) -> T& { return (*mm)(ii, k); }, m->c_);
@@ -187,6 +245,36 @@ public:
         }
     };
     RowRef row(long i) { return RowRef{this, i}; }
+    RowVec row(long i) const { RowVec v(c_); for (long j = 0; j < c_; j++) v(j) = (*this)(i, j); return v; }
+    struct RowwiseRef {
+        Matrix* m;
+        void normalize() {
+            for (long i = 0; i < m->r_; i++) {
+                double n = 0;
+                for (long j = 0; j < m->c_; j++) n += abs2_((*m)(i, j));
+                n = std::sqrt(n);
+                if (n > 0) for (long j = 0; j < m->c_; j++) (*m)(i, j) = (*m)(i, j) / n;
+            }
+        }
+    };
+    RowwiseRef rowwise() { return RowwiseRef{this}; }
+    using DynMat = Matrix<T, Dynamic, Dynamic>;
+    struct BlockRef {
+        Matrix* m;
+        long i0, j0, nr, nc;
+        template <int R2, int C2>
+        BlockRef& operator=(const Matrix<T, R2, C2>& o) {  // a vector fills a 1 x n / n x 1 block in order
+            const bool vec = o.rows() == 1 || o.cols() == 1;
+            for (long j = 0; j < nc; j++) for (long i = 0; i < nr; i++) (*m)(i0 + i, j0 + j) = vec ? o(j * nr + i) : o(i, j);
+            return *this;
+        }
+    };
+    BlockRef block(long i0, long j0, long nr, long nc) { return BlockRef{this, i0, j0, nr, nc}; }
+    DynMat block(long i0, long j0, long nr, long nc) const {
+        DynMat o(nr, nc);
+        for (long j = 0; j < nc; j++) for (long i = 0; i < nr; i++) o(i, j) = (*this)(i0 + i, j0 + j);
+        return o;
+    }
 
     CommaInit<T> operator<<(const T& s) {
         CommaInit<T> ci(filler(), size());
@@ -269,6 +357,7 @@ using RowVector3i = Matrix<int, 1, 3>;
 using RowVector3d = Matrix<double, 1, 3>;
 using Matrix2i = Matrix<int, 2, 2>;
 using Matrix2d = Matrix<double, 2, 2>;
+using MatrixXcd = Matrix<std::complex<double>, Dynamic, Dynamic>;
 
 // compressed sparse matrix, default (column-major) storage order only -- the only one the cited headers use
 template <class T, int Options = ColMajor>
@@ -396,6 +485,29 @@ public:
             Cm.outer_[j + 1] = (int)Cm.inner_.size();
         }
         return Cm;
+    }
+    void setIdentity() {
+        outer_.assign(cols_ + 1, 0); inner_.clear(); val_.clear();
+        for (int j = 0; j < cols_; j++) { if (j < rows_) { inner_.push_back(j); val_.push_back(T(1)); } outer_[j + 1] = (int)inner_.size(); }
+    }
+    static SparseMatrix combine(const SparseMatrix& A, const SparseMatrix& B, bool minus) {
+        std::vector<Triplet<T>> t;
+        for (int j = 0; j < A.cols_; j++) for (int k = A.outer_[j]; k < A.outer_[j + 1]; k++) t.emplace_back(A.inner_[k], j, A.val_[k]);
+        for (int j = 0; j < B.cols_; j++) for (int k = B.outer_[j]; k < B.outer_[j + 1]; k++) t.emplace_back(B.inner_[k], j, minus ? -B.val_[k] : B.val_[k]);
+        SparseMatrix o(A.rows_, A.cols_);
+        o.setFromTriplets(t.begin(), t.end());
+        return o;
+    }
+    friend SparseMatrix operator+(const SparseMatrix& A, const SparseMatrix& B) { return combine(A, B, false); }
+    friend SparseMatrix operator-(const SparseMatrix& A, const SparseMatrix& B) { return combine(A, B, true); }
+    // real scalar times a complex matrix (1e-9 * I, lambda * M: frf.h:28,75)
+    template <class S, class = std::enable_if_t<!std::is_same<S, T>::value && std::is_arithmetic<S>::value>>
+    friend SparseMatrix operator*(const S& s, const SparseMatrix& A) { SparseMatrix o = A; for (auto& x : o.val_) x = x * (double)s; return o; }
+    // row vector times sparse matrix
+    friend Matrix<T, 1, Dynamic> operator*(const Matrix<T, 1, Dynamic>& x, const SparseMatrix& A) {
+        Matrix<T, 1, Dynamic> y(A.cols_);
+        for (int j = 0; j < A.cols_; j++) { T acc{}; for (int k = A.outer_[j]; k < A.outer_[j + 1]; k++) acc += x(A.inner_[k]) * A.val_[k]; y(j) = acc; }
+        return y;
     }
     friend SparseMatrix operator*(const SparseMatrix& A, const T& s) { SparseMatrix o = A; for (auto& x : o.val_) x = x * s; return o; }
     friend SparseMatrix operator*(const T& s, const SparseMatrix& A) { SparseMatrix o = A; for (auto& x : o.val_) x = s * x; return o; }

@@ -32,6 +32,26 @@ def test_field_golden_agrees_with_reference_inverse_iteration(name):
 
 
 @pytest.mark.parametrize("name", CASES)
+def test_field_golden_agrees_with_reference_face_rosy_field(name):
+    """The reference's Hmesh(V, F) (hmesh.h:313-569) and FaceRosyField(mesh, 4, Smoothest) + computeMatching(Curl) + compute_combbed_field
+    (frf.h:17-249), run from the mesh and u0 alone, against what the goldens hold: the half-edge arrays and per-half angles the CUDA assembly
+    kernel is fed with (host glue), the oracle-assembled L, the 50th iterate, the singularities; and against the host glue's matching / combing."""
+    g, r = load_golden(name), _ref(name)
+    for k in ("twin", "next", "face", "face2half"):
+        assert np.array_equal(r["frf_" + k], g[k]), k
+    assert np.array_equal(r["frf_heArgOnFace"], g["heArgOnFace"]) and np.array_equal(r["frf_faceArea"], g["faceArea"])  # bit for bit
+    nF = len(g["faceArea"])
+    L = oracle.connection_laplacian(g["twin"], g["face"], g["heArgOnFace"], nF, 4)
+    Lr = sp.csr_matrix((r["frf_L_vals"], (r["frf_L_rows"], r["frf_L_cols"])), shape=(nF, nF))
+    assert abs(Lr - L).max() <= 1e-14 and Lr.nnz == L.nnz == 4 * nF
+    assert np.abs(r["frf_compressed"] - g["z50"]).max() <= 1e-12
+    assert np.abs(r["frf_field"].reshape(nF, 4) - oracle.decode_field(g["z50"], 4)).max() <= 1e-12  # frf.h:37-43
+    assert np.array_equal(r["frf_singular"], g["singular"])
+    assert np.array_equal(r["frf_matching"], r["hostglue_matching"]) and np.array_equal(r["frf_cmatching"], r["hostglue_cmatching"])
+    assert np.abs(r["frf_cfield"] - r["hostglue_cfield"]).max() <= 1e-12
+
+
+@pytest.mark.parametrize("name", CASES)
 def test_igm_golden_agrees_with_reference_iterative_rounding(name):
     g, r = load_golden(name), _ref(name)
     assert int(r["success"]) == 1
@@ -122,6 +142,41 @@ def small_sphere():
 def small_torus():
     from hostglue import Session
     return _igm_inputs(Session().make_torus(16, 12, bump=0.1), 7)
+
+
+@pytest.mark.parametrize("matching", ("curl", "principal"))
+@pytest.mark.parametrize("mesh", ("sphere", "torus"))
+def test_live_face_rosy_field(R, mesh, matching):
+    """Hmesh + FaceRosyField + computeMatching + compute_combbed_field + compute_extrinsic_field of the reference against the host glue (the
+    input generator of every test and of bench.py) and the oracle, on meshes no fixture holds."""
+    from hostglue import Session
+    s = Session().make_sphere(4, 3, bump=0.1, phase=1.1) if mesh == "sphere" else Session().make_torus(20, 14, bump=0.12, phase=0.4)
+    fi = s.field_inputs()
+    nF = s.dims["nF"]
+    u0 = oracle.random_u0(nF, 11)
+    L = oracle.connection_laplacian(fi["twin"], fi["face"], fi["heArgOnFace"], nF, 4)
+    z = oracle.solve_smallest_eig(L, oracle.galerkin_mass_matrix(fi["faceArea"]), u0, 50)
+    s.field_post(z, 4, matching)
+    r = R.face_rosy_field(s.get("pos"), s.get("idx"), 4, u0, matching, seam=s.get("seam"))
+    assert list(r["dims"]) == [s.dims[k] for k in ("nV", "nF", "nE", "nH", "euler")]
+    for k in ("twin", "next", "prev", "face", "tail", "head", "edge", "crnr", "face2half", "vert2half", "edge2face", "edge2vert", "face2edge"):
+        assert np.array_equal(r[k], s.get(k).reshape(-1)), k
+    for k in ("heArgOnFace", "faceArea", "angleDefect", "heLen", "faceBasisX", "faceBasisY", "faceNormal"):
+        assert np.array_equal(r[k], s.get(k).reshape(-1)), k
+    assert np.abs(r["dihedralArg"] - s.get("dihedralArg")).max() <= 1e-15
+    Lr = sp.csr_matrix((r["L_vals"], (r["L_rows"], r["L_cols"])), shape=(nF, nF))
+    assert abs(Lr - L).max() <= 1e-14
+    assert np.array_equal(r["M_vals"].real, fi["faceArea"]) and np.array_equal(r["M_rows"], np.arange(nF))
+    assert np.abs(r["compressed"] - z).max() <= 1e-12
+    for k in ("matching", "singular", "cmatching"):
+        assert np.array_equal(r[k], s.get(k)), k
+    assert r["singular"].sum() == 4 * s.dims["euler"]  # sum of the indices = N chi (frf.h:100-107)
+    assert np.abs(r["field"] - s.get("field").reshape(-1)).max() <= 1e-12 and np.abs(r["cfield"] - s.get("cfield").reshape(-1)).max() <= 1e-12
+    f = r["field"].reshape(nF, 4)
+    X, Y = s.get("faceBasisX").reshape(nF, 3), s.get("faceBasisY").reshape(nF, 3)
+    ext = f.real[:, :, None] * X[:, None, :] + f.imag[:, :, None] * Y[:, None, :]  # frf.h:251-264
+    ext /= np.linalg.norm(ext, axis=2, keepdims=True)
+    assert np.abs(r["ext"] - ext.reshape(-1)).max() <= 1e-14
 
 
 def test_live_inverse_iteration(R, small_sphere):
