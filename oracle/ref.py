@@ -152,12 +152,16 @@ class Ref:
 
 
     _INT = ("twin", "next", "prev", "face", "tail", "head", "edge", "crnr", "face2half", "vert2half", "edge2face", "edge2vert", "face2edge", "matching",
-            "singular", "cmatching", "dims", "L_rows", "L_cols", "M_rows")
+            "singular", "cmatching", "dims", "L_rows", "L_cols", "M_rows", "cutF", "fixedIdcs", "integerIdcs", "singularIdcs", "he2matching", "he2transidx",
+            "vtrans2cut_shape", "vtrans2cut_rows", "vtrans2cut_cols", "uncompress_shape", "uncompress_rows", "uncompress_cols", "constraint_shape",
+            "constraint_rows", "constraint_cols")
     _CPLX = ("L_vals", "M_vals", "compressed", "field", "connection", "cfield")
 
-    def face_rosy_field(self, V, F, N, u0, matching="curl", seam=None, names=None):
+    def face_rosy_field(self, V, F, N, u0, matching="curl", seam=None, names=None, parameterize=None):
         """Hmesh(V, F) (hmesh.h:313-569) + FaceRosyField(mesh, N, Smoothest) (frf.h:17-44) + computeMatching (frf.h:100-202) [+ the combed field
-        (frf.h:207-249) when a seam is given] run by the reference's own code; returns the requested arrays (default: all)."""
+        (frf.h:207-249) when a seam is given] run by the reference's own code; returns the requested arrays (default: all).
+        parameterize = dict(gridscale, seamless, localInjectivity, roundSeams): the rest of example_igm.cpp:17-33 as well (compute_cut_mesh,
+        RosyParameterization, setup(), integ()): adds integ_ok, fullx, nfn, cfn, the index lists and setup()'s matrices."""
         V = np.ascontiguousarray(V, np.float64).reshape(-1, 3)
         F = np.ascontiguousarray(F, np.int32).reshape(-1, 3)
         u0 = np.ascontiguousarray(u0, np.complex128)
@@ -173,6 +177,12 @@ class Ref:
                      "L_cols", "L_vals", "M_rows", "M_vals", "compressed", "field", "connection", "matching", "singular", "ext") + \
                     (("cfield", "cmatching") if seam is not None else ())
         out = {}
+        if parameterize is not None:
+            assert seam is not None
+            out["integ_ok"] = int(self.L.ref_field_parameterize(h, C.c_double(parameterize.get("gridscale", 0.02)), int(parameterize.get("seamless", True)),
+                                                               int(parameterize.get("localInjectivity", False)), int(parameterize.get("roundSeams", False))))
+            all_names += ("cext", "cutF", "cutPos", "fullx", "nfn", "cfn", "fixedIdcs", "fixedVals", "integerIdcs", "singularIdcs", "he2matching",
+                          "he2transidx") + tuple(f"{m}_{w}" for m in ("vtrans2cut", "uncompress", "constraint") for w in ("shape", "rows", "cols", "vals"))
         try:
             for k in (names or all_names):
                 n = self.L.ref_field_get(h, k.encode(), C.c_long(0), C.POINTER(C.c_double)())

@@ -13,11 +13,16 @@
 //                            FaceRosyField(mesh, N, FieldType::Smoothest) (vectorfield/face_rosy_field.h:17-44: connectionLaplacian frf.h:46-76,
 //                            galerkinMassMatrix frf.h:78-84, solveSmallestEig, decode frf.h:37-43), computeMatching (frf.h:100-202),
 //                            compute_combbed_field (frf.h:207-249, seam given), compute_extrinsic_field (frf.h:251-264)
+//   ref_field_parameterize   the rest of example/example_igm.cpp:17-33 on that field: compute_cut_mesh (param.h:126-152), RosyParameterization's
+//                            constructor (compute_he2transidx / compute_he2matching, setup.ipp:3-50), setup() (setup.ipp:52-170), integ()
+//                            (integ.ipp:3-121: G2, rawF2Vec, locally_injectivity_check, iterative_rounding, nfn / cfn). compute_seam (frf.h:268-360)
+//                            is libigl's cut graph + Dijkstra and is NOT compiled: the seam is an input
 #include <cstring>
 
 #include "metriko/core/igm/iterative_rounding/iter_rounding.h"
 #include "metriko/core/solver/sparse_linear_solver.h"
 #include "metriko/core/vectorfield/face_rosy_field.h"
+#include "metriko/core/igm/parameterization.h"
 
 using namespace metriko;
 
@@ -153,7 +158,11 @@ struct RefField {
     std::unique_ptr<Hmesh> mesh;
     std::unique_ptr<FaceRosyField> field, combed;
     SprsC L, M;
-    MatXd ext;
+    MatXd ext, cext;
+    std::vector<bool> seam;
+    std::unique_ptr<Hmesh> cut;
+    std::unique_ptr<RosyParameterization> rp;
+    int integ_ok = -1;
 };
 
 // V[3 nV] and F[3 nF] row-major. u0: 2 nF doubles for VecXc::Random. matching_type 0 = Principal, 1 = Curl. seam[nE] (0 / 1) or null: with a
@@ -177,8 +186,25 @@ void* ref_field_create(int nV, const double* V, int nF, const int* F, int N, con
         std::vector<bool> sm(r->mesh->nE);
         for (int e = 0; e < r->mesh->nE; e++) sm[e] = seam[e] != 0;
         r->combed = compute_combbed_field(*r->field, sm);
+        r->seam = sm;
     }
     return r;
+}
+
+// example_igm.cpp:17-33 from `auto cutm = compute_cut_mesh(*mesh, seam)` on. Needs a handle created with a seam. Returns integ()'s bool.
+int ref_field_parameterize(void* h, double gridscale, int seamless, int localInjectivity, int roundSeams) {
+    RefField& r = *static_cast<RefField*>(h);
+    if (!r.combed) return -1;
+    r.cut = compute_cut_mesh(*r.mesh, r.seam);
+    r.cext = compute_extrinsic_field(*r.mesh, *r.combed, r.field->rosyN);
+    r.rp = std::make_unique<RosyParameterization>(*r.mesh, *r.cut, r.cext, r.combed->singular, r.combed->matching, r.seam, r.field->rosyN, gridscale);
+    r.rp->seamless = seamless != 0;
+    r.rp->localInjectivity = localInjectivity != 0;
+    r.rp->roundSeams = roundSeams != 0;
+    r.rp->verbose = false;
+    r.rp->setup();
+    r.integ_ok = r.rp->integ() ? 1 : 0;
+    return r.integ_ok;
 }
 
 void ref_field_destroy(void* h) { delete static_cast<RefField*>(h); }
@@ -239,6 +265,25 @@ long ref_field_get(void* h, const char* name, long cap, double* out) {
     else if (k == "ext") matd(r.ext);
     else if (k == "cfield" && r.combed) matc(r.combed->field);
     else if (k == "cmatching" && r.combed) veci(r.combed->matching);
+    else if (k == "cext" && r.rp) matd(r.cext);
+    else if (k == "cutF" && r.cut) mati(r.cut->idx);
+    else if (k == "cutPos" && r.cut) matd(r.cut->pos);
+    else if (k == "fullx" && r.rp) vecd(r.rp->fullx);
+    else if (k == "nfn" && r.rp) matd(r.rp->nfn);
+    else if (k == "cfn" && r.rp) matd(r.rp->cfn);
+    else if (k == "fixedIdcs" && r.rp) veci(r.rp->fixedIdcs);
+    else if (k == "fixedVals" && r.rp) vecd(r.rp->fixedVals);
+    else if (k == "integerIdcs" && r.rp) veci(r.rp->integerIdcs);
+    else if (k == "singularIdcs" && r.rp) veci(r.rp->singularIdcs);
+    else if (k == "he2matching" && r.rp) veci(r.rp->he2matching);
+    else if (k == "he2transidx" && r.rp) veci(r.rp->he2transidx);
+    else if (r.rp && (k.rfind("vtrans2cut_", 0) == 0 || k.rfind("uncompress_", 0) == 0 || k.rfind("constraint_", 0) == 0)) {
+        const SprsD& a = k[0] == 'v' ? r.rp->vtrans2cut : (k[0] == 'u' ? r.rp->uncompress : r.rp->constraint);
+        const std::string what = k.substr(k.find('_') + 1);
+        if (what == "shape") v = {(double)a.rows(), (double)a.cols()};
+        else for (long j = 0; j < a.outerSize(); j++)
+            for (SprsD::InnerIterator it(a, j); it; ++it) v.push_back(what == "rows" ? it.row() : what == "cols" ? it.col() : it.value());
+    }
     else return -1;
     for (long i = 0; i < (long)v.size() && i < cap; i++) out[i] = v[i];
     return (long)v.size();

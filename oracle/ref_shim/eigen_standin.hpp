@@ -13,7 +13,8 @@
 //     oracle uses as well) -- Eigen's own factorisations are absent from the image, any direct solver is a stand-in;
 //   * FullPivLU follows Eigen 3.4's complete pivoting (first maximum in column-major order, rank threshold eps * diagSize * |maxpivot|,
 //     kernel = P_c [-U1^{-1} U2; I]) so that UFull comes out with Eigen's column choice;
-//   * SparseQR (matrix_ops.h:13-30, called from setup(), not on this path) only has to compile: it aborts when run;
+//   * SparseQR (reduce_to_linearly_independent, matrix_ops.h:12-30) picks independent columns in natural order (not COLAMD / Householder):
+//     an equivalent set of constraint rows, the same one tests/hostglue picks;
 //   * Matrix::Random() reads from refshim::random_source when the harness sets it (the reference's VecXc::Random is unseeded: u0 is an
 //     explicit input everywhere in this repository).
 #pragma once
@@ -88,6 +89,7 @@ struct ArrayX {
     std::vector<T> v;
     long r = 0, c = 0;
     ArrayX array() const { return *this; }
+    ArrayX& operator/=(const T& s) { for (auto& x : v) x = x / s; return *this; }
     ArrayX square() const { ArrayX o = *this; for (auto& x : o.v) x = x * x; return o; }
     friend ArrayX operator*(const ArrayX& a, const T& s) { ArrayX o = a; for (auto& x : o.v) x = x * s; return o; }
     ArrayX operator-() const { ArrayX o = *this; for (auto& x : o.v) x = -x; return o; }
@@ -95,21 +97,33 @@ struct ArrayX {
     friend ArrayX operator/(const ArrayX& a, const ArrayX& b) { ArrayX o = a; for (size_t i = 0; i < o.v.size(); i++) o.v[i] = a.v[i] / b.v[i]; return o; }
 };
 
-// `m << a, b, c;` -- coefficients in row-major order (vectors: in order); vector arguments append all their coefficients
+// `m << a, b, c;` -- Eigen's comma initializer: scalars and blocks are placed left to right, a full row of blocks moves the cursor down by the
+// block height; vector targets take vector arguments coefficient by coefficient whatever their orientation
 template <class T>
 class CommaInit {
 public:
-    CommaInit(std::function<T&(long)> at, long cap) : at_(std::move(at)), cap_(cap) {}
+    CommaInit(std::function<T&(long, long)> at, long rows, long cols) : at_(std::move(at)), rows_(rows), cols_(cols) {}
     CommaInit& operator,(const T& s) { put(s); return *this; }
     template <int R2, int C2>
-    CommaInit& operator,(const Matrix<T, R2, C2>& m) { for (long i = 0; i < m.size(); i++) put(m(i)); return *this; }
+    CommaInit& operator,(const Matrix<T, R2, C2>& m) { put_block(m); return *this; }
     void put(const T& s) {
-        if (k_ >= cap_) { std::fprintf(stderr, "eigen_standin: comma initializer overflow\n"); std::abort(); }
-        at_(k_++) = s;
+        wrap(1);
+        check(row_, col_);
+        at_(row_, col_++) = s;
+    }
+    template <int R2, int C2>
+    void put_block(const Matrix<T, R2, C2>& m) {
+        const bool target_vec = rows_ == 1 || cols_ == 1, arg_vec = m.rows() == 1 || m.cols() == 1;
+        if (target_vec && arg_vec) { for (long i = 0; i < m.size(); i++) { if (cols_ == 1) { wrap(1); check(row_, 0); at_(row_, 0) = m(i); col_ = 1; } else put(m(i)); } return; }
+        wrap(m.rows());
+        for (long i = 0; i < m.rows(); i++) for (long j2 = 0; j2 < m.cols(); j2++) { check(row_ + i, col_ + j2); at_(row_ + i, col_ + j2) = m(i, j2); }
+        col_ += m.cols();
     }
 private:
-    std::function<T&(long)> at_;
-    long cap_, k_ = 0;
+    void wrap(long next_block_rows) { if (col_ >= cols_) { row_ += block_rows_; col_ = 0; } if (col_ == 0) block_rows_ = next_block_rows; }
+    void check(long i, long j2) const { if (i >= rows_ || j2 >= cols_) { std::fprintf(stderr, "eigen_standin: comma initializer overflow\n"); std::abort(); } }
+    std::function<T&(long, long)> at_;
+    long rows_, cols_, row_ = 0, col_ = 0, block_rows_ = 1;
 };
 
 template <class T, int R, int C>
@@ -237,17 +251,19 @@ public:
         RowArr array() { return RowArr{m, i}; }
         friend RowVec operator-(const RowRef& a, const RowRef& b) { return a.vec() - b.vec(); }
         friend RowVec operator+(const RowRef& a, const RowRef& b) { return a.vec() + b.vec(); }
-        CommaInit<T> operator<<(const T& s) {
-            Matrix* mm = m; long ii = i;
-            CommaInit<T> ci([mm, ii](long k) -> T& { return (*mm)(ii, k); }, m->c_);
-            ci.put(s);
-            return ci;
-        }
+        CommaInit<T> comma() { Matrix* mm = m; long ii = i; return CommaInit<T>([mm, ii](long, long k) -> T& { return (*mm)(ii, k); }, 1, m->c_); }
+        CommaInit<T> operator<<(const T& s) { CommaInit<T> ci = comma(); ci.put(s); return ci; }
+        template <int R2, int C2>
+        CommaInit<T> operator<<(const Matrix<T, R2, C2>& o) { CommaInit<T> ci = comma(); ci.put_block(o); return ci; }
+        template <int R2, int C2>
+        Matrix<T, R2, C2> cast_() const { return Matrix<T, R2, C2>(vec()); }
+        RowVec segment(long o, long n) const { return vec().segment(o, n); }
     };
     RowRef row(long i) { return RowRef{this, i}; }
     RowVec row(long i) const { RowVec v(c_); for (long j = 0; j < c_; j++) v(j) = (*this)(i, j); return v; }
     struct RowwiseRef {
         Matrix* m;
+        Matrix<T, Dynamic, 1> sum() const { Matrix<T, Dynamic, 1> o(m->r_); for (long i = 0; i < m->r_; i++) { T a{}; for (long j = 0; j < m->c_; j++) a += (*m)(i, j); o(i) = a; } return o; }
         void normalize() {
             for (long i = 0; i < m->r_; i++) {
                 double n = 0;
@@ -258,10 +274,51 @@ public:
         }
     };
     RowwiseRef rowwise() { return RowwiseRef{this}; }
+    struct RowwiseConst {
+        const Matrix* m;
+        Matrix<T, Dynamic, 1> sum() const { Matrix<T, Dynamic, 1> o(m->r_); for (long i = 0; i < m->r_; i++) { T a{}; for (long j = 0; j < m->c_; j++) a += (*m)(i, j); o(i) = a; } return o; }
+    };
+    RowwiseConst rowwise() const { return RowwiseConst{this}; }
+    struct ColwiseConst {
+        const Matrix* m;
+        RowVec maxCoeff() const { RowVec o(m->c_); for (long j = 0; j < m->c_; j++) { T a = (*m)(0, j); for (long i = 1; i < m->r_; i++) a = std::max(a, (*m)(i, j)); o(j) = a; } return o; }
+        RowVec minCoeff() const { RowVec o(m->c_); for (long j = 0; j < m->c_; j++) { T a = (*m)(0, j); for (long i = 1; i < m->r_; i++) a = std::min(a, (*m)(i, j)); o(j) = a; } return o; }
+    };
+    ColwiseConst colwise() const { return ColwiseConst{this}; }
+    template <int R2, int C2>
+    Matrix cwiseProduct(const Matrix<T, R2, C2>& b) const { Matrix o = *this; for (long j = 0; j < c_; j++) for (long i = 0; i < r_; i++) o(i, j) = (*this)(i, j) * b(i, j); return o; }
+    Matrix cwiseAbs() const { Matrix o = *this; for (auto& x : o.v_) x = x < T{} ? -x : x; return o; }
+    Matrix<T, C, R> transpose() const { Matrix<T, C, R> o(c_, r_); for (long i = 0; i < r_; i++) for (long j = 0; j < c_; j++) o(j, i) = (*this)(i, j); return o; }
+    template <int Order>
+    Matrix<T, Dynamic, 1> reshaped() const {  // Order = RowMajor: the coefficients row by row
+        Matrix<T, Dynamic, 1> o(size());
+        long k = 0;
+        if (Order == RowMajor) { for (long i = 0; i < r_; i++) for (long j = 0; j < c_; j++) o(k++) = (*this)(i, j); }
+        else { for (long j = 0; j < c_; j++) for (long i = 0; i < r_; i++) o(k++) = (*this)(i, j); }
+        return o;
+    }
+    static Matrix Identity(long r, long c) { Matrix m(r, c); for (long i = 0; i < std::min(r, c); i++) m(i, i) = T(1); return m; }
+    void setConstant(const T& x) { std::fill(v_.begin(), v_.end(), x); }
+    void setZero() { std::fill(v_.begin(), v_.end(), T{}); }
+    T& x() { return v_[0]; }
+    T& y() { return v_[1]; }
+    T& z() { return v_[2]; }
+    const T& x() const { return v_[0]; }
+    const T& y() const { return v_[1]; }
+    const T& z() const { return v_[2]; }
     using DynMat = Matrix<T, Dynamic, Dynamic>;
     struct BlockRef {
         Matrix* m;
         long i0, j0, nr, nc;
+        DynMat mat() const { DynMat o(nr, nc); for (long j = 0; j < nc; j++) for (long i = 0; i < nr; i++) o(i, j) = (*m)(i0 + i, j0 + j); return o; }
+        template <int R2, int C2>
+        operator Matrix<T, R2, C2>() const { return Matrix<T, R2, C2>(mat()); }
+        DynMat operator-() const { return -mat(); }
+        BlockRef& operator=(const RowArr& a) { for (long j = 0; j < nc; j++) (*m)(i0, j0 + j) = (*a.m)(a.i, j); return *this; }
+        CommaInit<T> comma() { Matrix* mm = m; long a = i0, b = j0; return CommaInit<T>([mm, a, b](long i, long j) -> T& { return (*mm)(a + i, b + j); }, nr, nc); }
+        CommaInit<T> operator<<(const T& s) { CommaInit<T> ci = comma(); ci.put(s); return ci; }
+        template <int R2, int C2>
+        CommaInit<T> operator<<(const Matrix<T, R2, C2>& o) { CommaInit<T> ci = comma(); ci.put_block(o); return ci; }
         template <int R2, int C2>
         BlockRef& operator=(const Matrix<T, R2, C2>& o) {  // a vector fills a 1 x n / n x 1 block in order
             const bool vec = o.rows() == 1 || o.cols() == 1;
@@ -270,23 +327,18 @@ public:
         }
     };
     BlockRef block(long i0, long j0, long nr, long nc) { return BlockRef{this, i0, j0, nr, nc}; }
+    BlockRef middleCols(long j0, long nc) { return BlockRef{this, 0, j0, r_, nc}; }
+    DynMat middleCols(long j0, long nc) const { return block(0, j0, r_, nc); }
     DynMat block(long i0, long j0, long nr, long nc) const {
         DynMat o(nr, nc);
         for (long j = 0; j < nc; j++) for (long i = 0; i < nr; i++) o(i, j) = (*this)(i0 + i, j0 + j);
         return o;
     }
 
-    CommaInit<T> operator<<(const T& s) {
-        CommaInit<T> ci(filler(), size());
-        ci.put(s);
-        return ci;
-    }
+    CommaInit<T> comma() { Matrix* m = this; return CommaInit<T>([m](long i, long j) -> T& { return (*m)(i, j); }, r_, c_); }
+    CommaInit<T> operator<<(const T& s) { CommaInit<T> ci = comma(); ci.put(s); return ci; }
     template <int R2, int C2>
-    CommaInit<T> operator<<(const Matrix<T, R2, C2>& o) {
-        CommaInit<T> ci(filler(), size());
-        ci, o;
-        return ci;
-    }
+    CommaInit<T> operator<<(const Matrix<T, R2, C2>& o) { CommaInit<T> ci = comma(); ci.put_block(o); return ci; }
 
     ArrayX<T> array() const { ArrayX<T> a; a.v = v_; a.r = r_; a.c = c_; return a; }
 
@@ -325,11 +377,6 @@ private:
     }
     template <int R2, int C2>
     void assign(const Matrix<T, R2, C2>& o) { init_like(o.r_, o.c_); v_ = o.v_; }
-    std::function<T&(long)> filler() {
-        Matrix* m = this;
-        if (kIsVector || c_ == 1 || r_ == 1) return [m](long k) -> T& { return m->v_[k]; };
-        return [m](long k) -> T& { return (*m)(k / m->c_, k % m->c_); };
-    }
     long r_ = 0, c_ = 0;
     std::vector<T> v_;
 };
@@ -445,6 +492,8 @@ public:
         }
         return Rm;
     }
+
+    void prune(const T& ref, double eps = 1e-12) { *this = pruned(ref, eps); }
 
     SparseMatrix transpose() const {
         SparseMatrix Tm(cols_, rows_);
@@ -566,7 +615,11 @@ template <class M> using SparseLU = HookedSolver<M, 0>;
 template <class M> using SimplicialLLT = HookedSolver<M, 1>;
 template <class M> using SimplicialLDLT = HookedSolver<M, 1>;
 
-// matrix_ops.h:13-30 (reduce_to_linearly_independent, called from setup(): not on this path) has to compile, not to run
+// SparseQR<.., COLAMDOrdering> as reduce_to_linearly_independent uses it (matrix_ops.h:12-30, called by integ(), integ.ipp:6): rank() and a
+// column permutation whose first rank() entries are independent columns. NOT Eigen's algorithm (COLAMD + Householder with a pivot threshold):
+// columns are taken in their natural order by Gram-Schmidt with the relative tolerance 1e-9, which is what tests/hostglue/igm_glue.hpp's
+// independent_rows does. Another valid choice of independent constraint rows spans the same row space: UFull's kernel space and fullx are
+// the same, its basis (and x_small) may differ from an Eigen build's. UNPINNED, stated as such in DESIGN.md.
 template <class I>
 struct COLAMDOrdering {};
 template <class M, class O>
@@ -576,11 +629,40 @@ public:
         VectorXi idx;
         const VectorXi& indices() const { return idx; }
     };
-    void compute(const M&) { std::fprintf(stderr, "eigen_standin: SparseQR is not implemented (not on the hot path)\n"); std::abort(); }
-    int rank() const { return 0; }
+    void compute(const M& A) {
+        const long n = A.cols(), m = A.rows();
+        std::vector<std::vector<double>> basis;
+        std::vector<int> keep, drop;
+        for (long j = 0; j < n; j++) {
+            std::vector<double> r(m, 0.0);
+            for (typename M::InnerIterator it(A, j); it; ++it) r[it.row()] = it.value();
+            double n0 = 0;
+            for (double x : r) n0 += x * x;
+            n0 = std::sqrt(n0);
+            if (n0 == 0) { drop.push_back((int)j); continue; }
+            for (int pass = 0; pass < 2; pass++)
+                for (const auto& b : basis) {
+                    double d = 0;
+                    for (long k = 0; k < m; k++) d += r[k] * b[k];
+                    for (long k = 0; k < m; k++) r[k] -= d * b[k];
+                }
+            double n1 = 0;
+            for (double x : r) n1 += x * x;
+            n1 = std::sqrt(n1);
+            if (n1 > 1e-9 * n0) { for (double& x : r) x /= n1; basis.push_back(r); keep.push_back((int)j); }
+            else drop.push_back((int)j);
+        }
+        rank_ = (int)keep.size();
+        perm_.idx.resize(n);
+        long k = 0;
+        for (int c : keep) perm_.idx(k++) = c;
+        for (int c : drop) perm_.idx(k++) = c;
+    }
+    int rank() const { return rank_; }
     const Perm& colsPermutation() const { return perm_; }
 private:
     Perm perm_;
+    int rank_ = 0;
 };
 
 // Eigen 3.4 FullPivLU: complete pivoting, the first maximum in column-major order wins; rank counts |pivot| > eps * diagSize * |maxpivot|

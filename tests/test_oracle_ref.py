@@ -71,6 +71,20 @@ def test_igm_golden_agrees_with_reference_iterative_rounding(name):
     assert np.array_equal(np.round(fx[g["integerIdcs"]]), np.round(g["fullx"][g["integerIdcs"]]))
 
 
+@pytest.mark.parametrize("name", CASES)
+def test_igm_golden_agrees_with_reference_example_igm_end_to_end(name):
+    """example/example_igm.cpp:14-33 run by the reference's code from (V, F, u0, seam): Hmesh, FaceRosyField, computeMatching, compute_cut_mesh,
+    compute_combbed_field, compute_extrinsic_field, RosyParameterization (constructor, setup(), integ()). Only compute_seam (libigl's cut graph +
+    Dijkstra) is not the reference's: the seam comes from the host glue. Cut mesh, index lists and fullx2Nfunc are the host glue's bit for bit;
+    fullx is the golden's (the inputs now differ by the 1e-14 between the two field solves, amplified by the 1e10 penalty rows)."""
+    g, r = load_golden(name), _ref(name)
+    assert int(r["ex_integ_ok"]) == 1 and int(r["ex_cut_identical"]) == 1 and int(r["ex_indices_identical"]) == 1
+    assert float(r["ex_fullx2Nfunc_max_abs_diff"]) == 0.0
+    fx = r["ex_fullx"]
+    assert np.array_equal(np.round(fx[g["out_fixedIdcs"]]).astype(np.int64), g["out_fixedVals"])
+    assert np.abs(fx - g["fullx"]).max() <= 1e-6
+
+
 @pytest.mark.parametrize("name", ("sphere_ico3", "torus_24x16"))
 def test_barrier_golden_agrees_with_reference(name):
     gb, r = np.load(os.path.join(GOLDEN, name + "_barrier.npz")), _ref(name)
@@ -100,6 +114,14 @@ def test_reference_icosphere_golden_agrees_with_reference_code():
     assert 0 <= int(r["factorizations"]) - 1 - int(g["lm_factorizations"]) <= 1
     assert np.abs(r["fullx_qgp"] - r["fullx_qgp_oracle"]).max() <= 1e-9
     assert int(r["factorizations_qgp"]) == int(r["lm_factorizations_qgp_oracle"]) + 1 and int(r["iter_cb_calls_qgp"]) == 1
+    # both example programs END TO END by the reference's code on its own asset (README.md:38: `metriko_example ../models/icosphere.obj 0.03`):
+    # example_igm (curl matching, seamless, !roundSeams) against the oracle golden; example_qgp (principal matching, seamless = false,
+    # localInjectivity = true, roundSeams left at its default) against host glue + oracle on the same inputs
+    assert int(r["ex_igm_ok"]) == 1 and int(r["ex_qgp_ok"]) == 1
+    ex = r["ex_igm_fullx"]
+    assert np.array_equal(np.round(ex[g["out_fixedIdcs"]]).astype(np.int64), g["out_fixedVals"])
+    assert np.abs(ex[g["fullx_idx"]] - g["fullx_val"]).max() <= 1e-8
+    assert np.abs(r["ex_qgp_fullx"] - r["ex_qgp_fullx_oracle"]).max() <= 1e-9 and float(r["ex_qgp_cfn_max_abs_diff"]) <= 1e-9
 
 
 # ---------------------------------------------------------------- live: needs /root/reference (this container); skipped on the GPU box
@@ -177,6 +199,39 @@ def test_live_face_rosy_field(R, mesh, matching):
     ext = f.real[:, :, None] * X[:, None, :] + f.imag[:, :, None] * Y[:, None, :]  # frf.h:251-264
     ext /= np.linalg.norm(ext, axis=2, keepdims=True)
     assert np.abs(r["ext"] - ext.reshape(-1)).max() <= 1e-14
+
+
+@pytest.mark.parametrize("mesh", ("sphere", "torus"))
+def test_live_example_igm_end_to_end(R, mesh):
+    """The whole example_igm.cpp pipeline by the reference's code against host glue (setup) + oracle (solves) on meshes no fixture holds:
+    genus 0 and genus 1 (seam loops with translation dofs)."""
+    from hostglue import Session
+    s = Session().make_sphere(8, 2, bump=0.12, phase=0.3) if mesh == "sphere" else Session().make_torus(18, 12, bump=0.1, phase=0.9)
+    fi = s.field_inputs()
+    nF = s.dims["nF"]
+    u0 = oracle.random_u0(nF, 3)
+    L = oracle.connection_laplacian(fi["twin"], fi["face"], fi["heArgOnFace"], nF, 4)
+    z = oracle.solve_smallest_eig(L, oracle.galerkin_mass_matrix(fi["faceArea"]), u0, 50)
+    s.field_post(z, 4, "curl")
+    s.igm_setup(0.02)
+    inp, m = s.igm_inputs(), s.igm_mesh_inputs()
+    o = oracle.iterative_rounding(inp["fixedIdcs"], inp["fixedVals"], inp["singularIdcs"], inp["integerIdcs"], inp["length"], inp["UFull"], inp["G2p"],
+                                  inp["N"], inp["n"], inp["nF"], True, False, inp["F2"], ni_mode="lm")
+    fin = s.igm_finish(o["fullx"])
+    r = R.face_rosy_field(s.get("pos"), s.get("idx"), 4, u0, "curl", seam=s.get("seam"),
+                          parameterize=dict(gridscale=0.02, seamless=True, localInjectivity=False, roundSeams=False))
+    assert r["integ_ok"] == 1 and o["success"]
+    assert np.array_equal(r["cutF"], m["cutF"].reshape(-1)) and np.array_equal(r["cutPos"], m["cutPos"].reshape(-1))      # param.h:126-152
+    for k in ("fixedIdcs", "integerIdcs", "singularIdcs"):                                                             # setup.ipp:143-168
+        assert np.array_equal(r[k], inp[k]), k
+    V2C = sp.csr_matrix((r["vtrans2cut_vals"], (r["vtrans2cut_rows"], r["vtrans2cut_cols"])), shape=tuple(r["vtrans2cut_shape"]))
+    UNC = sp.csr_matrix((r["uncompress_vals"], (r["uncompress_rows"], r["uncompress_cols"])), shape=tuple(r["uncompress_shape"]))
+    assert abs(V2C @ UNC - m["fullx2Nfunc"]).max() == 0.0                                                              # setup.ipp:52-141, integ.ipp:4
+    assert np.abs(r["cext"] - s.get("ext")).max() <= 1e-12                                                              # frf.h:251-264 on the combed field
+    idx, val = np.asarray(o["fixedIdcs"]), np.asarray(o["fixedVals"])
+    assert np.array_equal(np.round(r["fullx"][idx]).astype(np.int64), val)
+    assert np.abs(r["fullx"] - o["fullx"]).max() <= 1e-6
+    assert np.abs(r["nfn"] - fin["nfn"].reshape(-1)).max() <= 1e-6 and np.abs(r["cfn"] - fin["cfn"].reshape(-1)).max() <= 1e-6  # integ.ipp:88-98
 
 
 def test_live_inverse_iteration(R, small_sphere):
