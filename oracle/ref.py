@@ -1,5 +1,5 @@
-"""ctypes binding of oracle/_ref/libmetriko_ref.so: the reference's OWN headers (iter_rounding*.h, levenberg_marquardt.h,
-injective_barrier.h, sparse_linear_solver.h -- included in place from /root/reference) compiled against the Eigen / libigl stand-ins of
+"""ctypes binding of oracle/_ref/libmetriko_ref.so: the reference's OWN headers (hmesh.h, face_rosy_field.h, parameterization.h,
+iter_rounding*.h, levenberg_marquardt.h, injective_barrier.h, sparse_linear_solver.h -- included in place from /root/reference) compiled against the Eigen / libigl stand-ins of
 oracle/ref_shim/ by oracle/Makefile. TEST INFRASTRUCTURE like the rest of oracle/: only tests/ (and the fixture generator
 tests/golden/make_golden_ref.py) import this module. /root/reference does not exist on the GPU box and the library is built from it, so
 everything here is used in this container only; what travels are the fixtures tests/golden/ref_*.npz it produced.
@@ -155,9 +155,9 @@ class Ref:
             "singular", "cmatching", "dims", "L_rows", "L_cols", "M_rows", "cutF", "fixedIdcs", "integerIdcs", "singularIdcs", "he2matching", "he2transidx",
             "vtrans2cut_shape", "vtrans2cut_rows", "vtrans2cut_cols", "uncompress_shape", "uncompress_rows", "uncompress_cols", "constraint_shape",
             "constraint_rows", "constraint_cols")
-    _CPLX = ("L_vals", "M_vals", "compressed", "field", "connection", "cfield")
+    _CPLX = ("L_vals", "M_vals", "compressed", "field", "connection", "cfield", "principalCurvatureDir")
 
-    def face_rosy_field(self, V, F, N, u0, matching="curl", seam=None, names=None, parameterize=None):
+    def face_rosy_field(self, V, F, N, u0, matching="curl", seam=None, names=None, parameterize=None, field_type="smoothest"):
         """Hmesh(V, F) (hmesh.h:313-569) + FaceRosyField(mesh, N, Smoothest) (frf.h:17-44) + computeMatching (frf.h:100-202) [+ the combed field
         (frf.h:207-249) when a seam is given] run by the reference's own code; returns the requested arrays (default: all).
         parameterize = dict(gridscale, seamless, localInjectivity, roundSeams): the rest of example_igm.cpp:17-33 as well (compute_cut_mesh,
@@ -166,12 +166,12 @@ class Ref:
         F = np.ascontiguousarray(F, np.int32).reshape(-1, 3)
         u0 = np.ascontiguousarray(u0, np.complex128)
         assert u0.size == F.shape[0]
-        self.L.ref_field_create.restype = C.c_void_p
+        self.L.ref_field_create2.restype = C.c_void_p
         self.L.ref_field_get.restype = C.c_long
         sm = None if seam is None else np.ascontiguousarray(seam, np.int32)
-        h = C.c_void_p(self.L.ref_field_create(int(V.shape[0]), _dp(V.reshape(-1)), int(F.shape[0]), _ip(F.reshape(-1)), int(N),
-                                               _dp(u0.view(np.float64)), 1 if matching == "curl" else 0,
-                                               _ip(sm) if sm is not None else C.POINTER(C.c_int)()))
+        h = C.c_void_p(self.L.ref_field_create2(int(V.shape[0]), _dp(V.reshape(-1)), int(F.shape[0]), _ip(F.reshape(-1)), int(N),
+                                                _dp(u0.view(np.float64)), 1 if matching == "curl" else 0,
+                                                _ip(sm) if sm is not None else C.POINTER(C.c_int)(), 2 if field_type == "curvature" else 1))
         all_names = ("dims", "twin", "next", "prev", "face", "tail", "head", "edge", "crnr", "face2half", "vert2half", "heArgOnFace", "faceArea",
                      "angleDefect", "dihedralArg", "heLen", "faceBasisX", "faceBasisY", "faceNormal", "edge2face", "edge2vert", "face2edge", "L_rows",
                      "L_cols", "L_vals", "M_rows", "M_vals", "compressed", "field", "connection", "matching", "singular", "ext") + \

@@ -167,7 +167,12 @@ struct RefField {
 
 // V[3 nV] and F[3 nF] row-major. u0: 2 nF doubles for VecXc::Random. matching_type 0 = Principal, 1 = Curl. seam[nE] (0 / 1) or null: with a
 // seam the combed field (compute_combbed_field) is computed as well.
+// field_type 1 = FieldType::Smoothest, 2 = FieldType::CurvatureAligned (frf.h:25-33: principalCurvatureDir frf.h:86-98, solveSquare sls.h:16-27).
+void* ref_field_create2(int nV, const double* V, int nF, const int* F, int N, const double* u0, int matching_type, const int* seam, int field_type);
 void* ref_field_create(int nV, const double* V, int nF, const int* F, int N, const double* u0, int matching_type, const int* seam) {
+    return ref_field_create2(nV, V, nF, F, N, u0, matching_type, seam, 1);
+}
+void* ref_field_create2(int nV, const double* V, int nF, const int* F, int N, const double* u0, int matching_type, const int* seam, int field_type) {
     MatXd Vm(nV, 3);
     MatXi Fm(nF, 3);
     for (int i = 0; i < nV; i++) for (int j = 0; j < 3; j++) Vm(i, j) = V[3 * i + j];
@@ -176,7 +181,7 @@ void* ref_field_create(int nV, const double* V, int nF, const int* F, int N, con
     r->mesh = std::make_unique<Hmesh>(Vm, Fm);
     refshim::random_source = u0;
     refshim::random_pos = 0;
-    r->field = std::make_unique<FaceRosyField>(*r->mesh, N, FieldType::Smoothest);
+    r->field = std::make_unique<FaceRosyField>(*r->mesh, N, field_type == 2 ? FieldType::CurvatureAligned : FieldType::Smoothest);
     refshim::random_source = nullptr;
     r->L = r->field->connectionLaplacian();
     r->M = r->field->galerkinMassMatrix();
@@ -258,6 +263,7 @@ long ref_field_get(void* h, const char* name, long cap, double* out) {
     else if (k == "M_rows") coo(r.M, 0);
     else if (k == "M_vals") coo(r.M, 2);
     else if (k == "compressed") vecc(r.field->compressed);
+    else if (k == "principalCurvatureDir") vecc(r.field->principalCurvatureDir());
     else if (k == "field") matc(r.field->field);
     else if (k == "connection") vecc(r.field->connection);
     else if (k == "matching") veci(r.field->matching);

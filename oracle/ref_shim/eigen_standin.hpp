@@ -1,10 +1,11 @@
 // eigen_standin.hpp -- TEST INFRASTRUCTURE (oracle/): a stand-in for the slice of Eigen's public API that the reference's own headers
-//   include/metriko/core/igm/iterative_rounding/{iter_rounding.h, iter_rounding_init.h, iter_rounding_loop.h, iter_rounding_common.h,
+//   include/metriko/core/hmesh/hmesh.h, vectorfield/{base_field.h, face_rosy_field.h}, igm/{parameterization.h, parameterization_setup.ipp,
+//   parameterization_integ.ipp}, igm/iterative_rounding/{iter_rounding.h, iter_rounding_init.h, iter_rounding_loop.h, iter_rounding_common.h,
 //   injective_barrier.h}, solver/{levenberg_marquardt.h, matrix_ops.h, sparse_linear_solver.h}, common/typedef.h
 // touch, so that THOSE FILES THEMSELVES (included in place from /root/reference, never copied) go through g++ and run in this image, which
 // has no Eigen. oracle/Makefile builds oracle/_ref/libmetriko_ref.so from oracle/ref_harness.cpp with this directory
-// in front of the include path; tests/test_oracle_ref.py pins the numpy restatement (oracle/igm.py, oracle/barrier.py, oracle/field.py)
-// against what the reference's code computes.
+// in front of the include path; tests/test_oracle_ref.py pins the numpy restatement (oracle/igm.py, oracle/barrier.py, oracle/field.py) and
+// the host glue (tests/hostglue) against what the reference's code computes.
 //
 // What is NOT Eigen here, and therefore what the pin does not cover:
 //   * everything is evaluated eagerly (no expression templates): same values, same operation order per coefficient for the operations

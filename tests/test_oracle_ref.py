@@ -1,6 +1,7 @@
 """The oracle pinned against the REFERENCE'S OWN CODE.
 
-tests/golden/ref_<name>.npz hold what metriko's own headers compute (iter_rounding.h:33-113 with everything below it, sls.h:29-54),
+tests/golden/ref_<name>.npz hold what metriko's own headers compute (example_igm.cpp:14-33 / example_qgp.cpp:18-31 end to end: hmesh.h,
+face_rosy_field.h, parameterization.h, iter_rounding.h:33-113 with everything below it, sls.h:16-54),
 compiled in place from /root/reference against the Eigen / libigl stand-ins of oracle/ref_shim/ (oracle/Makefile, oracle/ref_harness.cpp,
 generator tests/golden/make_golden_ref.py). The first group of tests runs everywhere and ties the committed oracle goldens -- the vectors
 the CUDA path is compared with on the GPU box -- to those outputs. The second group runs where the reference's sources are (this container):
@@ -232,6 +233,24 @@ def test_live_example_igm_end_to_end(R, mesh):
     assert np.array_equal(np.round(r["fullx"][idx]).astype(np.int64), val)
     assert np.abs(r["fullx"] - o["fullx"]).max() <= 1e-6
     assert np.abs(r["nfn"] - fin["nfn"].reshape(-1)).max() <= 1e-6 and np.abs(r["cfn"] - fin["cfn"].reshape(-1)).max() <= 1e-6  # integ.ipp:88-98
+
+
+@pytest.mark.parametrize("N", (4, 2))
+def test_live_curvature_aligned_field(R, N):
+    """FieldType::CurvatureAligned (frf.h:25-33): principalCurvatureDir (frf.h:86-98), squared for N = 4, rhs = M D / sqrt|D^H M D|,
+    solveSquare(L - 0 M, rhs) (sls.h:16-27), decode -- the reference's code against oracle.principal_curvature_dir / curvature_aligned."""
+    from hostglue import Session
+    s = Session().make_torus(20, 14, bump=0.12, phase=0.4)
+    fi, ci = s.field_inputs(), s.curvature_inputs()
+    nF = s.dims["nF"]
+    r = R.face_rosy_field(s.get("pos"), s.get("idx"), N, np.zeros(nF, np.complex128), "curl", field_type="curvature",
+                          names=("principalCurvatureDir", "compressed", "field"))
+    D = oracle.principal_curvature_dir(fi["face2half"], fi["next"], fi["heArgOnFace"], ci["heLen"], ci["dihedralArg"])
+    assert np.abs(r["principalCurvatureDir"] - D).max() <= 1e-13 * np.abs(D).max()
+    L = oracle.connection_laplacian(fi["twin"], fi["face"], fi["heArgOnFace"], nF, N)
+    x, _ = oracle.curvature_aligned(L, oracle.galerkin_mass_matrix(fi["faceArea"]), D, N)
+    assert np.abs(r["compressed"] - x).max() <= 1e-10 * np.abs(x).max()
+    assert np.abs(r["field"].reshape(nF, N) - oracle.decode_field(x, N)).max() <= 1e-9
 
 
 def test_live_inverse_iteration(R, small_sphere):
