@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import oracle
-from conftest import load_golden
+from conftest import assert_field_matches_reference_code, load_golden
 from metriko_b200 import api
 from hostglue import Session
 from oracle.field import field_angle_error
@@ -43,6 +43,7 @@ def test_field_matches_golden(ctx, name, precond, recycle):
     F = _mk(ctx, g)
     z = F.solveSmallestEig(g["u0"], 50, precond=precond, recycle=recycle)
     assert field_angle_error(z, g["z50"], 4).max() < ANGLE_TOL
+    assert_field_matches_reference_code(name, z, ANGLE_TOL)   # the reference's own FaceRosyField from (V, F, u0): tests/golden/ref_<name>.npz
     assert F.stats["relres_max"] <= 1e-10 * 1.001 and F.stats["status"] == 0
     assert abs(F.stats["lambda_"] - float(g["lam"])) < 1e-6
     nF = len(z)

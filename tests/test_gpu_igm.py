@@ -7,7 +7,7 @@ import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
 import oracle
-from conftest import load_golden
+from conftest import assert_rounding_matches_reference_code, load_golden
 from metriko_b200 import api
 from hostglue import Session
 
@@ -32,6 +32,9 @@ def test_rounding_matches_golden(ctx, name, precond):
     assert _ints(out) == dict(zip(g["out_fixedIdcs"].tolist(), g["out_fixedVals"].tolist()))   # bit-exact integers
     assert out["n_solves"] == int(g["n_solves"])
     assert np.abs(out["fullx"] - g["fullx"]).max() < 1e-6
+    # ... and against what the REFERENCE'S OWN CODE computed (oracle/_ref -> tests/golden/ref_<name>.npz): iterative_rounding on these inputs and the
+    # whole example_igm.cpp pipeline from the mesh
+    assert_rounding_matches_reference_code(name, out["fixedIdcs"], out["fixedVals"], out["fullx"])
     assert not any(f & 1 for f in out["tie_flags"])                         # no rounding near-ties in the fixtures
     fx = out["fullx"][np.asarray(out["fixedIdcs"])]
     assert np.abs(fx - np.round(fx)).max() <= 10e-7                         # post_checking

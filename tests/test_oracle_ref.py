@@ -15,7 +15,7 @@ import scipy.sparse as sp
 import oracle
 from oracle import ref as oref
 from oracle.barrier import InjectiveBarrier
-from conftest import GOLDEN, load_golden
+from conftest import GOLDEN, assert_field_matches_reference_code, assert_rounding_matches_reference_code, load_golden
 
 CASES = ("sphere_ico3", "torus_24x16", "sphere_octa4_roundseams")
 
@@ -84,6 +84,19 @@ def test_igm_golden_agrees_with_reference_example_igm_end_to_end(name):
     fx = r["ex_fullx"]
     assert np.array_equal(np.round(fx[g["out_fixedIdcs"]]).astype(np.int64), g["out_fixedVals"])
     assert np.abs(fx - g["fullx"]).max() <= 1e-6
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_gpu_side_checks_against_the_reference_fixtures(name):
+    """The two assertions tests/test_gpu_field.py / tests/test_gpu_igm.py make on the DEVICE results against the reference code's fixtures, run here
+    on the oracle golden's values: the helpers work and the oracle passes them with margin (1e-12 rad, 5e-8)."""
+    g = load_golden(name)
+    assert_field_matches_reference_code(name, g["z50"], 1e-10)
+    assert_rounding_matches_reference_code(name, g["out_fixedIdcs"].tolist(), g["out_fixedVals"].tolist(), g["fullx"], tol=1e-7)
+    with pytest.raises(AssertionError):
+        assert_rounding_matches_reference_code(name, g["out_fixedIdcs"].tolist(), (g["out_fixedVals"] + 1).tolist(), g["fullx"])
+    with pytest.raises(AssertionError):
+        assert_field_matches_reference_code(name, g["z50"] * np.exp(1j * 4e-5 * np.arange(len(g["z50"])) / len(g["z50"])), 1e-6)
 
 
 @pytest.mark.parametrize("name", ("sphere_ico3", "torus_24x16"))
