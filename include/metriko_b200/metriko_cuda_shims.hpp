@@ -15,6 +15,7 @@
 #pragma once
 #include <complex>
 #include <cstdio>
+#include <functional>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -175,6 +176,17 @@ inline bool iterative_rounding(const VecXi& fixedIdcs, const VecXd& fixedVals, c
                        ov.data(), &nfix, rf.data(), tf.data(), nullptr);
     mk_igm_destroy(g);
     return rc == MK_OK;  // MK_ERR_ROUNDING <-> "Rounding has failed!" (parameterization_integ.ipp:85)
+}
+
+// The reference's EXACT argument list (iter_rounding.h:33-51), so that the call in parameterization_integ.ipp:65-83 compiles unchanged against the
+// overlay (a one-word edit there, or `#define iterative_rounding cuda::iterative_rounding` around the include: tests/cpp/ref_overlay_test.cpp
+// compiles the reference's own headers that way). iter_cb is accepted and not called (see above).
+inline bool iterative_rounding(const VecXi& fixedIdcs, const VecXd& fixedVals, const VecXi& singularIdcs, const VecXi& integerIdcs,
+                               const double length, const SprsD& Cfull, const SprsD& G2, const int N, const int n, const int nF,
+                               const bool seamless, const bool roundSeams, const bool localInjectivity, const bool verbose,
+                               const VecXd& intrinsicField, const std::function<bool(const VecXd&)>& /*iter_cb*/, VecXd& fullx) {
+    return iterative_rounding(fixedIdcs, fixedVals, singularIdcs, integerIdcs, length, Cfull, G2, N, n, nF, seamless, roundSeams, localInjectivity,
+                              verbose, intrinsicField, fullx, Context::thread_default());
 }
 #endif  // METRIKO_B200_SHIM_NO_B4
 

@@ -31,6 +31,8 @@ def build() -> bool:
     """make -C oracle (needs the reference's sources); True when the library exists afterwards."""
     if os.path.isdir(os.path.join(REFERENCE, "include", "metriko")):
         subprocess.run(["make", "-C", _HERE, f"REF={REFERENCE}"], check=True, capture_output=True)
+        if os.path.exists(os.path.join(_HERE, "..", "metriko_b200", "libmetriko_b200.so")):
+            subprocess.run(["make", "-C", _HERE, f"REF={REFERENCE}", "overlay"], check=False, capture_output=True)  # optional: needs a GPU to run
     return os.path.exists(LIB_PATH)
 
 

@@ -578,6 +578,33 @@ private:
     std::vector<T> val_;
 };
 
+// row-major copy of a column-major matrix (`Eigen::SparseMatrix<double, Eigen::RowMajor> R = A;`): only what a CSR export needs
+template <class T>
+class SparseMatrix<T, RowMajor> {
+public:
+    using Scalar = T;
+    SparseMatrix() : outer_(1, 0) {}
+    SparseMatrix(const SparseMatrix<T, ColMajor>& A) {
+        const SparseMatrix<T, ColMajor> At = A.transpose();  // CSC of A^T = CSR of A
+        rows_ = (int)A.rows();
+        cols_ = (int)A.cols();
+        outer_.assign(At.outerIndexPtr(), At.outerIndexPtr() + rows_ + 1);
+        inner_.assign(At.innerIndexPtr(), At.innerIndexPtr() + At.nonZeros());
+        val_.assign(At.valuePtr(), At.valuePtr() + At.nonZeros());
+    }
+    long rows() const { return rows_; }
+    long cols() const { return cols_; }
+    long nonZeros() const { return (long)inner_.size(); }
+    void makeCompressed() {}
+    const int* outerIndexPtr() const { return outer_.data(); }
+    const int* innerIndexPtr() const { return inner_.data(); }
+    const T* valuePtr() const { return val_.data(); }
+private:
+    int rows_ = 0, cols_ = 0;
+    std::vector<int> outer_, inner_;
+    std::vector<T> val_;
+};
+
 // ---- direct solvers: hooks (see the header comment) ----
 template <class M, int KIND>
 class HookedSolver {

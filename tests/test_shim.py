@@ -144,3 +144,42 @@ def test_shim_b4_iterative_rounding_on_gpu(tmp_path):
     assert np.abs(fullx - ref["fullx"]).max() < 1e-6
     for i, v in zip(ref["fixedIdcs"], ref["fixedVals"]):
         assert abs(fullx[i] - v) < 1e-7
+
+
+# ---- the overlay against the reference's OWN headers (needs /root/reference: this container) ----
+REFERENCE = os.environ.get("METRIKO_REFERENCE", "/root/reference")
+
+
+def test_overlay_compiles_against_the_reference_headers_and_fails_loudly_without_gpu(tmp_path):
+    """tests/cpp/ref_overlay_test.cpp: metriko's own face_rosy_field.h and parameterization.h (included in place, Eigen / libigl = oracle/ref_shim)
+    with their two solver call sites -- solveSmallestEig at frf.h:22, iterative_rounding at integ.ipp:65 -- redirected to the overlay by the
+    preprocessor, i.e. the two edits of INTEGRATION.md without touching the reference. Compile, link against libmetriko_b200.so, check that the
+    C-ABI calls are really what the reference's code now reaches, and that example_igm's pipeline fails loudly (no CPU fallback) without a device."""
+    import ctypes as C
+    import torch
+    if not os.path.isdir(os.path.join(REFERENCE, "include", "metriko")):
+        pytest.skip("reference sources not present")
+    from metriko_b200 import build
+    build.build_cuda()
+    libdir = os.path.join(ROOT, "metriko_b200")
+    so = str(tmp_path / "libref_overlay.so")
+    subprocess.run(["g++", "-std=c++20", "-O1", "-w", "-fPIC", "-shared", "-I", os.path.join(ROOT, "oracle", "ref_shim"), "-I", os.path.join(REFERENCE, "include"),
+                    "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "ref_overlay_test.cpp"), "-o", so, "-L", libdir,
+                    "-lmetriko_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    undefined = subprocess.run(["nm", "-D", "--undefined-only", so], capture_output=True, text=True, check=True).stdout
+    for sym in ("mk_solve_smallest_eig_csc", "mk_igm_create", "mk_igm_round", "mk_igm_round_injective"):
+        assert sym in undefined, sym
+    if torch.cuda.is_available():
+        return  # running it is tests/test_gpu_*'s business; here only the build and the no-device behaviour
+    from hostglue import Session
+    s = Session().make_sphere(20, 1, bump=0.08)
+    nF = s.dims["nF"]
+    V, F = np.ascontiguousarray(s.get("pos"), np.float64), np.ascontiguousarray(s.get("idx"), np.int32)
+    u0 = np.ascontiguousarray(np.random.default_rng(0).uniform(-1, 1, 2 * nF))
+    seam = np.zeros(s.dims["nE"], np.int32)
+    fullx, flen = np.zeros(8), C.c_long(0)
+    lib = C.CDLL(so)
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    rc = lib.ref_overlay_example_igm(int(s.dims["nV"]), V.ctypes.data_as(dp), int(nF), F.ctypes.data_as(ip), 4, u0.ctypes.data_as(dp),
+                                     seam.ctypes.data_as(ip), C.c_double(0.02), 1, 0, 0, C.c_long(8), fullx.ctypes.data_as(dp), C.byref(flen), dp())
+    assert rc == -1  # the overlay's Context threw "no usable sm_100a device" inside the reference's FaceRosyField constructor
