@@ -8,7 +8,8 @@
 // are included FIRST (their definitions keep their names), then the names are #defined to the overlay's while face_rosy_field.h and
 // parameterization.h -- the callers -- are read. What comes out is example/example_igm.cpp:14-33 with both solver seams on the B200.
 // tests/test_shim.py builds this file into a shared library on the CPU (compile + link against libmetriko_b200.so + symbol check); running it needs
-// a GPU: ref_overlay_example_igm is the entry a GPU box would call (scripts/run_ref_overlay.py).
+// a GPU: scripts/run_ref_overlay.py calls ref_overlay_example_igm on the reference's icosphere.obj (round 2, B200: integ() true, integers identical
+// to the oracle golden, fullx within 7.2e-9 of the golden and of the reference's own CPU run; profiles/overlay_r02_reference_example_igm_on_b200.log).
 #include "metriko/core/solver/sparse_linear_solver.h"
 #include "metriko/core/igm/iterative_rounding/iter_rounding.h"
 
