@@ -1,7 +1,8 @@
 """Golden vectors of the localInjectivity (barrier) path of the oracle, derived from the committed fixtures:
     python tests/golden/make_golden_barrier.py      ->  tests/golden/<name>_barrier.npz
-The reference ships no fixtures for this path (parity unpinned); these pin the oracle's restatement (oracle/barrier.py, oracle/igm.py)
-so that the CUDA barrier path of the next round has a fixed target that travels to the GPU box."""
+The reference ships no fixtures for this path; these pin the oracle's restatement (oracle/barrier.py, oracle/igm.py) so that the CUDA barrier
+path has a fixed target that travels to the GPU box. tests/test_oracle_ref.py::test_barrier_golden_agrees_with_reference ties them to the
+reference's own injective_barrier.h / LM code compiled in place (oracle/_ref): fullx within 4e-13 / 3e-12, the same number of factorisations."""
 import os
 import sys
 
