@@ -1,8 +1,9 @@
 """One-off: the oracle/_ref pin (the reference's own example_igm.cpp pipeline compiled against the Eigen stand-ins) at a size between the unit
 fixtures (<= 5k faces) and the BASELINE configurations: an octahedron subdivided `levels` times (6: 32,768 faces). Prints the agreement of the
-reference's code with host glue + oracle; too slow for the test suite (the reference's LM re-factorises without reuse).
+reference's code with host glue + oracle; too slow for the test suite (the reference's LM re-factorises without reuse). Round 2: levels 5 and 6
+were stopped after 27 / 47 CPU-minutes (profiles/README.md); the committed pin ends at the 5,120 faces of icosphere.obj.
 
-    python tests/tools/ref_pin_midsize.py [levels]  >  profiles/ref_pin_r02_octa<levels>.txt
+    python tests/tools/ref_pin_midsize.py [levels]  
 """
 import os
 import sys
